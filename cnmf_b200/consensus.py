@@ -1,0 +1,211 @@
+"""Host orchestration of the consensus stage (cnmf.py:871-975) over the CUDA kernels.
+
+What runs where
+  * GPU (libcnmf_b200.so): L2 normalisation, all-pairs distances, k-NN local density, the Lloyd
+    E+M steps, k-means++ candidate distances, per-cluster medians, the three NNLS refits and the
+    OLS projection GEMM.
+  * Host (numpy, O(R) or O(K*G) work only): the k-means++ random draws (they must consume the
+    legacy RandomState(1) stream exactly like sklearn/cluster/_kmeans.py:231-262), centre averaging,
+    the K x K least-squares solve, bookkeeping.
+
+torch is used purely as the device-memory container (allocation + memcpy); no torch op touches
+the data.  There is no CPU fallback: without the CUDA library / a GPU this module raises.
+"""
+import ctypes
+
+import numpy as np
+
+from ._lib import check, ptr
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("cnmf_b200.consensus needs a CUDA device (no CPU fallback)")
+    return torch
+
+
+class SpectraMatrix:
+    """R x G fp32 matrix on the device (row stride ld = G padded to 32)."""
+
+    def __init__(self, engine, array=None, shape=None):
+        torch = _torch()
+        self.engine = engine
+        self.lib = engine.lib
+        if array is not None:
+            array = np.ascontiguousarray(array, dtype=np.float32)
+            shape = array.shape
+        self.R, self.G = int(shape[0]), int(shape[1])
+        self.ld = (self.G + 31) // 32 * 32
+        self.t = torch.zeros((self.R, self.ld), dtype=torch.float32, device="cuda:%d" % engine.device)
+        if array is not None:
+            self.t[:, :self.G].copy_(torch.from_numpy(array))     # H2D memcpy
+
+    @property
+    def p(self):
+        return ctypes.c_void_p(self.t.data_ptr())
+
+    def numpy(self):
+        return self.t[:, :self.G].cpu().numpy()
+
+    def l2_normalize(self):
+        check(self.lib.cnmf_l2_normalize_rows(self.engine._h, self.p, self.R, self.G, self.ld, None))
+        return self
+
+    def local_density(self, n_neighbors, return_dist=False):
+        torch = _torch()
+        dens = torch.empty(self.R, dtype=torch.float32, device=self.t.device)
+        D = torch.empty((self.R, self.R), dtype=torch.float32, device=self.t.device) if return_dist else None
+        check(self.lib.cnmf_local_density(self.engine._h, self.p, self.R, self.G, self.ld, int(n_neighbors),
+                                          ctypes.c_void_p(dens.data_ptr()),
+                                          ctypes.c_void_p(D.data_ptr()) if D is not None else None, None))
+        torch.cuda.synchronize(self.t.device)
+        return dens.cpu().numpy().astype(np.float64), (D.cpu().numpy() if D is not None else None)
+
+    def take_rows(self, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        out = SpectraMatrix(self.engine, shape=(len(idx), self.G))
+        check(self.lib.cnmf_gather_rows(self.engine._h, self.p, self.ld, ptr(idx), len(idx), self.G, out.p, out.ld, None))
+        return out
+
+    def sq_dists_to_rows(self, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        out = np.empty((len(idx), self.R), np.float32)
+        check(self.lib.cnmf_sq_dists_to_rows(self.engine._h, self.p, self.R, self.G, self.ld, ptr(idx), len(idx),
+                                             ptr(out), None))
+        return out.astype(np.float64)
+
+
+# ------------------------------------------------------------------------------ KMeans
+def _kmeans_plusplus(S, k, rng):
+    """sklearn/cluster/_kmeans.py:180-278 with unit weights; distances from the GPU, draws on the host."""
+    n = S.R
+    n_local_trials = 2 + int(np.log(k))
+    w = np.ones(n)
+    center_id = rng.choice(n, p=w / w.sum())
+    indices = [int(center_id)]
+    closest = S.sq_dists_to_rows([center_id])          # (1, n)
+    pot = closest @ w
+    for _ in range(1, k):
+        rand_vals = rng.uniform(size=n_local_trials) * pot
+        cand = np.searchsorted(np.cumsum(w * closest), rand_vals)
+        np.clip(cand, None, closest.size - 1, out=cand)
+        d = S.sq_dists_to_rows(cand)
+        np.minimum(closest, d, out=d)
+        cpot = d @ w.reshape(-1, 1)
+        best = int(np.argmin(cpot))
+        pot = cpot[best]
+        closest = d[best][None, :]
+        indices.append(int(cand[best]))
+    return np.array(indices, dtype=np.int32)
+
+
+def _same_clustering(l1, l2, k):
+    mapping = np.full(k, -1, dtype=np.int64)
+    for a, b in zip(l1, l2):
+        if mapping[a] == -1:
+            mapping[a] = b
+        elif mapping[a] != b:
+            return False
+    return True
+
+
+def kmeans(S, k, n_init=10, random_state=1, max_iter=300, tol=1e-4):
+    """KMeans(n_clusters=k, n_init=10, random_state=1).fit(l2_spectra).labels_ (cnmf.py:908-910).
+    Returns (labels int32 numpy, labels device tensor, inertia, centers)."""
+    torch = _torch()
+    lib, h = S.lib, S.engine._h
+    rng = np.random.RandomState(random_state)
+    G, R = S.G, S.R
+    # tolerance: mean of the per-feature variances * tol (sklearn _kmeans.py:285-293)
+    host = S.numpy().astype(np.float64) if R * G <= (1 << 22) else None
+    if host is not None:
+        var_mean = float(np.mean(np.var(host, axis=0)))
+    else:
+        mean = np.empty(G)
+        var = np.empty(G)
+        check(lib.cnmf_col_stats_dev(h, S.p, R, G, S.ld, ptr(mean), ptr(var), None))
+        var_mean = float(var.mean())
+    tol_abs = var_mean * tol
+
+    labels_t = torch.empty(R, dtype=torch.int32, device=S.t.device)
+    mind_t = torch.empty(R, dtype=torch.float32, device=S.t.device)
+    sums = np.empty((k, G), np.float64)
+    counts = np.empty(k, np.int32)
+    n_changed = ctypes.c_int32(0)
+    inertia = ctypes.c_double(0)
+    best = None
+    for _ in range(n_init):
+        idx = _kmeans_plusplus(S, k, rng)
+        centers = S.take_rows(idx).numpy().astype(np.float64)
+        labels_t.fill_(-1)
+        strict = False
+        n_it = 0
+        for n_it in range(max_iter):
+            c32 = np.ascontiguousarray(centers, dtype=np.float32)
+            check(lib.cnmf_kmeans_assign(h, S.p, R, G, S.ld, ptr(c32), k, ctypes.c_void_p(labels_t.data_ptr()),
+                                         ptr(sums), ptr(counts), ctypes.c_void_p(mind_t.data_ptr()),
+                                         ctypes.byref(n_changed), None, None))
+            new = sums.copy()
+            weight = counts.astype(np.float64)
+            empty = np.where(weight == 0)[0]
+            if len(empty) > 0:                      # sklearn _k_means_common.pyx:167-211
+                dist = mind_t.cpu().numpy().astype(np.float64)
+                if dist.max() != 0:
+                    lab = labels_t.cpu().numpy()
+                    far = np.argpartition(dist, -len(empty))[: -len(empty) - 1: -1]
+                    rows = S.take_rows(far).numpy().astype(np.float64)
+                    for j, new_id in enumerate(empty):
+                        old_id = lab[far[j]]
+                        new[old_id] -= rows[j]
+                        new[new_id] = rows[j]
+                        weight[new_id] = 1
+                        weight[old_id] -= 1
+            amax = int(np.argmax(weight))
+            for j in range(k):                      # _average_centers, _k_means_common.pyx:274-298
+                if weight[j] > 0:
+                    new[j] *= 1.0 / weight[j]
+                else:
+                    new[j] = new[amax]
+            shift_tot = float(((new - centers) ** 2).sum())
+            centers = new
+            if n_changed.value == 0:
+                strict = True
+                break
+            if shift_tot <= tol_abs:
+                break
+        c32 = np.ascontiguousarray(centers, dtype=np.float32)
+        # final E step (labels consistent with the final centres) + inertia
+        check(lib.cnmf_kmeans_assign(h, S.p, R, G, S.ld, ptr(c32), k, ctypes.c_void_p(labels_t.data_ptr()),
+                                     None, None, ctypes.c_void_p(mind_t.data_ptr()), ctypes.byref(n_changed),
+                                     ctypes.byref(inertia), None))
+        labels = labels_t.cpu().numpy().copy()
+        if best is None or (inertia.value < best[1] and not _same_clustering(labels, best[0], k)):
+            best = (labels, float(inertia.value), centers.copy(), n_it + 1)
+    labels_t.copy_(torch.from_numpy(best[0]))
+    return best[0], labels_t, best[1], best[2]
+
+
+def cluster_medians(S, labels_t, k):
+    """cnmf.py:913-916 on the device; returns K x G float64 (rows sum to 1)."""
+    torch = _torch()
+    M = torch.empty((k, S.ld), dtype=torch.float32, device=S.t.device)
+    check(S.lib.cnmf_cluster_median(S.engine._h, S.p, S.R, S.G, S.ld, ctypes.c_void_p(labels_t.data_ptr()), k,
+                                    ctypes.c_void_p(M.data_ptr()), S.ld, None))
+    torch.cuda.synchronize(S.t.device)
+    return M[:, :S.G].cpu().numpy().astype(np.float64)
+
+
+def ols_zscore(usages, tpm_ds):
+    """efficient_ols_all_cols(rf_usages, tpm.X, normalize_y=True) (cnmf.py:55-125).
+    U^T Z with Z = (T - mean)/std equals (U - mean(U))^T T / std because the columns of T - mean sum to
+    zero; centring U instead of T keeps the GEMM free of catastrophic cancellation in fp32 accumulation."""
+    U = np.asarray(usages, dtype=np.float64)
+    mean, var = tpm_ds.col_stats()
+    var[var < 1e-12] = 1e-12
+    std = np.sqrt(var)
+    Uc = U - U.mean(axis=0)
+    UtZ = tpm_ds.project_rows(np.ascontiguousarray(Uc.T, dtype=np.float32)).astype(np.float64) / std
+    UtU = U.T @ U
+    beta, *_ = np.linalg.lstsq(UtU, UtZ, rcond=None)
+    return beta

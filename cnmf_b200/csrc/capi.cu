@@ -1,0 +1,389 @@
+// extern "C" entry points declared in include/cnmf_b200.h (handle, dataset, factorize, refit).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "engine.h"
+#include "gemm.h"
+#include "legacy_rng.h"
+#include "nmf_kernels.cuh"
+
+namespace cnmf {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+}  // namespace cnmf
+
+using namespace cnmf;
+
+#define CNMF_TRY(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != 0) return _rc;     \
+  } while (0)
+
+// ----------------------------------------------------------------------------- handle
+void* cnmf_handle_s::dev_buf(const std::string& name, size_t bytes) {
+  auto& e = ws[name];
+  if (e.second >= bytes && e.first) return e.first;
+  if (e.first) cudaFree(e.first);
+  e.first = nullptr;
+  e.second = 0;
+  const size_t want = std::max<size_t>(bytes, 256);
+  cudaError_t err = cudaMalloc(&e.first, want);
+  if (err != cudaSuccess) {
+    set_last_error("cudaMalloc(" + name + ", " + std::to_string(want) + " bytes) failed: " + cudaGetErrorString(err));
+    e.first = nullptr;
+    return nullptr;
+  }
+  e.second = want;
+  return e.first;
+}
+
+void* cnmf_handle_s::host_buf(const std::string& name, size_t bytes) {
+  auto& e = pinned[name];
+  if (e.second >= bytes && e.first) return e.first;
+  if (e.first) cudaFreeHost(e.first);
+  e.first = nullptr;
+  e.second = 0;
+  const size_t want = std::max<size_t>(bytes, 256);
+  cudaError_t err = cudaMallocHost(&e.first, want);
+  if (err != cudaSuccess) {
+    set_last_error("cudaMallocHost(" + name + ", " + std::to_string(want) + " bytes) failed: " + cudaGetErrorString(err));
+    e.first = nullptr;
+    return nullptr;
+  }
+  e.second = want;
+  return e.first;
+}
+
+void cnmf_handle_s::release_all() {
+  for (auto& kv : ws)
+    if (kv.second.first) cudaFree(kv.second.first);
+  ws.clear();
+  for (auto& kv : pinned)
+    if (kv.second.first) cudaFreeHost(kv.second.first);
+  pinned.clear();
+}
+
+extern "C" {
+
+int cnmf_abi_version(void) { return CNMF_B200_ABI_VERSION; }
+const char* cnmf_last_error(void) { return g_last_error.c_str(); }
+
+int cnmf_create(cnmf_handle_t* out, int device) {
+  CNMF_REQUIRE(out != nullptr, "cnmf_create: out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_last_error(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                   "); cnmf_b200 has no CPU fallback");
+    return -2;
+  }
+  CNMF_REQUIRE(device >= 0 && device < n, "cnmf_create: bad device index");
+  CNMF_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CNMF_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_last_error("cnmf_b200 is built for sm_100a only; device reports sm_" + std::to_string(prop.major) +
+                   std::to_string(prop.minor));
+    return -3;
+  }
+  auto* h = new cnmf_handle_s();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  *out = h;
+  return 0;
+}
+
+int cnmf_destroy(cnmf_handle_t h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  h->release_all();
+  delete h;
+  return 0;
+}
+
+long long cnmf_launch_count(cnmf_handle_t h) { return h ? h->launches : 0; }
+
+// ----------------------------------------------------------------------------- dataset
+static int dataset_alloc(cnmf_dataset_s* d, float** p, size_t elems) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(elems, 64) * sizeof(float));
+  if (e != cudaSuccess) {
+    set_last_error(std::string("dataset cudaMalloc failed: ") + cudaGetErrorString(e));
+    return -2;
+  }
+  d->owned.push_back(q);
+  *p = static_cast<float*>(q);
+  return 0;
+}
+
+// builds Xt / tf32 pieces / sums from d->X (already resident, padding zeroed)
+static int dataset_finish(cnmf_dataset_s* d, cudaStream_t s) {
+  cnmf_handle_s* h = d->h;
+  const size_t nx = (size_t)d->n_rows * d->ld_c, nxt = (size_t)d->n_cols * d->ld_r;
+  if (d->precision == CNMF_PRECISION_TF32X3) {
+    CNMF_TRY(dataset_alloc(d, &d->X_hi, nx));
+    CNMF_TRY(dataset_alloc(d, &d->X_lo, nx));
+    CNMF_TRY(dataset_alloc(d, &d->Xt_hi, nxt));
+    CNMF_TRY(dataset_alloc(d, &d->Xt_lo, nxt));
+    CNMF_CUDA_CHECK(cudaMemsetAsync(d->Xt_hi, 0, nxt * sizeof(float), s));
+    CNMF_CUDA_CHECK(cudaMemsetAsync(d->Xt_lo, 0, nxt * sizeof(float), s));
+    CNMF_TRY(launch_split_tf32(d->X, d->X_hi, d->X_lo, (long long)nx, s));
+    CNMF_TRY(launch_transpose(d->X, d->n_rows, d->n_cols, d->ld_c, nullptr, d->Xt_hi, d->Xt_lo, d->ld_r, s));
+    h->launches += 2;
+  } else {
+    CNMF_TRY(dataset_alloc(d, &d->Xt, nxt));
+    CNMF_CUDA_CHECK(cudaMemsetAsync(d->Xt, 0, nxt * sizeof(float), s));
+    CNMF_TRY(launch_transpose(d->X, d->n_rows, d->n_cols, d->ld_c, d->Xt, nullptr, nullptr, d->ld_r, s));
+    h->launches += 1;
+  }
+  const int scratch_len = 2 * 148 * 8 + 2;
+  double* scratch = static_cast<double*>(h->dev_buf("dataset.sums", sizeof(double) * (scratch_len + 2)));
+  if (!scratch) return -2;
+  CNMF_TRY(launch_matrix_sums(d->X, d->n_rows, d->n_cols, d->ld_c, scratch + scratch_len, scratch, scratch_len, s));
+  h->launches += 2;
+  double out2[2];
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(out2, scratch + scratch_len, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  d->sum = out2[0];
+  d->sum_sq = out2[1];
+  return 0;
+}
+
+int cnmf_dataset_create(cnmf_handle_t h, const float* X, int n_rows, int n_cols, long long ld, int src_is_device,
+                        int precision, void* stream, cnmf_dataset_t* out) {
+  CNMF_REQUIRE(h && X && out, "dataset_create: NULL argument");
+  CNMF_REQUIRE(n_rows > 0 && n_cols > 0 && ld >= n_cols, "dataset_create: bad shape");
+  CNMF_REQUIRE(precision == CNMF_PRECISION_FP32 || precision == CNMF_PRECISION_TF32X3, "dataset_create: bad precision");
+  cudaStream_t s = as_stream(stream);
+  CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  auto* d = new cnmf_dataset_s();
+  d->h = h;
+  d->n_rows = n_rows;
+  d->n_cols = n_cols;
+  d->ld_c = pad_ld(n_cols);
+  d->ld_r = pad_ld(n_rows);
+  d->precision = precision;
+  int rc = dataset_alloc(d, &d->X, (size_t)n_rows * d->ld_c);
+  if (rc == 0) {
+    cudaError_t e = cudaMemsetAsync(d->X, 0, (size_t)n_rows * d->ld_c * sizeof(float), s);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(d->X, (size_t)d->ld_c * sizeof(float), X, (size_t)ld * sizeof(float),
+                            (size_t)n_cols * sizeof(float), n_rows,
+                            src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) {
+      set_last_error(std::string("dataset upload failed: ") + cudaGetErrorString(e));
+      rc = -2;
+    }
+  }
+  if (rc == 0) rc = dataset_finish(d, s);
+  if (rc != 0) {
+    cnmf_dataset_destroy(d);
+    return rc;
+  }
+  *out = d;
+  return 0;
+}
+
+int cnmf_dataset_finish_internal(cnmf_dataset_t d, void* stream) { return dataset_finish(d, as_stream(stream)); }
+
+int cnmf_dataset_destroy(cnmf_dataset_t d) {
+  if (!d) return 0;
+  for (void* p : d->owned) cudaFree(p);
+  delete d;
+  return 0;
+}
+
+int cnmf_dataset_shape(cnmf_dataset_t d, int* n_rows, int* n_cols) {
+  CNMF_REQUIRE(d, "dataset_shape: NULL dataset");
+  if (n_rows) *n_rows = d->n_rows;
+  if (n_cols) *n_cols = d->n_cols;
+  return 0;
+}
+
+int cnmf_dataset_sums(cnmf_dataset_t d, double* sum, double* sum_sq) {
+  CNMF_REQUIRE(d, "dataset_sums: NULL dataset");
+  if (sum) *sum = d->sum;
+  if (sum_sq) *sum_sq = d->sum_sq;
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- random init
+int cnmf_random_init_host(uint32_t seed, double avg, int n_samples, int n_features, int k, float* Wt, long long ldW,
+                          float* H, long long ldH) {
+  CNMF_REQUIRE(Wt && H && n_samples > 0 && n_features > 0 && k > 0, "random_init: bad arguments");
+  CNMF_REQUIRE(ldW >= n_samples && ldH >= n_features, "random_init: leading dimension too small");
+  nmf_random_init(seed, avg, n_samples, n_features, k, Wt, ldW, H, ldH);
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- factorize
+namespace {
+
+struct FactorBuffers {
+  float *Fr, *Fr_hi, *Fr_lo, *Fc, *Fc_hi, *Fc_lo;
+};
+
+int alloc_factors(cnmf_handle_s* h, int SK, int ld_r, int ld_c, bool tf32, FactorBuffers* fb) {
+  const size_t nr = (size_t)SK * ld_r, nc = (size_t)SK * ld_c;
+  fb->Fr = static_cast<float*>(h->dev_buf("fac.Fr", nr * 4));
+  fb->Fc = static_cast<float*>(h->dev_buf("fac.Fc", nc * 4));
+  fb->Fr_hi = fb->Fr_lo = fb->Fc_hi = fb->Fc_lo = nullptr;
+  if (!fb->Fr || !fb->Fc) return -2;
+  if (tf32) {
+    fb->Fr_hi = static_cast<float*>(h->dev_buf("fac.Fr_hi", nr * 4));
+    fb->Fr_lo = static_cast<float*>(h->dev_buf("fac.Fr_lo", nr * 4));
+    fb->Fc_hi = static_cast<float*>(h->dev_buf("fac.Fc_hi", nc * 4));
+    fb->Fc_lo = static_cast<float*>(h->dev_buf("fac.Fc_lo", nc * 4));
+    if (!fb->Fr_hi || !fb->Fr_lo || !fb->Fc_hi || !fb->Fc_lo) return -2;
+  }
+  return 0;
+}
+
+void parallel_for(int n, const std::function<void(int)>& fn) {
+  int nt = (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  nt = std::min(nt, n);
+  if (nt <= 1) {
+    for (int i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<int> next{0};
+  std::vector<std::thread> th;
+  th.reserve(nt);
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&] {
+      for (;;) {
+        const int i = next.fetch_add(1);
+        if (i >= n) break;
+        fn(i);
+      }
+    });
+  for (auto& t : th) t.join();
+}
+
+// shared tail of cnmf_factorize / cnmf_factorize_init: factors already in fb.Fr / fb.Fc (full fp32)
+int run_and_download(cnmf_dataset_s* d, const std::vector<int>& ks, int SK, FactorBuffers& fb,
+                     const cnmf_nmf_params& p, float* spectra_host, float* usages_host, int32_t* n_iter_host,
+                     double* err_host, cudaStream_t s) {
+  cnmf_handle_s* h = d->h;
+  const bool tf32 = p.precision == CNMF_PRECISION_TF32X3;
+  if (tf32) {
+    CNMF_TRY(launch_split_tf32(fb.Fr, fb.Fr_hi, fb.Fr_lo, (long long)SK * d->ld_r, s));
+    CNMF_TRY(launch_split_tf32(fb.Fc, fb.Fc_hi, fb.Fc_lo, (long long)SK * d->ld_c, s));
+    h->launches += 2;
+  }
+  DataView v = make_view(d, false);
+  SolveIO io;
+  io.R = (int)ks.size();
+  io.ks = ks;
+  io.Fr = fb.Fr; io.Fr_hi = fb.Fr_hi; io.Fr_lo = fb.Fr_lo;
+  io.Fc = fb.Fc; io.Fc_hi = fb.Fc_hi; io.Fc_lo = fb.Fc_lo;
+  io.update_cols = true;
+  CNMF_TRY(solve_batched(h, v, io, p, s));
+  CNMF_CUDA_CHECK(cudaMemcpy2DAsync(spectra_host, (size_t)d->n_cols * 4, fb.Fc, (size_t)d->ld_c * 4,
+                                    (size_t)d->n_cols * 4, SK, cudaMemcpyDeviceToHost, s));
+  if (usages_host)
+    CNMF_CUDA_CHECK(cudaMemcpy2DAsync(usages_host, (size_t)d->n_rows * 4, fb.Fr, (size_t)d->ld_r * 4,
+                                      (size_t)d->n_rows * 4, SK, cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  for (size_t r = 0; r < ks.size(); ++r) {
+    if (n_iter_host) n_iter_host[r] = io.n_iter[r];
+    if (err_host) err_host[r] = io.err[r];
+  }
+  return 0;
+}
+
+int check_params(cnmf_dataset_s* d, const cnmf_nmf_params* p) {
+  CNMF_REQUIRE(d && p, "NULL dataset or params");
+  CNMF_REQUIRE(p->precision == d->precision, "params.precision must match the precision the dataset was created with");
+  return 0;
+}
+
+}  // namespace
+
+int cnmf_factorize(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, const uint32_t* seeds,
+                   const cnmf_nmf_params* p, float* spectra_host, float* usages_host, int32_t* n_iter_host,
+                   double* err_host, void* stream) {
+  CNMF_TRY(check_params(d, p));
+  CNMF_REQUIRE(n_restarts > 0 && ks_in && seeds && spectra_host, "factorize: bad arguments");
+  cnmf_handle_s* h = d->h;
+  cudaStream_t s = as_stream(stream);
+  CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  std::vector<int> ks(ks_in, ks_in + n_restarts), off(n_restarts);
+  int SK = 0;
+  for (int r = 0; r < n_restarts; ++r) {
+    CNMF_REQUIRE(ks[r] >= 1 && ks[r] <= KMAX, "factorize: n_components must be in [1, 32] on the CUDA path");
+    off[r] = SK;
+    SK += ks[r];
+  }
+  FactorBuffers fb;
+  CNMF_TRY(alloc_factors(h, SK, d->ld_r, d->ld_c, p->precision == CNMF_PRECISION_TF32X3, &fb));
+
+  // host RNG (bit-exact numpy legacy stream) in groups through a pinned staging buffer
+  const double mean = d->sum / ((double)d->n_rows * (double)d->n_cols);
+  const size_t group_budget = (size_t)256 << 20;   // bytes of W^T staged per group
+  int r0 = 0;
+  while (r0 < n_restarts) {
+    int r1 = r0;
+    size_t bytes = 0;
+    while (r1 < n_restarts && (r1 == r0 || bytes + (size_t)ks[r1] * d->ld_r * 4 <= group_budget)) {
+      bytes += (size_t)ks[r1] * d->ld_r * 4;
+      ++r1;
+    }
+    const int rows = off[r1 - 1] + ks[r1 - 1] - off[r0];
+    float* stW = static_cast<float*>(h->host_buf("stage.W", (size_t)rows * d->ld_r * 4));
+    float* stH = static_cast<float*>(h->host_buf("stage.H", (size_t)rows * d->ld_c * 4));
+    if (!stW || !stH) return -2;
+    std::memset(stW, 0, (size_t)rows * d->ld_r * 4);
+    std::memset(stH, 0, (size_t)rows * d->ld_c * 4);
+    parallel_for(r1 - r0, [&](int i) {
+      const int r = r0 + i;
+      const double avg = std::sqrt(mean / ks[r]);
+      nmf_random_init(seeds[r], avg, d->n_rows, d->n_cols, ks[r], stW + (size_t)(off[r] - off[r0]) * d->ld_r, d->ld_r,
+                      stH + (size_t)(off[r] - off[r0]) * d->ld_c, d->ld_c);
+    });
+    CNMF_CUDA_CHECK(cudaMemcpyAsync(fb.Fr + (size_t)off[r0] * d->ld_r, stW, (size_t)rows * d->ld_r * 4,
+                                    cudaMemcpyHostToDevice, s));
+    CNMF_CUDA_CHECK(cudaMemcpyAsync(fb.Fc + (size_t)off[r0] * d->ld_c, stH, (size_t)rows * d->ld_c * 4,
+                                    cudaMemcpyHostToDevice, s));
+    CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+    r0 = r1;
+  }
+  return run_and_download(d, ks, SK, fb, *p, spectra_host, usages_host, n_iter_host, err_host, s);
+}
+
+int cnmf_factorize_init(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, const float* Wt0_host,
+                        const float* H0_host, const cnmf_nmf_params* p, float* spectra_host, float* usages_host,
+                        int32_t* n_iter_host, double* err_host, void* stream) {
+  CNMF_TRY(check_params(d, p));
+  CNMF_REQUIRE(n_restarts > 0 && ks_in && Wt0_host && H0_host && spectra_host, "factorize_init: bad arguments");
+  cnmf_handle_s* h = d->h;
+  cudaStream_t s = as_stream(stream);
+  CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  std::vector<int> ks(ks_in, ks_in + n_restarts);
+  int SK = 0;
+  for (int r = 0; r < n_restarts; ++r) {
+    CNMF_REQUIRE(ks[r] >= 1 && ks[r] <= KMAX, "factorize_init: n_components must be in [1, 32] on the CUDA path");
+    SK += ks[r];
+  }
+  FactorBuffers fb;
+  CNMF_TRY(alloc_factors(h, SK, d->ld_r, d->ld_c, p->precision == CNMF_PRECISION_TF32X3, &fb));
+  CNMF_CUDA_CHECK(cudaMemsetAsync(fb.Fr, 0, (size_t)SK * d->ld_r * 4, s));
+  CNMF_CUDA_CHECK(cudaMemsetAsync(fb.Fc, 0, (size_t)SK * d->ld_c * 4, s));
+  CNMF_CUDA_CHECK(cudaMemcpy2DAsync(fb.Fr, (size_t)d->ld_r * 4, Wt0_host, (size_t)d->n_rows * 4, (size_t)d->n_rows * 4,
+                                    SK, cudaMemcpyHostToDevice, s));
+  CNMF_CUDA_CHECK(cudaMemcpy2DAsync(fb.Fc, (size_t)d->ld_c * 4, H0_host, (size_t)d->n_cols * 4, (size_t)d->n_cols * 4,
+                                    SK, cudaMemcpyHostToDevice, s));
+  return run_and_download(d, ks, SK, fb, *p, spectra_host, usages_host, n_iter_host, err_host, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,322 @@
+// extern "C": NNLS refits (cNMF.refit_usage / refit_spectra, cnmf.py:776-820), prediction error
+// (cnmf.py:926-930), left projections for the OLS step (cnmf.py:98-119), column statistics,
+// column-subset datasets (cnmf.py:965-969) and a raw GEMM hook used by tests / micro-benchmarks.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "engine.h"
+#include "gemm.h"
+#include "nmf_kernels.cuh"
+
+using namespace cnmf;
+
+#define CNMF_TRY(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != 0) return _rc;     \
+  } while (0)
+
+namespace {
+
+__global__ void fill_kernel(float* p, float v, int rows, int n, int ld) {
+  const long long total = (long long)rows * n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    p[(i / n) * ld + (i % n)] = v;
+}
+
+__global__ void col_stats_kernel(const float* __restrict__ X, int rows, int cols, int ld, double* __restrict__ mean,
+                                 double* __restrict__ var) {
+  // one warp-wide column strip per block.x: threads own columns (coalesced), loop over rows in fp64
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double s = 0.0, q = 0.0;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    const double v = X[(long long)r * ld + c];
+    s += v;
+    q += v * v;
+  }
+  atomicAdd(&mean[c], s);
+  atomicAdd(&var[c], q);
+}
+
+__global__ void gather_cols_kernel(const float* __restrict__ src, int rows, int ld_src, const int* __restrict__ cols,
+                                   const float* __restrict__ scale, int n_cols, float* __restrict__ dst, int ld_dst) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= n_cols) return;
+  dst[(long long)r * ld_dst + c] = src[(long long)r * ld_src + cols[c]] * scale[c];
+}
+
+int dataset_alloc2(cnmf_dataset_s* d, float** p, size_t elems) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(elems, 64) * sizeof(float));
+  if (e != cudaSuccess) {
+    set_last_error(std::string("dataset cudaMalloc failed: ") + cudaGetErrorString(e));
+    return -2;
+  }
+  d->owned.push_back(q);
+  *p = static_cast<float*>(q);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cnmf_dataset_col_stats(cnmf_dataset_t d, double* mean_host, double* var_host, void* stream) {
+  CNMF_REQUIRE(d && mean_host && var_host, "col_stats: NULL argument");
+  cnmf_handle_s* h = d->h;
+  cudaStream_t s = as_stream(stream);
+  CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  double* buf = static_cast<double*>(h->dev_buf("colstats", sizeof(double) * 2 * d->n_cols));
+  if (!buf) return -2;
+  CNMF_CUDA_CHECK(cudaMemsetAsync(buf, 0, sizeof(double) * 2 * d->n_cols, s));
+  dim3 grid((d->n_cols + 127) / 128, std::min(d->n_rows, 256));
+  col_stats_kernel<<<grid, 128, 0, s>>>(d->X, d->n_rows, d->n_cols, d->ld_c, buf, buf + d->n_cols);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  h->launches += 1;
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(mean_host, buf, sizeof(double) * d->n_cols, cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(var_host, buf + d->n_cols, sizeof(double) * d->n_cols, cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  const double n = d->n_rows;
+  for (int c = 0; c < d->n_cols; ++c) {
+    const double m = mean_host[c] / n;
+    mean_host[c] = m;
+    var_host[c] = std::max(var_host[c] / n - m * m, 0.0);
+  }
+  return 0;
+}
+
+// defined in capi.cu (internal; not in the public header)
+int cnmf_dataset_finish_internal(cnmf_dataset_t d, void* stream);
+
+int cnmf_dataset_from_columns(cnmf_dataset_t src, const int32_t* cols_host, const float* col_scale_host, int n_cols,
+                              void* stream, cnmf_dataset_t* out) {
+  CNMF_REQUIRE(src && cols_host && col_scale_host && out && n_cols > 0, "dataset_from_columns: bad arguments");
+  for (int c = 0; c < n_cols; ++c)
+    CNMF_REQUIRE(cols_host[c] >= 0 && cols_host[c] < src->n_cols, "dataset_from_columns: column index out of range");
+  cnmf_handle_s* h = src->h;
+  cudaStream_t s = as_stream(stream);
+  CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  int* d_cols = static_cast<int*>(h->dev_buf("fromcols.idx", sizeof(int) * n_cols));
+  float* d_scale = static_cast<float*>(h->dev_buf("fromcols.scale", sizeof(float) * n_cols));
+  if (!d_cols || !d_scale) return -2;
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(d_cols, cols_host, sizeof(int) * n_cols, cudaMemcpyHostToDevice, s));
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(d_scale, col_scale_host, sizeof(float) * n_cols, cudaMemcpyHostToDevice, s));
+  auto* d = new cnmf_dataset_s();
+  d->h = h;
+  d->n_rows = src->n_rows;
+  d->n_cols = n_cols;
+  d->ld_c = pad_ld(n_cols);
+  d->ld_r = pad_ld(src->n_rows);
+  d->precision = src->precision;
+  int rc = dataset_alloc2(d, &d->X, (size_t)d->n_rows * d->ld_c);
+  if (rc == 0) {
+    cudaError_t e = cudaMemsetAsync(d->X, 0, (size_t)d->n_rows * d->ld_c * sizeof(float), s);
+    if (e != cudaSuccess) rc = -2;
+  }
+  if (rc == 0) {
+    dim3 grid((n_cols + 127) / 128, d->n_rows);
+    if (d->n_rows > 65535) {
+      set_last_error("dataset_from_columns: more than 65535 rows per launch not supported yet");
+      rc = -3;
+    } else {
+      gather_cols_kernel<<<grid, 128, 0, s>>>(src->X, d->n_rows, src->ld_c, d_cols, d_scale, n_cols, d->X, d->ld_c);
+      h->launches += 1;
+      if (cudaGetLastError() != cudaSuccess) rc = -2;
+    }
+  }
+  if (rc == 0) rc = cnmf_dataset_finish_internal(d, stream);
+  if (rc != 0) {
+    cnmf_dataset_destroy(d);
+    return rc;
+  }
+  *out = d;
+  return 0;
+}
+
+// --------------------------------------------------------------------------------- refit
+int cnmf_refit(cnmf_dataset_t d, int transposed, int k, const float* fixed_host, const cnmf_nmf_params* p,
+               float* out_host, int32_t* n_iter_host, double* err_host, void* stream) {
+  CNMF_REQUIRE(d && fixed_host && p && out_host, "refit: NULL argument");
+  CNMF_REQUIRE(p->precision == d->precision, "params.precision must match the precision the dataset was created with");
+  CNMF_REQUIRE(k >= 1 && k <= KMAX, "refit: n_components must be in [1, 32] on the CUDA path");
+  cnmf_handle_s* h = d->h;
+  cudaStream_t s = as_stream(stream);
+  CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  const bool tf32 = p->precision == CNMF_PRECISION_TF32X3;
+  DataView v = make_view(d, transposed != 0);
+
+  const size_t nr = (size_t)k * v.ld_r, nc = (size_t)k * v.ld_c;
+  float* Fr = static_cast<float*>(h->dev_buf("refit.Fr", nr * 4));
+  float* Fc = static_cast<float*>(h->dev_buf("refit.Fc", nc * 4));
+  float *Fr_hi = nullptr, *Fr_lo = nullptr, *Fc_hi = nullptr, *Fc_lo = nullptr;
+  if (!Fr || !Fc) return -2;
+  if (tf32) {
+    Fr_hi = static_cast<float*>(h->dev_buf("refit.Fr_hi", nr * 4));
+    Fr_lo = static_cast<float*>(h->dev_buf("refit.Fr_lo", nr * 4));
+    Fc_hi = static_cast<float*>(h->dev_buf("refit.Fc_hi", nc * 4));
+    Fc_lo = static_cast<float*>(h->dev_buf("refit.Fc_lo", nc * 4));
+    if (!Fr_hi || !Fr_lo || !Fc_hi || !Fc_lo) return -2;
+  }
+  CNMF_CUDA_CHECK(cudaMemsetAsync(Fr, 0, nr * 4, s));
+  CNMF_CUDA_CHECK(cudaMemsetAsync(Fc, 0, nc * 4, s));
+  CNMF_CUDA_CHECK(cudaMemcpy2DAsync(Fc, (size_t)v.ld_c * 4, fixed_host, (size_t)v.n_c * 4, (size_t)v.n_c * 4, k,
+                                    cudaMemcpyHostToDevice, s));
+  if (p->solver == CNMF_SOLVER_MU) {
+    // sklearn _nmf.py:1223-1226: W = full(sqrt(X.mean() / k))
+    const double mean = v.sum / ((double)v.n_r * (double)v.n_c);
+    fill_kernel<<<148 * 4, 256, 0, s>>>(Fr, (float)std::sqrt(mean / k), k, v.n_r, v.ld_r);
+    CNMF_CUDA_CHECK(cudaGetLastError());
+    h->launches += 1;
+  }  // 'cd': zeros (sklearn _nmf.py:1227-1228)
+  if (tf32) {
+    CNMF_TRY(launch_split_tf32(Fr, Fr_hi, Fr_lo, (long long)nr, s));
+    CNMF_TRY(launch_split_tf32(Fc, Fc_hi, Fc_lo, (long long)nc, s));
+    h->launches += 2;
+  }
+  SolveIO io;
+  io.R = 1;
+  io.ks = {k};
+  io.Fr = Fr; io.Fr_hi = Fr_hi; io.Fr_lo = Fr_lo;
+  io.Fc = Fc; io.Fc_hi = Fc_hi; io.Fc_lo = Fc_lo;
+  io.update_cols = false;
+  CNMF_TRY(solve_batched(h, v, io, *p, s));
+
+  // Fr is k x n_r; the caller wants n_r x k (row-major)
+  const int ldt = pad_ld(k);
+  float* T = static_cast<float*>(h->dev_buf("refit.T", (size_t)v.n_r * ldt * 4));
+  if (!T) return -2;
+  CNMF_TRY(launch_transpose(Fr, k, v.n_r, v.ld_r, T, nullptr, nullptr, ldt, s));
+  h->launches += 1;
+  CNMF_CUDA_CHECK(cudaMemcpy2DAsync(out_host, (size_t)k * 4, T, (size_t)ldt * 4, (size_t)k * 4, v.n_r,
+                                    cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (n_iter_host) *n_iter_host = io.n_iter[0];
+  if (err_host) *err_host = io.err[0];
+  return 0;
+}
+
+// --------------------------------------------------------------------------------- projections
+// out (k x n_cols) = Ut (k x n_rows) * X  -- the X^T Y accumulator of efficient_ols_all_cols (cnmf.py:119)
+int cnmf_project_rows(cnmf_dataset_t d, int k, const float* Ut_host, float* out_host, void* stream) {
+  CNMF_REQUIRE(d && Ut_host && out_host && k >= 1, "project_rows: bad arguments");
+  cnmf_handle_s* h = d->h;
+  cudaStream_t s = as_stream(stream);
+  CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  const bool tf32 = d->precision == CNMF_PRECISION_TF32X3;
+  const size_t nr = (size_t)k * d->ld_r;
+  float* A = static_cast<float*>(h->dev_buf("proj.A", nr * 4));
+  float *A_hi = nullptr, *A_lo = nullptr;
+  if (!A) return -2;
+  CNMF_CUDA_CHECK(cudaMemsetAsync(A, 0, nr * 4, s));
+  CNMF_CUDA_CHECK(cudaMemcpy2DAsync(A, (size_t)d->ld_r * 4, Ut_host, (size_t)d->n_rows * 4, (size_t)d->n_rows * 4, k,
+                                    cudaMemcpyHostToDevice, s));
+  if (tf32) {
+    A_hi = static_cast<float*>(h->dev_buf("proj.A_hi", nr * 4));
+    A_lo = static_cast<float*>(h->dev_buf("proj.A_lo", nr * 4));
+    if (!A_hi || !A_lo) return -2;
+    CNMF_TRY(launch_split_tf32(A, A_hi, A_lo, (long long)nr, s));
+    h->launches += 1;
+  }
+  GemmArgs g{};
+  g.M = k; g.N = d->n_cols; g.Kd = d->n_rows;
+  g.lda = d->ld_r; g.ldb = d->ld_r; g.ldc = d->ld_c;
+  int splits = 1;
+  {
+    const int tiles = ((k + 127) / 128) * ((d->n_cols + 255) / 256);
+    if (tiles < 2 * h->sm_count) splits = (2 * h->sm_count + tiles - 1) / tiles;
+    splits = std::min(splits, std::max(1, ((d->n_rows + 31) / 32) / 8));
+    splits = std::min(splits, 32);
+    splits = gemm_effective_splits(d->n_rows, splits);
+  }
+  g.splits = g.splits_effective = splits;
+  g.c_split_stride = (long long)k * d->ld_c;
+  float* C = static_cast<float*>(h->dev_buf("proj.C", (size_t)splits * k * d->ld_c * 4));
+  if (!C) return -2;
+  g.C = C;
+  if (tf32) {
+    g.A_hi = A_hi; g.A_lo = A_lo; g.B_hi = d->Xt_hi; g.B_lo = d->Xt_lo;
+    CNMF_TRY(gemm_tf32x3(g, s));
+  } else {
+    g.A_hi = A; g.B_hi = d->Xt;
+    CNMF_TRY(gemm_fp32_simt(g, s));
+  }
+  h->launches += 1;
+  std::vector<float> tmp((size_t)splits * k * d->ld_c);
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), C, tmp.size() * 4, cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  for (int c = 0; c < k; ++c)
+    for (int j = 0; j < d->n_cols; ++j) {
+      double a = 0.0;
+      for (int z = 0; z < splits; ++z) a += tmp[(size_t)z * k * d->ld_c + (size_t)c * d->ld_c + j];
+      out_host[(size_t)c * d->n_cols + j] = (float)a;
+    }
+  return 0;
+}
+
+// --------------------------------------------------------------------------------- raw GEMM hook
+// C (M x N) = A (M x Kd) * B (N x Kd)^T on host buffers; reps > 1 re-runs the kernel and reports the
+// mean device time per launch in *ms_out (CUDA events).  Used by tests and by the roofline micro-bench.
+int cnmf_gemm_abt_host(cnmf_handle_t h, int precision, const float* A, const float* B, int M, int N, int Kd, int splits,
+                       float* C, int reps, float* ms_out, void* stream) {
+  CNMF_REQUIRE(h && A && B && C && M > 0 && N > 0 && Kd > 0, "gemm_abt_host: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  const int lda = pad_ld(Kd), ldc = pad_ld(N);
+  const size_t na = (size_t)M * lda, nb = (size_t)N * lda;
+  float* dA = static_cast<float*>(h->dev_buf("gemmtest.A", na * 4));
+  float* dB = static_cast<float*>(h->dev_buf("gemmtest.B", nb * 4));
+  float* dAh = static_cast<float*>(h->dev_buf("gemmtest.Ah", na * 4));
+  float* dAl = static_cast<float*>(h->dev_buf("gemmtest.Al", na * 4));
+  float* dBh = static_cast<float*>(h->dev_buf("gemmtest.Bh", nb * 4));
+  float* dBl = static_cast<float*>(h->dev_buf("gemmtest.Bl", nb * 4));
+  const int se = gemm_effective_splits(Kd, splits);
+  float* dC = static_cast<float*>(h->dev_buf("gemmtest.C", (size_t)se * M * ldc * 4));
+  if (!dA || !dB || !dAh || !dAl || !dBh || !dBl || !dC) return -2;
+  CNMF_CUDA_CHECK(cudaMemsetAsync(dA, 0, na * 4, s));
+  CNMF_CUDA_CHECK(cudaMemsetAsync(dB, 0, nb * 4, s));
+  CNMF_CUDA_CHECK(cudaMemcpy2DAsync(dA, (size_t)lda * 4, A, (size_t)Kd * 4, (size_t)Kd * 4, M, cudaMemcpyHostToDevice, s));
+  CNMF_CUDA_CHECK(cudaMemcpy2DAsync(dB, (size_t)lda * 4, B, (size_t)Kd * 4, (size_t)Kd * 4, N, cudaMemcpyHostToDevice, s));
+  CNMF_TRY(launch_split_tf32(dA, dAh, dAl, (long long)na, s));
+  CNMF_TRY(launch_split_tf32(dB, dBh, dBl, (long long)nb, s));
+  CNMF_CUDA_CHECK(cudaMemsetAsync(dC, 0xff, (size_t)se * M * ldc * 4, s));   // NaN pattern: unwritten outputs show up
+  GemmArgs g{};
+  g.M = M; g.N = N; g.Kd = Kd; g.lda = lda; g.ldb = lda; g.ldc = ldc;
+  g.C = dC; g.c_split_stride = (long long)M * ldc; g.splits = splits; g.splits_effective = se;
+  if (precision == CNMF_PRECISION_TF32X3) { g.A_hi = dAh; g.A_lo = dAl; g.B_hi = dBh; g.B_lo = dBl; }
+  else { g.A_hi = dA; g.B_hi = dB; }
+  cudaEvent_t e0, e1;
+  CNMF_CUDA_CHECK(cudaEventCreate(&e0));
+  CNMF_CUDA_CHECK(cudaEventCreate(&e1));
+  if (reps < 1) reps = 1;
+  int rc = precision == CNMF_PRECISION_TF32X3 ? gemm_tf32x3(g, s) : gemm_fp32_simt(g, s);   // warm-up + result
+  if (rc == 0 && reps > 1) {
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < reps && rc == 0; ++i) rc = precision == CNMF_PRECISION_TF32X3 ? gemm_tf32x3(g, s) : gemm_fp32_simt(g, s);
+    cudaEventRecord(e1, s);
+  }
+  h->launches += reps;
+  if (rc != 0) return rc;
+  std::vector<float> tmp((size_t)se * M * ldc);
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), dC, tmp.size() * 4, cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (ms_out) {
+    float ms = 0.f;
+    if (reps > 1) cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = reps > 1 ? ms / reps : 0.f;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      double a = 0.0;
+      for (int z = 0; z < se; ++z) a += tmp[(size_t)z * M * ldc + (size_t)m * ldc + n];
+      C[(size_t)m * N + n] = (float)a;
+    }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// Host-side engine objects behind the C ABI (handle, dataset, workspace).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/cnmf_b200.h"
+#include "common.cuh"
+
+struct cnmf_handle_s {
+  int device = 0;
+  int sm_count = 148;
+  long long launches = 0;                       // kernels launched by this library (bench: gpu_launches)
+  std::map<std::string, std::pair<void*, size_t>> ws;   // named grow-only device buffers
+  std::map<std::string, std::pair<void*, size_t>> pinned;  // named grow-only pinned host buffers
+
+  void* dev_buf(const std::string& name, size_t bytes);      // nullptr on failure (error set)
+  void* host_buf(const std::string& name, size_t bytes);
+  void release_all();
+};
+
+// A cells x genes matrix resident on the device in the forms the two GEMM orientations need.
+//   X   (n_rows x ld_c)  : K-major over columns  -> B operand of  NUM_rows = F_cols * X^T
+//   Xt  (n_cols x ld_r)  : K-major over rows     -> B operand of  NUM_cols = F_rows * X
+// fp32 mode keeps X and Xt; tf32x3 mode keeps X (full, for column ops) + the hi/lo pieces of both.
+struct cnmf_dataset_s {
+  cnmf_handle_s* h = nullptr;
+  int n_rows = 0, n_cols = 0;
+  int ld_c = 0;   // row stride of X  (>= n_cols)
+  int ld_r = 0;   // row stride of Xt (>= n_rows)
+  int precision = 0;
+  float *X = nullptr, *Xt = nullptr;
+  float *X_hi = nullptr, *X_lo = nullptr, *Xt_hi = nullptr, *Xt_lo = nullptr;
+  double sum = 0.0, sum_sq = 0.0;
+  std::vector<void*> owned;
+};
+
+namespace cnmf {
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+struct Operand {     // a K-major matrix as the GEMM sees it
+  const float* full;
+  const float* hi;
+  const float* lo;
+  int rows, cols, ld;
+};
+
+// View of a dataset for one solve: "rows" are the items of the row factor (Fr: SK x n_r),
+// "cols" the items of the column factor (Fc: SK x n_c).  transposed swaps the roles.
+struct DataView {
+  Operand B_rows;   // n_r x n_c : B operand when updating Fr (reduction over n_c)
+  Operand B_cols;   // n_c x n_r : B operand when updating Fc (reduction over n_r)
+  int n_r, n_c, ld_r, ld_c;
+  double sum, sum_sq;
+};
+
+DataView make_view(const cnmf_dataset_s* d, bool transposed);
+
+struct SolveIO {
+  int R = 0;
+  std::vector<int> ks;      // per restart
+  // packed device factors (SK x ld): row factor Fr (e.g. W^T), column factor Fc (e.g. H)
+  float *Fr = nullptr, *Fr_hi = nullptr, *Fr_lo = nullptr;
+  float *Fc = nullptr, *Fc_hi = nullptr, *Fc_lo = nullptr;
+  bool update_cols = true;  // false: Fc fixed (refit)
+  std::vector<int> n_iter;  // out
+  std::vector<double> last; // out: last convergence statistic (mu: error, cd: violation)
+  std::vector<double> err;  // out: final ||X - Fr^T Fc||_F
+};
+
+// Runs the batched solver in place on io.Fr / io.Fc.
+int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_nmf_params& p, cudaStream_t s);
+
+}  // namespace cnmf

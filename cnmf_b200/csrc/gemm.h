@@ -1,0 +1,29 @@
+// Internal GEMM interface: C[z] (M x N) = A[:, Kz] (M x Kd, K-major) * B[:, Kz]^T (N x Kd, K-major).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace cnmf {
+
+struct GemmArgs {
+  const float* A_hi;   // M x Kd, row stride lda   (tf32x3: tf32 "hi" piece; fp32 path: the full matrix)
+  const float* A_lo;   // tf32 "lo" piece (unused by the fp32 path)
+  const float* B_hi;   // N x Kd, row stride ldb
+  const float* B_lo;
+  float* C;            // splits_effective x (M x ldc)
+  int M, N, Kd;
+  int lda, ldb, ldc;
+  long long c_split_stride;   // elements between consecutive split-K slices of C
+  int splits;                 // requested split-K factor
+  int splits_effective;       // gemm_effective_splits(Kd, splits): what the kernel will actually write
+};
+
+// number of non-empty split-K slices for a reduction length Kd (k-blocks of 32)
+int gemm_effective_splits(int Kd, int splits);
+
+// tcgen05 / TMEM / TMA path (gemm_tf32x3.cu)
+int gemm_tf32x3(const GemmArgs& g, cudaStream_t stream);
+
+// plain fp32 FFMA path (gemm_simt.cu): A = A_hi, B = B_hi exactly; same split-K contract
+int gemm_fp32_simt(const GemmArgs& g, cudaStream_t stream);
+
+}  // namespace cnmf

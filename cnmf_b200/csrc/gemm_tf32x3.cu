@@ -1,0 +1,379 @@
+// 3xTF32 tensor-core GEMM for sm_100a (tcgen05 + TMEM + TMA), hand-written PTX.
+//
+//   C[z] (M x N, row-major, ldc) = A[:, Kz] * B[:, Kz]^T          z = split-K slice
+//
+// A (M x Kd) and B (N x Kd) are both K-major (row-major with the reduction index contiguous),
+// each given as two tf32-representable pieces  A = A_hi + A_lo,  B = B_hi + B_lo  and the
+// product is accumulated in fp32 in tensor memory as  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo
+// (the dropped A_lo*B_lo term is <= 2^-22 relative): fp32-class accuracy from kind::tf32 MMAs.
+//
+// This is the shape of both big products of an NMF multiplicative-update / coordinate-descent
+// iteration once the restarts are batched:
+//   M = sum of K over live restarts (rows of H_batch or W^T_batch),  N = cells or genes.
+//   X H^T   (sklearn _nmf.py:538, :380)  ->  A = H_batch (SK x G),   B = X   (cells x G)
+//   W^T X   (sklearn _nmf.py:634, :380)  ->  A = W^T_batch (SK x N), B = X^T (G x cells), split-K
+//
+// Structure (one CTA per SM, persistent over a static tile schedule, 192 threads):
+//   warp 0     TMA producer: cp.async.bulk.tensor 2D, 128B-swizzled tiles, mbarrier full/empty ring
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 8, kind::tf32)
+//   warps 2-5  epilogue: tcgen05.ld 32x32b -> registers -> float4 global stores
+//              (TMEM accumulator double-buffered so the epilogue overlaps the next tile's MMAs)
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+
+#include "common.cuh"
+#include "gemm.h"
+
+namespace cnmf {
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M (rows of A per tile) -- one TMEM lane per row
+constexpr int BK = 32;           // fp32 elements per k-block = 128 B = one swizzle row
+constexpr int UMMA_K = 8;        // kind::tf32: 32 B of K per instruction
+constexpr int NUM_THREADS = 192;
+constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;   // ~2 s: a dead pipeline traps instead of hanging
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 4;              // 16 KB
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = TILE_BYTES;            // full[STAGES], empty[STAGES], tfull[2], tempty[2]
+  static constexpr int TMEM_PTR_OFFSET = BAR_OFFSET + (2 * STAGES + 4) * 8;
+  static constexpr int TOTAL = TMEM_PTR_OFFSET + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;           // slack for manual 1024 B alignment
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) {
+      printf("cnmf gemm_tf32x3: mbarrier wait timed out (block %d, role %d, parity %u)\n", blockIdx.x, who, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor, canonical layout Swizzle<3,4,3> o ((8,m),(T,2)):((8T,SBO),(1,T))).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);   // start address   bits [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                        // LBO (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                // SBO = 1024 B    bits [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                        // descriptor version 1 (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                        // SWIZZLE_128B
+  return d;
+}
+
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major A and B, N>>3 @17, M>>4 @24
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+         (static_cast<uint32_t>(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------ the kernel
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                   float* __restrict__ C, int M, int N, int ldc, long long c_split_stride,
+                   int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024 B alignment
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::TMEM_PTR_OFFSET);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 2 * BN;                      // two accumulators (power of two: 256 or 512)
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_base + L::TMEM_PTR_OFFSET), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int items = m_tiles * n_tiles * splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < items; w += gridDim.x) {
+        const int mt = w % m_tiles;
+        const int nt = (w / m_tiles) % n_tiles;
+        const int z = w / (m_tiles * n_tiles);
+        const int kb0 = z * kb_per_split;
+        const int kb1 = min(total_kb, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, 0);
+          const uint32_t st = smem_base + stage * L::STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), L::STAGE_BYTES);
+          tma_load_2d(st, &tmA_hi, full_bar(stage), kb * BK, mt * BM);
+          tma_load_2d(st + L::A_BYTES, &tmA_lo, full_bar(stage), kb * BK, mt * BM);
+          tma_load_2d(st + 2 * L::A_BYTES, &tmB_hi, full_bar(stage), kb * BK, nt * BN);
+          tma_load_2d(st + 2 * L::A_BYTES + L::B_BYTES, &tmB_lo, full_bar(stage), kb * BK, nt * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < items; w += gridDim.x) {
+        const int z = w / (m_tiles * n_tiles);
+        const int kb0 = z * kb_per_split;
+        const int kb1 = min(total_kb, kb0 + kb_per_split);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase, 2);
+          tc_fence_after();
+          const uint32_t st = smem_base + stage * L::STAGE_BYTES;
+          const uint64_t a_hi = make_smem_desc(st);
+          const uint64_t a_lo = make_smem_desc(st + L::A_BYTES);
+          const uint64_t b_hi = make_smem_desc(st + 2 * L::A_BYTES);
+          const uint64_t b_lo = make_smem_desc(st + 2 * L::A_BYTES + L::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 4) >> 4);   // +32 B per k-step inside the swizzle row
+            umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, 1u);
+            umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1u);
+          }
+          umma_commit(empty_bar(stage));           // smem slot is free once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));               // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
+    const int q = warp & 3;                        // tcgen05.ld: warp w may touch lanes 32*(w%4) .. +31
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < items; w += gridDim.x) {
+      const int mt = w % m_tiles;
+      const int nt = (w / m_tiles) % n_tiles;
+      const int z = w / (m_tiles * n_tiles);
+      mbar_wait(tfull_bar(acc), acc_phase, 3);
+      tc_fence_after();
+      const int row = mt * BM + q * 32 + lane;
+      float* crow = C + static_cast<long long>(z) * c_split_stride + static_cast<long long>(row) * ldc;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c, r);
+        tmem_ld_wait();
+        const int col0 = nt * BN + c;
+        if (row < M) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            if (col0 + i + 3 < ldc) {
+              float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                                     __uint_as_float(r[i + 3]));
+              *reinterpret_cast<float4*>(crow + col0 + i) = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// 2D fp32 tensor (rows x cols, row stride ld elements), box = 32 cols x box_rows rows, 128B swizzle, zero OOB fill
+int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) { set_last_error("cuTensorMapEncodeTiled entry point not available"); return -2; }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return -2;
+  }
+  return 0;
+}
+
+template <int BN, int STAGES>
+int launch(const GemmArgs& g, cudaStream_t stream) {
+  using L = SmemLayout<BN, STAGES>;
+  CUtensorMap mAh, mAl, mBh, mBl;
+  int rc;
+  if ((rc = make_map(&mAh, g.A_hi, g.M, g.Kd, g.lda, BM))) return rc;
+  if ((rc = make_map(&mAl, g.A_lo, g.M, g.Kd, g.lda, BM))) return rc;
+  if ((rc = make_map(&mBh, g.B_hi, g.N, g.Kd, g.ldb, BN))) return rc;
+  if ((rc = make_map(&mBl, g.B_lo, g.N, g.Kd, g.ldb, BN))) return rc;
+
+  const int m_tiles = (g.M + BM - 1) / BM;
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int total_kb = (g.Kd + BK - 1) / BK;
+  int splits = g.splits < 1 ? 1 : g.splits;
+  if (splits > total_kb) splits = total_kb;
+  const int kb_per_split = (total_kb + splits - 1) / splits;
+  splits = (total_kb + kb_per_split - 1) / kb_per_split;      // no empty slices
+  if (splits != g.splits_effective) { set_last_error("gemm: splits_effective mismatch (use gemm_effective_splits)"); return -1; }
+
+  auto kern = gemm_tf32x3_kernel<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CNMF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    attr_set = true;
+  }
+  int dev = 0, sms = 0;
+  CNMF_CUDA_CHECK(cudaGetDevice(&dev));
+  CNMF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int items = m_tiles * n_tiles * splits;
+  const int grid = items < sms ? items : sms;
+  kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(mAh, mAl, mBh, mBl, g.C, g.M, g.N, g.ldc, g.c_split_stride,
+                                                    m_tiles, n_tiles, splits, total_kb, kb_per_split);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int gemm_effective_splits(int Kd, int splits) {
+  const int total_kb = (Kd + BK - 1) / BK;
+  if (splits < 1) splits = 1;
+  if (splits > total_kb) splits = total_kb;
+  const int kb_per_split = (total_kb + splits - 1) / splits;
+  return (total_kb + kb_per_split - 1) / kb_per_split;
+}
+
+int gemm_tf32x3(const GemmArgs& g, cudaStream_t stream) {
+  CNMF_REQUIRE(g.M > 0 && g.N > 0 && g.Kd > 0, "gemm: empty problem");
+  CNMF_REQUIRE(g.lda % 4 == 0 && g.ldb % 4 == 0 && g.ldc % 4 == 0, "gemm: leading dimensions must be multiples of 4 floats");
+  CNMF_REQUIRE((reinterpret_cast<uintptr_t>(g.A_hi) | reinterpret_cast<uintptr_t>(g.A_lo) |
+                reinterpret_cast<uintptr_t>(g.B_hi) | reinterpret_cast<uintptr_t>(g.B_lo) |
+                reinterpret_cast<uintptr_t>(g.C)) % 16 == 0, "gemm: pointers must be 16-byte aligned");
+  return launch<256, 2>(g, stream);
+}
+
+}  // namespace cnmf

@@ -1,0 +1,285 @@
+// Batched NMF solver: all (k, seed) restarts of cNMF.factorize (cnmf.py:735-745) advance together.
+//
+// One outer iteration of sklearn's solvers (MU: _nmf.py:826-879, CD: _nmf.py:491-516) becomes
+//   NUM_r = Fc * X^T            tensor-core GEMM, M = sum k (all restarts), N = n_r, reduce over n_c
+//   Fr   <- update(Fr, NUM_r, Gram(Fc))       elementwise, K x K Gram from smem
+//   NUM_c = Fr * X              tensor-core GEMM, split-K over n_r
+//   Fc   <- update(Fc, NUM_c, Gram(Fr))
+// with Fr = W^T (SK x cells) and Fc = H (SK x genes), so the data matrix is streamed once per
+// product for ALL restarts.  Convergence is evaluated on the device per restart (trace-form
+// Frobenius error for MU, projected-gradient violation for CD); converged restarts are frozen
+// (their blocks exit) and the host only polls the flags.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "engine.h"
+#include "gemm.h"
+#include "nmf_kernels.cuh"
+
+namespace cnmf {
+
+DataView make_view(const cnmf_dataset_s* d, bool transposed) {
+  Operand X{d->X, d->X_hi, d->X_lo, d->n_rows, d->n_cols, d->ld_c};
+  Operand Xt{d->Xt, d->Xt_hi, d->Xt_lo, d->n_cols, d->n_rows, d->ld_r};
+  DataView v;
+  if (!transposed) {
+    v.B_rows = X; v.B_cols = Xt;
+    v.n_r = d->n_rows; v.n_c = d->n_cols; v.ld_r = d->ld_r; v.ld_c = d->ld_c;
+  } else {
+    v.B_rows = Xt; v.B_cols = X;
+    v.n_r = d->n_cols; v.n_c = d->n_rows; v.ld_r = d->ld_c; v.ld_c = d->ld_r;
+  }
+  v.sum = d->sum;
+  v.sum_sq = d->sum_sq;
+  return v;
+}
+
+namespace {
+
+int pick_splits(int sm_count, int M, int N, int Kd) {
+  const int tiles = ((M + 127) / 128) * ((N + 255) / 256);
+  const int total_kb = (Kd + 31) / 32;
+  int splits = 1;
+  if (tiles < 2 * sm_count) splits = (2 * sm_count + tiles - 1) / tiles;
+  splits = std::min(splits, std::max(1, total_kb / 8));
+  splits = std::min(splits, 32);
+  return gemm_effective_splits(Kd, splits);
+}
+
+struct GemmPlan {
+  int splits;
+  long long split_stride;   // elements
+};
+
+// C[z] (SK x N) = A (SK x Kd) * B (N x Kd)^T
+int run_gemm(cnmf_handle_s* h, int precision, const float* A, const float* A_hi, const float* A_lo, int SK, int lda,
+             const Operand& B, float* C, int ldc, const GemmPlan& plan, cudaStream_t s) {
+  GemmArgs g{};
+  g.M = SK; g.N = B.rows; g.Kd = B.cols;
+  g.lda = lda; g.ldb = B.ld; g.ldc = ldc;
+  g.C = C;
+  g.c_split_stride = plan.split_stride;
+  g.splits = plan.splits;
+  g.splits_effective = plan.splits;
+  h->launches += 1;
+  if (precision == CNMF_PRECISION_TF32X3) {
+    g.A_hi = A_hi; g.A_lo = A_lo; g.B_hi = B.hi; g.B_lo = B.lo;
+    return gemm_tf32x3(g, s);
+  }
+  g.A_hi = A; g.A_lo = nullptr; g.B_hi = B.full; g.B_lo = nullptr;
+  return gemm_fp32_simt(g, s);
+}
+
+#define CNMF_TRY(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != 0) return _rc;     \
+  } while (0)
+
+}  // namespace
+
+int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_nmf_params& p, cudaStream_t s) {
+  const int R = io.R;
+  CNMF_REQUIRE(R > 0 && (int)io.ks.size() == R, "solve: bad restart list");
+  CNMF_REQUIRE(p.solver == CNMF_SOLVER_MU || p.solver == CNMF_SOLVER_CD, "solve: unknown solver");
+  CNMF_REQUIRE(p.max_iter >= 1, "solve: max_iter must be >= 1");
+  const bool tf32 = p.precision == CNMF_PRECISION_TF32X3;
+  const bool mu = p.solver == CNMF_SOLVER_MU;
+
+  std::vector<int> off(R);
+  int SK = 0, kmax = 0;
+  for (int r = 0; r < R; ++r) {
+    CNMF_REQUIRE(io.ks[r] >= 1 && io.ks[r] <= KMAX, "solve: n_components must be in [1, 32] on the CUDA path");
+    off[r] = SK;
+    SK += io.ks[r];
+    kmax = std::max(kmax, io.ks[r]);
+  }
+  const int kp = kmax <= 8 ? 8 : (kmax <= 16 ? 16 : 32);
+  const int chunks_r = col_chunks(v.n_r), chunks_c = col_chunks(v.n_c);
+  const int chunks_max = std::max(chunks_r, chunks_c);
+
+  // ---- workspace
+  int* d_meta = static_cast<int*>(h->dev_buf("solve.meta", sizeof(int) * 4 * R));
+  double* d_state = static_cast<double*>(h->dev_buf("solve.state", sizeof(double) * 8 * R));
+  double* d_gram = static_cast<double*>(h->dev_buf("solve.gram", sizeof(double) * 2 * R * KMAX * KMAX));
+  double* d_gram_part =
+      static_cast<double*>(h->dev_buf("solve.gram_part", sizeof(double) * (size_t)R * chunks_max * kp * kp));
+  double* d_scal_part = static_cast<double*>(h->dev_buf("solve.scal_part", sizeof(double) * 2 * (size_t)R * chunks_max));
+  if (!d_meta || !d_state || !d_gram || !d_gram_part || !d_scal_part) return -2;
+
+  GemmPlan plan_r, plan_c;   // plan_r: NUM_r = Fc * B_rows^T (reduce over n_c); plan_c: NUM_c = Fr * B_cols^T
+  plan_r.splits = pick_splits(h->sm_count, SK, v.n_r, v.n_c);
+  plan_r.split_stride = (long long)SK * v.ld_r;
+  plan_c.splits = pick_splits(h->sm_count, SK, v.n_c, v.n_r);
+  plan_c.split_stride = (long long)SK * v.ld_c;
+  float* NUMr = static_cast<float*>(h->dev_buf("solve.NUMr", sizeof(float) * plan_r.splits * (size_t)plan_r.split_stride));
+  float* NUMc = io.update_cols
+                    ? static_cast<float*>(h->dev_buf("solve.NUMc", sizeof(float) * plan_c.splits * (size_t)plan_c.split_stride))
+                    : nullptr;
+  if (!NUMr || (io.update_cols && !NUMc)) return -2;
+
+  int* d_off = d_meta;
+  int* d_k = d_meta + R;
+  int* d_done = d_meta + 2 * R;
+  int* d_niter = d_meta + 3 * R;
+  {
+    std::vector<int> hm(4 * R, 0);
+    std::memcpy(hm.data(), off.data(), sizeof(int) * R);
+    std::memcpy(hm.data() + R, io.ks.data(), sizeof(int) * R);
+    CNMF_CUDA_CHECK(cudaMemcpyAsync(d_meta, hm.data(), sizeof(int) * 4 * R, cudaMemcpyHostToDevice, s));
+    CNMF_CUDA_CHECK(cudaStreamSynchronize(s));   // hm goes out of scope
+  }
+  CNMF_CUDA_CHECK(cudaMemsetAsync(d_state, 0, sizeof(double) * 8 * R, s));
+  ConvState st{d_state, d_state + R, d_state + 2 * R, d_done, d_niter};
+  double* d_crossA = d_state + 3 * R;   // finalised scalars: cross / violation of the row half
+  double* d_crossB = d_state + 4 * R;   // ... of the column half
+  double* d_gramR = d_gram;                           // Gram of Fr (e.g. W^T W)
+  double* d_gramC = d_gram + (size_t)R * KMAX * KMAX; // Gram of Fc (e.g. H H^T)
+  double* d_scalA = d_scal_part;
+  double* d_scalB = d_scal_part + (size_t)R * chunks_max;
+
+  BatchMeta bm{d_off, d_k, d_done, R, kp};
+  FactorView fr{io.Fr, tf32 ? io.Fr_hi : nullptr, tf32 ? io.Fr_lo : nullptr, v.n_r, v.ld_r};
+  FactorView fc{io.Fc, tf32 ? io.Fc_hi : nullptr, tf32 ? io.Fc_lo : nullptr, v.n_c, v.ld_c};
+  if (!io.update_cols) { fc.F_hi = nullptr; fc.F_lo = nullptr; }   // never rewritten
+
+  auto gram_of = [&](const FactorView& f, double* gram_out, int chunks) -> int {
+    h->launches += 2;
+    CNMF_TRY(launch_gram_partial(f, bm, d_gram_part, s));
+    return launch_finalize(d_gram_part, gram_out, nullptr, nullptr, chunks, bm, s);
+  };
+  auto finalize_scal = [&](const double* part, double* out, int chunks) -> int {
+    h->launches += 1;
+    return launch_finalize(nullptr, nullptr, part, out, chunks, bm, s);
+  };
+  auto gemm_rows = [&]() -> int {   // NUM_r = Fc * B_rows^T
+    return run_gemm(h, p.precision, io.Fc, io.Fc_hi, io.Fc_lo, SK, v.ld_c, v.B_rows, NUMr, v.ld_r, plan_r, s);
+  };
+  auto gemm_cols = [&]() -> int {   // NUM_c = Fr * B_cols^T
+    return run_gemm(h, p.precision, io.Fr, io.Fr_hi, io.Fr_lo, SK, v.ld_r, v.B_cols, NUMc, v.ld_c, plan_c, s);
+  };
+
+  std::vector<int> h_done(R, 0);
+  auto poll_all_done = [&]() -> int {   // 1 = all done, 0 = not yet, <0 error
+    CNMF_CUDA_CHECK(cudaMemcpyAsync(h_done.data(), d_done, sizeof(int) * R, cudaMemcpyDeviceToHost, s));
+    CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int r = 0; r < R; ++r)
+      if (!h_done[r]) return 0;
+    return 1;
+  };
+
+  const float l1W = (float)p.l1_reg_W, l2W = (float)p.l2_reg_W, l1H = (float)p.l1_reg_H, l2H = (float)p.l2_reg_H;
+  const double normX2 = v.sum_sq;
+  int it = 0;
+
+  if (mu) {
+    // ---------------- multiplicative update (sklearn _nmf.py:726-888) ----------------
+    CNMF_TRY(gram_of(fc, d_gramC, chunks_c));
+    CNMF_TRY(gram_of(fr, d_gramR, chunks_r));
+    if (io.update_cols) {
+      CNMF_TRY(gemm_cols());
+      h->launches += 1;
+      CNMF_TRY(launch_cross(fc, NUMc, plan_c.splits, plan_c.split_stride, bm, d_scalB, s));
+      CNMF_TRY(finalize_scal(d_scalB, d_crossB, chunks_c));
+    } else {
+      CNMF_TRY(gemm_rows());          // H fixed: X H^T is computed once (sklearn caches XHt, _nmf.py:537-548)
+      h->launches += 1;
+      CNMF_TRY(launch_cross(fr, NUMr, plan_r.splits, plan_r.split_stride, bm, d_scalA, s));
+      CNMF_TRY(finalize_scal(d_scalA, d_crossB, chunks_r));
+    }
+    h->launches += 1;
+    CNMF_TRY(launch_mu_check(st, d_crossB, d_gramR, d_gramC, normX2, bm, 0, p.tol, p.max_iter, s));
+
+    for (it = 1; it <= p.max_iter; ++it) {
+      if (io.update_cols) CNMF_TRY(gemm_rows());
+      h->launches += 1;
+      CNMF_TRY(launch_mu_update(fr, NUMr, plan_r.splits, plan_r.split_stride, d_gramC, bm, l1W, l2W,
+                                io.update_cols ? nullptr : d_scalA, s));
+      if (io.update_cols) {
+        CNMF_TRY(gram_of(fr, d_gramR, chunks_r));
+        CNMF_TRY(gemm_cols());
+        h->launches += 1;
+        CNMF_TRY(launch_mu_update(fc, NUMc, plan_c.splits, plan_c.split_stride, d_gramR, bm, l1H, l2H, d_scalB, s));
+        CNMF_TRY(gram_of(fc, d_gramC, chunks_c));
+      }
+      const bool check = (p.tol > 0 && it % 10 == 0) || it == p.max_iter;
+      if (check) {
+        if (io.update_cols) {
+          CNMF_TRY(finalize_scal(d_scalB, d_crossB, chunks_c));
+        } else {
+          CNMF_TRY(gram_of(fr, d_gramR, chunks_r));
+          CNMF_TRY(finalize_scal(d_scalA, d_crossB, chunks_r));
+        }
+        h->launches += 1;
+        // at it == max_iter with it % 10 != 0 sklearn does not test; tol = -1 makes the test never fire
+        const double tol_eff = (p.tol > 0 && it % 10 == 0) ? p.tol : -1.0;
+        CNMF_TRY(launch_mu_check(st, d_crossB, d_gramR, d_gramC, normX2, bm, it, tol_eff, p.max_iter, s));
+        const int all = poll_all_done();
+        if (all < 0) return all;
+        if (all) break;
+      }
+    }
+  } else {
+    // ---------------- coordinate descent (sklearn _nmf.py:399-518, shuffle=False) ----------------
+    const int poll_every = 4;
+    for (it = 1; it <= p.max_iter; ++it) {
+      if (io.update_cols || it == 1) {
+        CNMF_TRY(gram_of(fc, d_gramC, chunks_c));
+        CNMF_TRY(gemm_rows());
+      }
+      h->launches += 1;
+      CNMF_TRY(launch_cd_update(fr, NUMr, plan_r.splits, plan_r.split_stride, d_gramC, bm, l1W, l2W, d_scalA, s));
+      CNMF_TRY(finalize_scal(d_scalA, d_crossA, chunks_r));
+      if (io.update_cols) {
+        CNMF_TRY(gram_of(fr, d_gramR, chunks_r));
+        CNMF_TRY(gemm_cols());
+        h->launches += 1;
+        CNMF_TRY(launch_cd_update(fc, NUMc, plan_c.splits, plan_c.split_stride, d_gramR, bm, l1H, l2H, d_scalB, s));
+        CNMF_TRY(finalize_scal(d_scalB, d_crossB, chunks_c));
+      }
+      h->launches += 1;
+      CNMF_TRY(launch_cd_check(st, d_crossA, io.update_cols ? d_crossB : nullptr, bm, it, p.tol, p.max_iter, s));
+      if (it % poll_every == 0 || it == p.max_iter) {
+        const int all = poll_all_done();
+        if (all < 0) return all;
+        if (all) break;
+      }
+    }
+  }
+
+  // final ||X - Fr^T Fc||_F for every restart (MU already holds it in st.last from its last check;
+  // CD tracks the projected-gradient violation instead, so evaluate the trace form once here)
+  double* d_err = st.last;
+  if (!mu) {
+    int* d_zero = static_cast<int*>(h->dev_buf("solve.zero", sizeof(int) * 2 * R));
+    if (!d_zero) return -2;
+    CNMF_CUDA_CHECK(cudaMemsetAsync(d_zero, 0, sizeof(int) * 2 * R, s));
+    BatchMeta bm0{d_off, d_k, d_zero, R, kp};
+    h->launches += 7;
+    CNMF_TRY(launch_gram_partial(fr, bm0, d_gram_part, s));
+    CNMF_TRY(launch_finalize(d_gram_part, d_gramR, nullptr, nullptr, chunks_r, bm0, s));
+    CNMF_TRY(launch_gram_partial(fc, bm0, d_gram_part, s));
+    CNMF_TRY(launch_finalize(d_gram_part, d_gramC, nullptr, nullptr, chunks_c, bm0, s));
+    if (io.update_cols) {
+      CNMF_TRY(launch_cross(fc, NUMc, plan_c.splits, plan_c.split_stride, bm0, d_scalB, s));
+      CNMF_TRY(launch_finalize(nullptr, nullptr, d_scalB, d_crossB, chunks_c, bm0, s));
+    } else {
+      CNMF_TRY(launch_cross(fr, NUMr, plan_r.splits, plan_r.split_stride, bm0, d_scalA, s));
+      CNMF_TRY(launch_finalize(nullptr, nullptr, d_scalA, d_crossB, chunks_r, bm0, s));
+    }
+    ConvState scratch{d_state + 5 * R, d_state + 6 * R, d_state + 7 * R, d_zero, d_zero + R};
+    CNMF_TRY(launch_mu_check(scratch, d_crossB, d_gramR, d_gramC, normX2, bm0, 0, 0.0, p.max_iter, s));
+    d_err = scratch.last;
+  }
+  io.n_iter.assign(R, 0);
+  io.last.assign(R, 0.0);
+  io.err.assign(R, 0.0);
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(io.n_iter.data(), d_niter, sizeof(int) * R, cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(io.last.data(), st.last, sizeof(double) * R, cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(io.err.data(), d_err, sizeof(double) * R, cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+}  // namespace cnmf

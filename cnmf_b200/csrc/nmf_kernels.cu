@@ -1,0 +1,439 @@
+// Elementwise / reduction kernels of the batched NMF engine (see nmf_kernels.cuh for the layout).
+// All of these are HBM-bound streaming kernels: coalesced along the item (cell / gene) axis,
+// the tiny K x K Gram matrices are broadcast from shared memory, fp64 only for the scalars
+// that feed the convergence decisions.
+#include "nmf_kernels.cuh"
+
+namespace cnmf {
+
+namespace {
+
+constexpr float EPSILON_F32 = 1.1920928955078125e-07f;   // np.finfo(np.float32).eps, sklearn _nmf.py:32
+
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* smem /* >= 32 entries */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  T r = (threadIdx.x < nw) ? smem[threadIdx.x] : T(0);
+  if (warp == 0) r = warp_sum(r);
+  return r;   // valid in thread 0
+}
+
+// ------------------------------------------------------------------ split / transpose / sums
+__global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
+                                  long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x);
+    split_tf32(v.y, h.y, l.y);
+    split_tf32(v.z, h.z, l.z);
+    split_tf32(v.w, h.w, l.w);
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
+  }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ src, int rows, int cols, int ld_src, float* __restrict__ dst,
+                                 float* __restrict__ dst_hi, float* __restrict__ dst_lo, int ld_dst) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(long long)r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;      // dst row = c, dst col = r
+    if (c < cols && r < rows) {
+      const float v = tile[threadIdx.x][i];
+      const long long o = (long long)c * ld_dst + r;
+      if (dst) dst[o] = v;
+      if (dst_hi) {
+        float h, l;
+        split_tf32(v, h, l);
+        dst_hi[o] = h;
+        dst_lo[o] = l;
+      }
+    }
+  }
+}
+
+__global__ void sums_partial_kernel(const float* __restrict__ X, int rows, int cols, int ld, double* __restrict__ part) {
+  __shared__ double sm[32];
+  double s = 0, q = 0;
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const double v = X[(long long)r * ld + c];
+    s += v;
+    q += v * v;
+  }
+  s = block_sum(s, sm);
+  q = block_sum(q, sm);
+  if (threadIdx.x == 0) {
+    part[2 * blockIdx.x] = s;
+    part[2 * blockIdx.x + 1] = q;
+  }
+}
+__global__ void sums_final_kernel(const double* __restrict__ part, int nblocks, double* __restrict__ out2) {
+  __shared__ double sm[32];
+  double s = 0, q = 0;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
+    s += part[2 * i];
+    q += part[2 * i + 1];
+  }
+  s = block_sum(s, sm);
+  q = block_sum(q, sm);
+  if (threadIdx.x == 0) {
+    out2[0] = s;
+    out2[1] = q;
+  }
+}
+
+// ------------------------------------------------------------------ multiplicative update
+template <int KP>
+__global__ void __launch_bounds__(UPD_THREADS)
+mu_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
+                 const double* __restrict__ gram, BatchMeta b, float l1, float l2, double* __restrict__ cross_partial) {
+  const int r = blockIdx.y;
+  if (b.done[r]) return;
+  const int K = b.k[r], o = b.off[r];
+  __shared__ float G[KP][KP + 1];
+  __shared__ double red[32];
+  for (int idx = threadIdx.x; idx < KP * KP; idx += UPD_THREADS) {
+    const int c = idx / KP, i = idx % KP;
+    G[c][i] = (c < K && i < K) ? (float)gram[(long long)r * KMAX * KMAX + c * KMAX + i] : 0.f;
+  }
+  __syncthreads();
+  const int col_begin = blockIdx.x * UPD_COLS_PER_BLOCK;
+  const int col_end = min(f.n, col_begin + UPD_COLS_PER_BLOCK);
+  double cross = 0.0;
+  for (int col = col_begin + threadIdx.x; col < col_end; col += UPD_THREADS) {
+    float fv[KP];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) fv[i] = (i < K) ? f.F[(long long)(o + i) * f.ld + col] : 0.f;
+#pragma unroll
+    for (int c = 0; c < KP; ++c) {
+      if (c < K) {
+        const long long e = (long long)(o + c) * f.ld + col;
+        float num = NUM[e];
+        for (int s = 1; s < nsplit; ++s) num += NUM[s * sstride + e];
+        float den = 0.f;
+#pragma unroll
+        for (int i = 0; i < KP; ++i) den = fmaf(G[c][i], fv[i], den);
+        if (l1 > 0.f) den += l1;
+        if (l2 > 0.f) den += l2 * fv[c];
+        if (den == 0.f) den = EPSILON_F32;
+        const float fn = fv[c] * (num / den);
+        f.F[e] = fn;
+        if (f.F_hi) {
+          float h, l;
+          split_tf32(fn, h, l);
+          f.F_hi[e] = h;
+          f.F_lo[e] = l;
+        }
+        cross += (double)num * (double)fn;
+      }
+    }
+  }
+  if (cross_partial) {
+    cross = block_sum(cross, red);
+    if (threadIdx.x == 0) cross_partial[(long long)r * gridDim.x + blockIdx.x] = cross;
+  }
+}
+
+// ------------------------------------------------------------------ coordinate descent sweep
+template <int KP>
+__global__ void __launch_bounds__(UPD_THREADS)
+cd_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
+                 const double* __restrict__ gram, BatchMeta b, float l1, float l2, double* __restrict__ viol_partial) {
+  const int r = blockIdx.y;
+  if (b.done[r]) return;
+  const int K = b.k[r], o = b.off[r];
+  __shared__ float G[KP][KP + 1];
+  __shared__ double red[32];
+  for (int idx = threadIdx.x; idx < KP * KP; idx += UPD_THREADS) {
+    const int c = idx / KP, i = idx % KP;
+    float g = (c < K && i < K) ? (float)gram[(long long)r * KMAX * KMAX + c * KMAX + i] : 0.f;
+    if (c == i && c < K) g += l2;                       // sklearn _nmf.py:383-385
+    G[c][i] = g;
+  }
+  __syncthreads();
+  const int col_begin = blockIdx.x * UPD_COLS_PER_BLOCK;
+  const int col_end = min(f.n, col_begin + UPD_COLS_PER_BLOCK);
+  double viol = 0.0;
+  for (int col = col_begin + threadIdx.x; col < col_end; col += UPD_THREADS) {
+    float fv[KP];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) fv[i] = (i < K) ? f.F[(long long)(o + i) * f.ld + col] : 0.f;
+#pragma unroll
+    for (int t = 0; t < KP; ++t) {
+      if (t < K) {
+        const long long e = (long long)(o + t) * f.ld + col;
+        float num = NUM[e];
+        for (int s = 1; s < nsplit; ++s) num += NUM[s * sstride + e];
+        float g = l1 - num;                             // -(XHt - l1), sklearn _nmf.py:386-388
+#pragma unroll
+        for (int i = 0; i < KP; ++i) g = fmaf(G[t][i], fv[i], g);
+        const float pg = (fv[t] == 0.f) ? fminf(0.f, g) : g;
+        viol += (double)fabsf(pg);
+        const float h = G[t][t];
+        if (h != 0.f) fv[t] = fmaxf(fv[t] - g / h, 0.f);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < KP; ++t) {
+      if (t < K) {
+        const long long e = (long long)(o + t) * f.ld + col;
+        f.F[e] = fv[t];
+        if (f.F_hi) {
+          float h, l;
+          split_tf32(fv[t], h, l);
+          f.F_hi[e] = h;
+          f.F_lo[e] = l;
+        }
+      }
+    }
+  }
+  if (viol_partial) {
+    viol = block_sum(viol, red);
+    if (threadIdx.x == 0) viol_partial[(long long)r * gridDim.x + blockIdx.x] = viol;
+  }
+}
+
+// ------------------------------------------------------------------ <NUM, F> without update
+__global__ void __launch_bounds__(UPD_THREADS)
+cross_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride, BatchMeta b,
+             double* __restrict__ cross_partial) {
+  const int r = blockIdx.y;
+  if (b.done[r]) return;
+  const int K = b.k[r], o = b.off[r];
+  __shared__ double red[32];
+  const int col_begin = blockIdx.x * UPD_COLS_PER_BLOCK;
+  const int col_end = min(f.n, col_begin + UPD_COLS_PER_BLOCK);
+  double cross = 0.0;
+  for (int col = col_begin + threadIdx.x; col < col_end; col += UPD_THREADS) {
+    for (int c = 0; c < K; ++c) {
+      const long long e = (long long)(o + c) * f.ld + col;
+      float num = NUM[e];
+      for (int s = 1; s < nsplit; ++s) num += NUM[s * sstride + e];
+      cross += (double)num * (double)f.F[e];
+    }
+  }
+  cross = block_sum(cross, red);
+  if (threadIdx.x == 0) cross_partial[(long long)r * gridDim.x + blockIdx.x] = cross;
+}
+
+// ------------------------------------------------------------------ K x K Gram partials
+template <int KP>
+__global__ void __launch_bounds__(KP * KP)
+gram_partial_kernel(FactorView f, BatchMeta b, double* __restrict__ gram_partial) {
+  constexpr int TILE = 128;
+  const int r = blockIdx.y;
+  if (b.done[r]) return;
+  const int K = b.k[r], o = b.off[r];
+  __shared__ float s[KP][TILE + 1];
+  const int c = threadIdx.x / KP, i = threadIdx.x % KP;
+  const int col_begin = blockIdx.x * UPD_COLS_PER_BLOCK;
+  const int col_end = min(f.n, col_begin + UPD_COLS_PER_BLOCK);
+  double acc = 0.0;
+  for (int c0 = col_begin; c0 < col_end; c0 += TILE) {
+    for (int idx = threadIdx.x; idx < KP * TILE; idx += KP * KP) {
+      const int row = idx / TILE, cc = idx % TILE;
+      const int col = c0 + cc;
+      s[row][cc] = (row < K && col < col_end) ? f.F[(long long)(o + row) * f.ld + col] : 0.f;
+    }
+    __syncthreads();
+    float a = 0.f;
+#pragma unroll 16
+    for (int j = 0; j < TILE; ++j) a = fmaf(s[c][j], s[i][j], a);
+    acc += (double)a;
+    __syncthreads();
+  }
+  gram_partial[((long long)r * gridDim.x + blockIdx.x) * (KP * KP) + threadIdx.x] = acc;
+}
+
+__global__ void finalize_kernel(const double* __restrict__ gram_partial, double* __restrict__ gram,
+                                const double* __restrict__ scal_partial, double* __restrict__ scal, int chunks,
+                                BatchMeta b) {
+  const int r = blockIdx.x;
+  if (b.done[r]) return;
+  const int KP = b.kp;
+  if (gram_partial) {
+    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
+      double a = 0.0;
+      for (int ch = 0; ch < chunks; ++ch) a += gram_partial[((long long)r * chunks + ch) * (KP * KP) + e];
+      const int c = e / KP, i = e % KP;
+      gram[(long long)r * KMAX * KMAX + c * KMAX + i] = a;
+    }
+  }
+  if (scal_partial && threadIdx.x == 0) {
+    double a = 0.0;
+    for (int ch = 0; ch < chunks; ++ch) a += scal_partial[(long long)r * chunks + ch];
+    scal[r] = a;
+  }
+}
+
+// ------------------------------------------------------------------ convergence
+__global__ void mu_check_kernel(ConvState st, const double* __restrict__ cross, const double* __restrict__ gramA,
+                                const double* __restrict__ gramB, double normX2, BatchMeta b, int it, double tol,
+                                int max_iter) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= b.R || st.done[r]) return;
+  const int K = b.k[r];
+  double dot = 0.0;
+  for (int c = 0; c < K; ++c)
+    for (int i = 0; i < K; ++i)
+      dot += gramA[(long long)r * KMAX * KMAX + c * KMAX + i] * gramB[(long long)r * KMAX * KMAX + c * KMAX + i];
+  const double err = sqrt(fmax(normX2 - 2.0 * cross[r] + dot, 0.0));
+  st.last[r] = err;
+  if (it == 0) {
+    st.err0[r] = err;
+    st.prev[r] = err;
+    return;
+  }
+  if ((st.prev[r] - err) / st.err0[r] < tol) {
+    st.done[r] = 1;
+    st.n_iter[r] = it;
+  } else {
+    st.prev[r] = err;
+    if (it >= max_iter) {
+      st.done[r] = 1;
+      st.n_iter[r] = it;
+    }
+  }
+}
+
+__global__ void cd_check_kernel(ConvState st, const double* __restrict__ violA, const double* __restrict__ violB,
+                                BatchMeta b, int it, double tol, int max_iter) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= b.R || st.done[r]) return;
+  const double viol = violA[r] + (violB ? violB[r] : 0.0);
+  st.last[r] = viol;
+  if (it == 1) st.err0[r] = viol;
+  const double v0 = st.err0[r];
+  if (v0 == 0.0 || viol / v0 <= tol || it >= max_iter) {
+    st.done[r] = 1;
+    st.n_iter[r] = it;
+  }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ src_off,
+                                   float* __restrict__ dst, const int* __restrict__ dst_off,
+                                   const int* __restrict__ k, int ld) {
+  const int r = blockIdx.x / KMAX, c = blockIdx.x % KMAX;
+  if (c >= k[r]) return;
+  const float4* s = reinterpret_cast<const float4*>(src + (long long)(src_off[r] + c) * ld);
+  float4* d = reinterpret_cast<float4*>(dst + (long long)(dst_off[r] + c) * ld);
+  for (int i = threadIdx.x; i < ld / 4; i += blockDim.x) d[i] = s[i];
+}
+
+}  // namespace
+
+// ============================================================================ launchers
+int launch_split_tf32(const float* src, float* hi, float* lo, long long n_elems, cudaStream_t s) {
+  CNMF_REQUIRE(n_elems % 4 == 0, "split_tf32: element count must be a multiple of 4");
+  const long long n4 = n_elems / 4;
+  if (n4 == 0) return 0;
+  const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  split_tf32_kernel<<<blocks, 256, 0, s>>>(src, hi, lo, n4);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_transpose(const float* src, int rows, int cols, int ld_src, float* dst, float* dst_hi, float* dst_lo,
+                     int ld_dst, cudaStream_t s) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  CNMF_REQUIRE(grid.y <= 65535, "transpose: too many rows for one launch");
+  transpose_kernel<<<grid, block, 0, s>>>(src, rows, cols, ld_src, dst, dst_hi, dst_lo, ld_dst);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_matrix_sums(const float* X, int rows, int cols, int ld, double* out2, double* scratch, int scratch_len,
+                       cudaStream_t s) {
+  int blocks = 148 * 8;
+  if (2 * blocks > scratch_len) blocks = scratch_len / 2;
+  CNMF_REQUIRE(blocks >= 1, "matrix_sums: scratch too small");
+  sums_partial_kernel<<<blocks, 256, 0, s>>>(X, rows, cols, ld, scratch);
+  sums_final_kernel<<<1, 256, 0, s>>>(scratch, blocks, out2);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+#define CNMF_DISPATCH_KP(kp, CALL)                                   \
+  switch (kp) {                                                      \
+    case 8: { constexpr int KP = 8; CALL; } break;                   \
+    case 16: { constexpr int KP = 16; CALL; } break;                 \
+    case 32: { constexpr int KP = 32; CALL; } break;                 \
+    default: set_last_error("kp must be 8, 16 or 32"); return -1;    \
+  }
+
+int launch_mu_update(const FactorView& f, const float* NUM, int nsplit, long long sstride, const double* gram,
+                     const BatchMeta& b, float l1, float l2, double* cross_partial, cudaStream_t s) {
+  dim3 grid(col_chunks(f.n), b.R);
+  CNMF_DISPATCH_KP(b.kp, (mu_update_kernel<KP><<<grid, UPD_THREADS, 0, s>>>(f, NUM, nsplit, sstride, gram, b, l1, l2,
+                                                                             cross_partial)));
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_cd_update(const FactorView& f, const float* NUM, int nsplit, long long sstride, const double* gram,
+                     const BatchMeta& b, float l1, float l2, double* viol_partial, cudaStream_t s) {
+  dim3 grid(col_chunks(f.n), b.R);
+  CNMF_DISPATCH_KP(b.kp, (cd_update_kernel<KP><<<grid, UPD_THREADS, 0, s>>>(f, NUM, nsplit, sstride, gram, b, l1, l2,
+                                                                             viol_partial)));
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_cross(const FactorView& f, const float* NUM, int nsplit, long long sstride, const BatchMeta& b,
+                 double* cross_partial, cudaStream_t s) {
+  dim3 grid(col_chunks(f.n), b.R);
+  cross_kernel<<<grid, UPD_THREADS, 0, s>>>(f, NUM, nsplit, sstride, b, cross_partial);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_gram_partial(const FactorView& f, const BatchMeta& b, double* gram_partial, cudaStream_t s) {
+  dim3 grid(col_chunks(f.n), b.R);
+  CNMF_DISPATCH_KP(b.kp, (gram_partial_kernel<KP><<<grid, KP * KP, 0, s>>>(f, b, gram_partial)));
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_finalize(const double* gram_partial, double* gram, const double* scal_partial, double* scal, int chunks,
+                    const BatchMeta& b, cudaStream_t s) {
+  finalize_kernel<<<b.R, 256, 0, s>>>(gram_partial, gram, scal_partial, scal, chunks, b);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_mu_check(const ConvState& st, const double* cross, const double* gramA, const double* gramB, double normX2,
+                    const BatchMeta& b, int it, double tol, int max_iter, cudaStream_t s) {
+  mu_check_kernel<<<(b.R + 127) / 128, 128, 0, s>>>(st, cross, gramA, gramB, normX2, b, it, tol, max_iter);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_cd_check(const ConvState& st, const double* violA, const double* violB, const BatchMeta& b, int it,
+                    double tol, int max_iter, cudaStream_t s) {
+  cd_check_kernel<<<(b.R + 127) / 128, 128, 0, s>>>(st, violA, violB, b, it, tol, max_iter);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_gather_rows(const float* src, const int* src_off, float* dst, const int* dst_off, const int* k, int R,
+                       int ld, cudaStream_t s) {
+  if (R == 0) return 0;
+  gather_rows_kernel<<<R * KMAX, 128, 0, s>>>(src, src_off, dst, dst_off, k, ld);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cnmf

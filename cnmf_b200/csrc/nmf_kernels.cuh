@@ -1,0 +1,93 @@
+// Device kernels of the batched NMF engine (declarations; definitions in nmf_kernels.cu).
+//
+// Layout ("packed factor"): all live restarts are stacked along rows. Restart r owns rows
+// [off[r], off[r]+k[r]) of every SK x n factor array (SK = sum of k).  Wt is the transposed
+// usage matrix (SK x cells), H the spectra (SK x genes).  Row stride ld = pad_ld(n) floats,
+// padding columns stay zero.  Because both factors are stored "components x items", the W half
+// and the H half of an iteration are the SAME kernels with the roles of the arrays swapped.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace cnmf {
+
+constexpr int UPD_THREADS = 256;
+constexpr int UPD_COLS_PER_BLOCK = 2048;   // columns handled by one block of the update / gram kernels
+
+struct FactorView {
+  float* F;        // SK x ld, in/out
+  float* F_hi;     // optional tf32 pieces (nullptr in fp32 mode)
+  float* F_lo;
+  int n;           // valid columns
+  int ld;
+};
+
+struct BatchMeta {
+  const int* off;  // [R] first packed row of restart r
+  const int* k;    // [R] n_components of restart r
+  const int* done; // [R] 1 = converged, frozen
+  int R;
+  int kp;          // 8, 16 or 32: >= max k in the batch (template dispatch)
+};
+
+inline int col_chunks(int n) { return (n + UPD_COLS_PER_BLOCK - 1) / UPD_COLS_PER_BLOCK; }
+
+// x -> (hi, lo) tf32 pieces, elementwise over rows x ld (padding included)
+int launch_split_tf32(const float* src, float* hi, float* lo, long long n_elems, cudaStream_t s);
+
+// dst (cols x ld_dst) = src (rows x ld_src)^T ; optionally also emits tf32 pieces of dst
+int launch_transpose(const float* src, int rows, int cols, int ld_src, float* dst, float* dst_hi, float* dst_lo,
+                     int ld_dst, cudaStream_t s);
+
+// out[0] = sum(X), out[1] = sum(X^2) over the valid rows x cols region, fp64
+int launch_matrix_sums(const float* X, int rows, int cols, int ld, double* out2, double* scratch, int scratch_len,
+                       cudaStream_t s);
+
+// Multiplicative update (sklearn _nmf.py:535-549,610-624 / :633-635,696-721):
+//   F[c, j] <- F[c, j] * NUM[c, j] / max-style-guard( sum_i gram[c, i] F[i, j] + l1 + l2 F[c, j] )
+// NUM = sum over `nsplit` split-K slices (stride num_split_stride elements).
+// cross_partial[r * chunks + chunk] = sum NUM * F_new (fp64), used by the trace-form error.
+int launch_mu_update(const FactorView& f, const float* NUM, int nsplit, long long num_split_stride,
+                     const double* gram, const BatchMeta& b, float l1, float l2, double* cross_partial,
+                     cudaStream_t s);
+
+// One coordinate-descent sweep over the K coordinates of every column (sklearn _cdnmf_fast.pyx:8-37):
+//   viol_partial[r * chunks + chunk] = sum |projected gradient|
+int launch_cd_update(const FactorView& f, const float* NUM, int nsplit, long long num_split_stride,
+                     const double* gram, const BatchMeta& b, float l1, float l2, double* viol_partial,
+                     cudaStream_t s);
+
+// cross_partial[r*chunks+chunk] = sum_{c,j} NUM[c,j] * F[c,j]   (no update; used for the error at init)
+int launch_cross(const FactorView& f, const float* NUM, int nsplit, long long num_split_stride, const BatchMeta& b,
+                 double* cross_partial, cudaStream_t s);
+
+// gram_partial[(r*chunks+chunk)*kp*kp + c*kp + i] = sum_j F[c,j] F[i,j] over the chunk's columns
+int launch_gram_partial(const FactorView& f, const BatchMeta& b, double* gram_partial, cudaStream_t s);
+
+// gram[r][c*KMAX+i] = sum over chunks (fixed order -> deterministic); scal[r] = sum over chunks of scal_partial
+int launch_finalize(const double* gram_partial, double* gram, const double* scal_partial, double* scal, int chunks,
+                    const BatchMeta& b, cudaStream_t s);
+
+struct ConvState {     // device arrays, one entry per restart
+  double* err0;        // MU: error at init            CD: violation of iteration 1
+  double* prev;        // MU: error at the last check
+  double* last;        // last evaluated error / violation (reported back)
+  int* done;
+  int* n_iter;
+};
+
+// MU: err = sqrt(max(normX2 - 2 cross + <gramA, gramB>, 0)); it==0 initialises err0/prev;
+// otherwise stop if (prev - err)/err0 < tol (sklearn _nmf.py:867-879).
+int launch_mu_check(const ConvState& st, const double* cross, const double* gramA, const double* gramB, double normX2,
+                    const BatchMeta& b, int it, double tol, int max_iter, cudaStream_t s);
+
+// CD: viol = violA (+ violB); it==1 sets viol0; stop if viol0 == 0 or viol/viol0 <= tol (sklearn _nmf.py:504-516)
+int launch_cd_check(const ConvState& st, const double* violA, const double* violB, const BatchMeta& b, int it,
+                    double tol, int max_iter, cudaStream_t s);
+
+// packed-row gather: dst rows [dst_off[r], +k[r]) <- src rows [src_off[r], +k[r])  for r < R (compaction / output)
+int launch_gather_rows(const float* src, const int* src_off, float* dst, const int* dst_off, const int* k, int R,
+                       int n_ld, cudaStream_t s);
+
+}  // namespace cnmf

@@ -1,0 +1,192 @@
+"""Thin Python layer over the C ABI: Engine (handle) and Dataset objects.
+
+Host logic only -- argument marshalling and sklearn-compatible parameter scaling.  All
+arithmetic happens inside libcnmf_b200.so on the GPU.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import NmfParams, PRECISION_FP32, PRECISION_TF32X3, SOLVER_CD, SOLVER_MU, check, f32c, ptr
+
+_DEFAULT_PRECISION = PRECISION_TF32X3
+
+
+def precision_code(p):
+    if p in (PRECISION_FP32, PRECISION_TF32X3):
+        return p
+    return {"fp32": PRECISION_FP32, "tf32x3": PRECISION_TF32X3}[p]
+
+
+def make_params(nmf_kwargs, n_samples, n_features, precision):
+    """nmf_kwargs dict of cnmf.py:618-631 -> struct cnmf_nmf_params.
+
+    Regularisation scaling follows sklearn/decomposition/_nmf.py:1249-1260.  Only what the CUDA
+    path implements is accepted; anything else raises (no silent fallback)."""
+    solver = nmf_kwargs.get("solver", "mu")
+    beta = nmf_kwargs.get("beta_loss", "frobenius")
+    if beta not in ("frobenius", 2, 2.0):
+        raise NotImplementedError("cnmf_b200: only the Frobenius loss is implemented on the CUDA path (got %r)" % (beta,))
+    if nmf_kwargs.get("init", "random") != "random":
+        raise NotImplementedError("cnmf_b200: only init='random' is implemented on the CUDA path")
+    if solver not in ("mu", "cd"):
+        raise ValueError("solver must be 'mu' or 'cd'")
+    alpha_W = float(nmf_kwargs.get("alpha_W", 0.0))
+    alpha_H = nmf_kwargs.get("alpha_H", 0.0)
+    alpha_H = alpha_W if alpha_H == "same" else float(alpha_H)
+    l1_ratio = float(nmf_kwargs.get("l1_ratio", 0.0))
+    p = NmfParams()
+    p.solver = SOLVER_MU if solver == "mu" else SOLVER_CD
+    p.precision = precision_code(precision)
+    p.max_iter = int(nmf_kwargs.get("max_iter", 1000))
+    p.tol = float(nmf_kwargs.get("tol", 1e-4))
+    p.l1_reg_W = n_features * alpha_W * l1_ratio
+    p.l1_reg_H = n_samples * alpha_H * l1_ratio
+    p.l2_reg_W = n_features * alpha_W * (1.0 - l1_ratio)
+    p.l2_reg_H = n_samples * alpha_H * (1.0 - l1_ratio)
+    return p
+
+
+class Engine:
+    """One per process and GPU: owns the library handle and its cached device workspace."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        check(self.lib.cnmf_create(ctypes.byref(self._h), int(device)))
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            self.lib.cnmf_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self):
+        return int(self.lib.cnmf_launch_count(self._h))
+
+    def dataset(self, X, precision=_DEFAULT_PRECISION, stream=None):
+        return Dataset(self, X, precision, stream)
+
+    def gemm_abt(self, A, B, precision=_DEFAULT_PRECISION, splits=1, reps=1):
+        """C = A @ B.T through the solver's GEMM kernels (test / micro-benchmark hook)."""
+        A, B = f32c(A), f32c(B)
+        M, Kd = A.shape
+        N = B.shape[0]
+        assert B.shape[1] == Kd
+        C = np.empty((M, N), np.float32)
+        ms = ctypes.c_float(0)
+        check(self.lib.cnmf_gemm_abt_host(self._h, precision_code(precision), ptr(A), ptr(B), M, N, Kd, splits,
+                                          ptr(C), reps, ctypes.byref(ms), None))
+        return C, float(ms.value)
+
+
+class Dataset:
+    """A cells x genes matrix resident on the GPU (norm_counts.X / tpm.X of the reference)."""
+
+    def __init__(self, engine, X, precision=_DEFAULT_PRECISION, stream=None, _handle=None):
+        self.engine = engine
+        self.lib = engine.lib
+        self.precision = precision_code(precision)
+        self._d = ctypes.c_void_p()
+        if _handle is not None:
+            self._d = _handle
+        else:
+            if hasattr(X, "toarray"):       # scipy sparse: the CUDA path is dense
+                X = X.toarray()
+            X = f32c(X)
+            n, g = X.shape
+            check(self.lib.cnmf_dataset_create(engine._h, ptr(X), n, g, g, 0, self.precision, stream,
+                                               ctypes.byref(self._d)))
+        n, g = ctypes.c_int(), ctypes.c_int()
+        check(self.lib.cnmf_dataset_shape(self._d, ctypes.byref(n), ctypes.byref(g)))
+        self.shape = (n.value, g.value)
+
+    def close(self):
+        if self._d:
+            self.lib.cnmf_dataset_destroy(self._d)
+            self._d = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sums(self):
+        s, q = ctypes.c_double(), ctypes.c_double()
+        check(self.lib.cnmf_dataset_sums(self._d, ctypes.byref(s), ctypes.byref(q)))
+        return s.value, q.value
+
+    def col_stats(self):
+        g = self.shape[1]
+        mean, var = np.empty(g), np.empty(g)
+        check(self.lib.cnmf_dataset_col_stats(self._d, ptr(mean), ptr(var), None))
+        return mean, var
+
+    def from_columns(self, cols, scale):
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        scale = f32c(scale)
+        out = ctypes.c_void_p()
+        check(self.lib.cnmf_dataset_from_columns(self._d, ptr(cols), ptr(scale), len(cols), None, ctypes.byref(out)))
+        return Dataset(self.engine, None, self.precision, _handle=out)
+
+    def params(self, nmf_kwargs):
+        return make_params(nmf_kwargs, self.shape[0], self.shape[1], self.precision)
+
+    def factorize(self, ks, seeds, nmf_kwargs, return_usages=False, W0=None, H0=None):
+        """All restarts (ks[r], seeds[r]) at once.  Returns (spectra_list, usages_list|None, n_iter, err)."""
+        ks = np.ascontiguousarray(ks, dtype=np.int32)
+        R = len(ks)
+        SK = int(ks.sum())
+        n, g = self.shape
+        p = self.params(nmf_kwargs)
+        spectra = np.empty((SK, g), np.float32)
+        usages = np.empty((SK, n), np.float32) if return_usages else None
+        n_iter = np.zeros(R, np.int32)
+        err = np.zeros(R, np.float64)
+        if W0 is None:
+            seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+            check(self.lib.cnmf_factorize(self._d, R, ptr(ks), ptr(seeds), ctypes.byref(p), ptr(spectra), ptr(usages),
+                                          ptr(n_iter), ptr(err), None))
+        else:
+            W0, H0 = f32c(W0), f32c(H0)      # packed (SK x n), (SK x g)
+            assert W0.shape == (SK, n) and H0.shape == (SK, g)
+            check(self.lib.cnmf_factorize_init(self._d, R, ptr(ks), ptr(W0), ptr(H0), ctypes.byref(p), ptr(spectra),
+                                               ptr(usages), ptr(n_iter), ptr(err), None))
+        offs = np.concatenate([[0], np.cumsum(ks)])
+        sp = [spectra[offs[r]:offs[r + 1]] for r in range(R)]
+        us = [usages[offs[r]:offs[r + 1]].T for r in range(R)] if return_usages else None
+        return sp, us, n_iter, err
+
+    def refit(self, fixed, nmf_kwargs, transposed=False):
+        """NMF with `fixed` held constant (update_H=False).  transposed=False: fixed = H (k x genes),
+        returns W (cells x k).  transposed=True: fixed = W^T (k x cells), returns H^T (genes x k)."""
+        fixed = f32c(fixed)
+        k = fixed.shape[0]
+        n, g = self.shape
+        n_r, n_c = (g, n) if transposed else (n, g)
+        assert fixed.shape[1] == n_c
+        p = make_params(nmf_kwargs, n_r, n_c, self.precision)
+        out = np.empty((n_r, k), np.float32)
+        it = ctypes.c_int32(0)
+        err = ctypes.c_double(0)
+        check(self.lib.cnmf_refit(self._d, 1 if transposed else 0, k, ptr(fixed), ctypes.byref(p), ptr(out),
+                                  ctypes.byref(it), ctypes.byref(err), None))
+        return out, int(it.value), float(err.value)
+
+    def project_rows(self, Ut):
+        """Ut (k x cells) @ X -> (k x genes)."""
+        Ut = f32c(Ut)
+        k = Ut.shape[0]
+        assert Ut.shape[1] == self.shape[0]
+        out = np.empty((k, self.shape[1]), np.float32)
+        check(self.lib.cnmf_project_rows(self._d, k, ptr(Ut), ptr(out), None))
+        return out

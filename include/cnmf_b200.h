@@ -1,0 +1,148 @@
+/* cnmf_b200 -- C ABI of the B200-native consensus-NMF hot path.
+ *
+ * Plain C, plain pointers and sizes, no torch / C++ types.  This is the boundary a reference
+ * maintainer binds instead of scikit-learn at the seam
+ *
+ *     cNMF._nmf(X, nmf_kwargs) -> (spectra, usages)          /root/reference/src/cnmf/cnmf.py:661-674
+ *
+ * which the reference calls from cNMF.factorize (cnmf.py:735-745, one call per (k, seed)
+ * restart) and cNMF.refit_usage (cnmf.py:776-802, update_H=False), plus the numeric steps of
+ * cNMF.consensus (cnmf.py:882-975).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; cnmf_last_error() gives the message
+ *     (thread-local).  -1 = invalid argument, -2 = CUDA error, -3 = unsupported.
+ *   - "host" pointers are ordinary (ideally pinned) host memory; "dev" pointers are device
+ *     memory of the device the handle was created on (e.g. torch.Tensor.data_ptr()).
+ *   - matrices are dense row-major fp32; `ld` = row stride in elements.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are
+ *     synchronous with respect to the host on return unless stated otherwise.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef CNMF_B200_H
+#define CNMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNMF_B200_ABI_VERSION 1
+#define CNMF_MAX_COMPONENTS 32          /* largest n_components per restart on the CUDA path */
+
+typedef struct cnmf_handle_s* cnmf_handle_t;
+typedef struct cnmf_dataset_s* cnmf_dataset_t;
+
+enum { CNMF_SOLVER_MU = 0, CNMF_SOLVER_CD = 1 };            /* yaml 'solver': cnmf.py:618-631 */
+enum { CNMF_PRECISION_FP32 = 0, CNMF_PRECISION_TF32X3 = 1 }; /* FFMA  |  tcgen05 3xTF32 (default) */
+
+/* Mirrors the nmf_kwargs dict of cnmf.py:618-627 after sklearn's own scaling of the
+ * regularisation (sklearn/decomposition/_nmf.py:1249-1260): l1_reg_W = n_features*alpha_W*l1_ratio ... */
+typedef struct cnmf_nmf_params {
+  int32_t solver;        /* CNMF_SOLVER_* */
+  int32_t precision;     /* CNMF_PRECISION_* */
+  int32_t max_iter;      /* 'max_iter' (cnmf.py:625) */
+  int32_t reserved;
+  double tol;            /* 'tol' (cnmf.py:624) */
+  double l1_reg_W, l2_reg_W, l1_reg_H, l2_reg_H;
+} cnmf_nmf_params;
+
+/* ---- library / handle -------------------------------------------------------------- */
+int cnmf_abi_version(void);
+const char* cnmf_last_error(void);
+int cnmf_create(cnmf_handle_t* out, int device);
+int cnmf_destroy(cnmf_handle_t h);
+/* number of kernels this library has launched through the handle since creation */
+long long cnmf_launch_count(cnmf_handle_t h);
+
+/* ---- dataset: a cells x genes matrix made resident on the device ------------------- */
+/* Replaces `norm_counts.X` / `tpm.X` handed to _nmf (cnmf.py:726,741,873,919,950-952).
+ * Builds the device-side forms both GEMM orientations need (X, X^T, tf32 pieces) and
+ * sum(X), sum(X^2).  `src_is_device` = 0: X is host memory (copied H2D inside the call). */
+int cnmf_dataset_create(cnmf_handle_t h, const float* X, int n_rows, int n_cols, long long ld,
+                        int src_is_device, int precision, void* stream, cnmf_dataset_t* out);
+/* new dataset = src[:, cols] * col_scale (cnmf.py:965-969: tpm[:, hvgs] / std) */
+int cnmf_dataset_from_columns(cnmf_dataset_t src, const int32_t* cols_host, const float* col_scale_host,
+                              int n_cols, void* stream, cnmf_dataset_t* out);
+int cnmf_dataset_destroy(cnmf_dataset_t d);
+int cnmf_dataset_shape(cnmf_dataset_t d, int* n_rows, int* n_cols);
+int cnmf_dataset_sums(cnmf_dataset_t d, double* sum, double* sum_sq);
+/* per-column mean and population variance (StandardScaler(with_mean=False), cnmf.py:131-134) */
+int cnmf_dataset_col_stats(cnmf_dataset_t d, double* mean_host, double* var_host, void* stream);
+
+/* ---- random init (sklearn _nmf.py:296-307; host RNG, bit-exact numpy legacy stream) -- */
+/* Writes |avg*z| as fp32: H (k x n_features, row stride ldH) first, then W stored transposed
+ * Wt (k x n_samples, row stride ldW).  Pure host code (no CUDA). */
+int cnmf_random_init_host(uint32_t seed, double avg, int n_samples, int n_features, int k,
+                          float* Wt, long long ldW, float* H, long long ldH);
+
+/* ---- batched factorize: replaces the restart loop of cNMF.factorize ---------------- */
+/* For r in [0, n_restarts): one NMF of the dataset with n_components = ks[r] and
+ * random_state = seeds[r] (cnmf.py:738-741), all restarts advanced together on the GPU.
+ *   spectra_host : packed (sum ks) x n_cols, row stride n_cols; restart r owns rows
+ *                  [sum ks[0..r), +ks[r])  -- what factorize saves per restart (cnmf.py:742-745)
+ *   usages_host  : optional (may be NULL; the reference discards W) packed (sum ks) x n_rows,
+ *                  i.e. W^T per restart
+ *   n_iter_host  : optional [n_restarts] iterations run;  err_host: optional [n_restarts]
+ *                  final ||X - WH||_F (mu) or last projected-gradient violation (cd) */
+int cnmf_factorize(cnmf_dataset_t d, int n_restarts, const int32_t* ks, const uint32_t* seeds,
+                   const cnmf_nmf_params* params, float* spectra_host, float* usages_host,
+                   int32_t* n_iter_host, double* err_host, void* stream);
+
+/* Same, but initial factors are supplied (host, packed like the outputs) instead of seeds. */
+int cnmf_factorize_init(cnmf_dataset_t d, int n_restarts, const int32_t* ks, const float* Wt0_host,
+                        const float* H0_host, const cnmf_nmf_params* params, float* spectra_host,
+                        float* usages_host, int32_t* n_iter_host, double* err_host, void* stream);
+
+/* ---- NNLS refit: replaces cNMF.refit_usage / refit_spectra (cnmf.py:776-820) ------- */
+/* NMF with one factor fixed (sklearn update_H=False), same solver as factorize (cnmf.py:792).
+ * transposed = 0 (refit_usage,  cnmf.py:798):  fixed_host = H   (k x n_cols), out_host = W (n_rows x k)
+ * transposed = 1 (refit_spectra, cnmf.py:820): fixed_host = W^T (k x n_rows), out_host = H^T (n_cols x k)
+ * W0 follows sklearn _nmf.py:1223-1228 ('mu': sqrt(X.mean()/k) constant, 'cd': zeros).
+ * err_host (optional): final ||X - W H||_F (its square is the prediction error of cnmf.py:926-930). */
+int cnmf_refit(cnmf_dataset_t d, int transposed, int k, const float* fixed_host, const cnmf_nmf_params* params,
+               float* out_host, int32_t* n_iter_host, double* err_host, void* stream);
+
+/* out (k x n_cols) = Ut (k x n_rows) * X : the X^T Y accumulator of efficient_ols_all_cols
+ * (cnmf.py:98-119) as one tensor-core GEMM; the caller centres U (see cnmf_b200/consensus.py). */
+int cnmf_project_rows(cnmf_dataset_t d, int k, const float* Ut_host, float* out_host, void* stream);
+
+/* test / micro-benchmark hook: C (M x N) = A (M x Kd) * B (N x Kd)^T through the same GEMM kernels the
+ * solver uses (precision selects FFMA or tcgen05 3xTF32); reps > 1 reports mean device ms per launch. */
+int cnmf_gemm_abt_host(cnmf_handle_t h, int precision, const float* A, const float* B, int M, int N, int Kd,
+                       int splits, float* C, int reps, float* ms_out, void* stream);
+
+/* ---- consensus kernels (cnmf.py:882-916) on a stacked-spectra matrix S (R x G, device, row stride ld) -- */
+/* rows / ||row||_2 in place (cnmf.py:882) */
+int cnmf_l2_normalize_rows(cnmf_handle_t h, float* S_dev, int R, int G, int ld, void* stream);
+/* local density (cnmf.py:891-896): density[i] = (sum of the n_neighbors+1 smallest entries of row i of the
+ * Euclidean distance matrix, self-distance 0 included) / n_neighbors.  D_dev: optional R x R output
+ * (ld = R) for the clustergram; NULL keeps it in the library's workspace. Asynchronous on `stream`. */
+int cnmf_local_density(cnmf_handle_t h, const float* S_dev, int R, int G, int ld, int n_neighbors,
+                       float* density_dev, float* D_dev, void* stream);
+/* per-column mean and population variance of a device matrix (KMeans tolerance, sklearn _kmeans.py:285-293) */
+int cnmf_col_stats_dev(cnmf_handle_t h, const float* S_dev, int R, int G, int ld, double* mean_host,
+                       double* var_host, void* stream);
+/* dst row i = src row idx[i] (density filter compaction, cnmf.py:903-904) */
+int cnmf_gather_rows(cnmf_handle_t h, const float* src_dev, int ld_src, const int32_t* idx_host, int n, int G,
+                     float* dst_dev, int ld_dst, void* stream);
+/* squared Euclidean distances from rows idx[0..n_c) of S to every row of S -> out_host (n_c x R):
+ * candidate scoring of k-means++ (sklearn _kmeans.py:231-262; the random draws stay on the host) */
+int cnmf_sq_dists_to_rows(cnmf_handle_t h, const float* S_dev, int R, int G, int ld, const int32_t* idx_host,
+                          int n_c, float* out_host, void* stream);
+/* one Lloyd E+M step (sklearn _k_means_lloyd.pyx:168-219): labels_dev updated in place (first minimum wins),
+ * mind_dev[i] = squared distance to the assigned centre; optional host outputs: per-cluster fp64 column
+ * sums (K x G) + counts, number of labels that changed, inertia = sum(mind). */
+int cnmf_kmeans_assign(cnmf_handle_t h, const float* S_dev, int R, int G, int ld, const float* centers_host, int K,
+                       int32_t* labels_dev, double* sums_host, int32_t* counts_host, float* mind_dev,
+                       int32_t* n_changed_host, double* inertia_host, void* stream);
+/* per-cluster per-gene median (pandas groupby().median(), cnmf.py:913), rows then divided by their sum
+ * (cnmf.py:916) -> M_dev (K x ldm). Asynchronous on `stream`. */
+int cnmf_cluster_median(cnmf_handle_t h, const float* S_dev, int R, int G, int ld, const int32_t* labels_dev, int K,
+                        float* M_dev, int ldm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNMF_B200_H */

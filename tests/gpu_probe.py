@@ -1,0 +1,180 @@
+#!/usr/bin/env python
+"""GPU bring-up probe (not a pytest file): run one stage per process so that a hung kernel
+only costs its own `timeout`.  Usage on the GPU box:
+
+    for s in gemm_fp32 gemm_tf32 nmf_fp32 nmf_tf32 perf; do timeout 300 python tests/gpu_probe.py $s; done
+"""
+import json
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from cnmf_b200.engine import Engine  # noqa: E402
+from cnmf_golden import load_golden  # noqa: E402
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b))
+
+
+def stage_gemm(precision):
+    eng = Engine()
+    rng = np.random.RandomState(0)
+    shapes = [(128, 256, 32, 1), (128, 256, 64, 1), (128, 256, 2048, 1), (256, 512, 128, 1), (200, 300, 100, 1),
+              (7, 1000, 500, 1), (70, 40, 33, 1), (1000, 2000, 2000, 1), (300, 500, 4000, 4), (1000, 2000, 20000, 9)]
+    for (M, N, K, sp) in shapes:
+        A = np.abs(rng.randn(M, K)).astype(np.float32)
+        B = np.abs(rng.randn(N, K)).astype(np.float32)
+        C, _ = eng.gemm_abt(A, B, precision=precision, splits=sp)
+        ref = A.astype(np.float64) @ B.astype(np.float64).T
+        bad = int(np.isnan(C).sum())
+        print("gemm %s M=%d N=%d K=%d splits=%d rel=%.3e maxabs=%.3e nan=%d" % (
+            precision, M, N, K, sp, rel(C, ref), float(np.abs(C - ref).max()), bad), flush=True)
+    # signed inputs as well (the OLS projection uses centred usages)
+    A = rng.randn(64, 1000).astype(np.float32)
+    B = rng.randn(300, 1000).astype(np.float32)
+    C, _ = eng.gemm_abt(A, B, precision=precision)
+    print("gemm %s signed rel=%.3e" % (precision, rel(C, A.astype(np.float64) @ B.astype(np.float64).T)), flush=True)
+
+
+def stage_nmf(precision):
+    eng = Engine()
+    for tag in ("sim_mu", "sim_cd"):
+        g = load_golden(tag)
+        ds = eng.dataset(g["X"], precision=precision)
+        kw = dict(solver=g["solver"], tol=1e-4, max_iter=1000, alpha_W=0.0, alpha_H=0.0, l1_ratio=0.0)
+        table = g["table"]
+        t0 = time.time()
+        sp, us, n_iter, err = ds.factorize(table[:, 0], table[:, 2], kw, return_usages=True)
+        dt = time.time() - t0
+        worst = 0.0
+        for r, (k, it, seed) in enumerate(table):
+            ref = g["merged_k%d" % k][it * k:(it + 1) * k]
+            worst = max(worst, rel(sp[r], ref))
+        print("nmf %s %s: %d restarts in %.3fs, worst rel-L2 vs reference spectra %.3e, n_iter %s" % (
+            precision, tag, len(table), dt, worst, n_iter.tolist()), flush=True)
+        from oracle import nmf_ref
+        its = [nmf_ref.nmf(g["X"], int(k), int(seed), solver=g["solver"])[2] for (k, it, seed) in table]
+        print("   oracle n_iter %s  match=%s" % (its, its == n_iter.tolist()), flush=True)
+        # refit
+        k = int(g["ks"][0])
+        H = g["cspectra_k%d" % k]
+        W, it, e = ds.refit(H, kw)
+        Wr, itr = nmf_ref.refit(g["X"], H, g["solver"])
+        print("   refit: n_iter %d (oracle %d) rel %.3e err %.6f (oracle %.6f)" % (
+            it, itr, rel(W, Wr), e, nmf_ref.frobenius_error(g["X"], Wr, H)), flush=True)
+
+
+def stage_perf():
+    eng = Engine()
+    rng = np.random.RandomState(0)
+    out = {}
+    for name, (M, N, K, sp) in {"XHt_c2": (1000, 20000, 2000, 1), "WtX_c2": (1000, 2000, 20000, 9),
+                                "XHt_c3": (8100, 50000, 2000, 1)}.items():
+        A = np.abs(rng.randn(M, K)).astype(np.float32)
+        B = np.abs(rng.randn(N, K)).astype(np.float32)
+        for prec in ("tf32x3", "fp32"):
+            if prec == "fp32" and M > 2000:
+                continue
+            _, ms = eng.gemm_abt(A, B, precision=prec, splits=sp, reps=5)
+            tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+            out["%s_%s" % (name, prec)] = dict(ms=ms, algo_tflops=tf)
+            print("perf gemm %s %s: %.3f ms  %.1f algorithmic TFLOP/s" % (name, prec, ms, tf), flush=True)
+    from cnmf_b200.synth import make_counts, normalise, restart_table
+    counts = make_counts(20000, 2000, k_true=12)
+    X, _ = normalise(counts)
+    rows = restart_table([10], 100)
+    kw = dict(solver="mu", tol=1e-4, max_iter=1000)
+    for prec in ("tf32x3", "fp32"):
+        t0 = time.time()
+        ds = eng.dataset(X, precision=prec)
+        t1 = time.time()
+        sp, _, n_iter, err = ds.factorize([r[0] for r in rows], [r[2] for r in rows], kw)
+        t2 = time.time()
+        out["c2_%s" % prec] = dict(upload_s=t1 - t0, factorize_s=t2 - t1, restarts_per_s=len(rows) / (t2 - t1),
+                                   n_iter_mean=float(n_iter.mean()), n_iter_max=int(n_iter.max()))
+        print("perf c2 %s: upload %.2fs factorize %.2fs -> %.1f restarts/s; n_iter mean %.1f max %d" % (
+            prec, t1 - t0, t2 - t1, len(rows) / (t2 - t1), n_iter.mean(), n_iter.max()), flush=True)
+        if prec == "tf32x3":
+            from oracle import nmf_ref
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                for r in (0, 1):
+                    t3 = time.time()
+                    W, H, it = nmf_ref.nmf(X.astype(np.float64), rows[r][0], rows[r][2], solver="mu")
+                    print("   oracle restart %d: n_iter %d (gpu %d) rel-L2 %.3e  cpu %.1fs" % (
+                        r, it, n_iter[r], rel(sp[r], H), time.time() - t3), flush=True)
+        ds.close()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "probe_perf.json"), "w"), indent=1)
+
+
+def stage_consensus():
+    from cnmf_b200 import consensus as cs
+    from oracle import consensus_ref as cr
+    eng = Engine()
+    for tag in ("sim_mu",):
+        g = load_golden(tag)
+        for k in g["ks"]:
+            k = int(k)
+            merged = g["merged_k%d" % k]
+            S = cs.SpectraMatrix(eng, merged).l2_normalize()
+            l2 = cr.l2_normalize_rows(merged)
+            print("consensus k=%d l2 rel %.3e" % (k, rel(S.numpy(), l2)), flush=True)
+            n_nb = int(0.3 * merged.shape[0] / k)
+            dens, D = S.local_density(n_nb, return_dist=True)
+            Dref = cr.euclidean_distances(l2)
+            dref = cr.local_density(Dref, n_nb)
+            print("   dist maxabs %.3e  density rel %.3e  (golden rel %.3e)" % (
+                float(np.abs(D - Dref).max()), rel(dens, dref), rel(dens, g["density_k%d" % k])), flush=True)
+            labels, labels_t, inertia, centers = cs.kmeans(S, k)
+            lref, iref, cref = cr.kmeans(l2, k)
+            print("   kmeans labels equal %s inertia %.6e vs %.6e" % (np.array_equal(labels, lref), inertia, iref), flush=True)
+            med = cs.cluster_medians(S, labels_t, k)
+            mref = cr.cluster_medians(l2, lref, k)
+            print("   medians rel %.3e" % rel(med, mref), flush=True)
+    # a bigger random case: R=3000 x G=2000, 12 clusters + outliers
+    rng = np.random.RandomState(5)
+    cen = np.abs(rng.randn(12, 2000))
+    pts = np.vstack([c + 0.05 * np.abs(rng.randn(240, 2000)) for c in cen] + [np.abs(rng.randn(120, 2000))])
+    S = cs.SpectraMatrix(eng, pts).l2_normalize()
+    l2 = cr.l2_normalize_rows(pts)
+    t0 = time.time()
+    dens, _ = S.local_density(72)
+    t1 = time.time()
+    dref = cr.local_density(cr.euclidean_distances(l2), 72)
+    print("big: density rel %.3e gpu %.3fs" % (rel(dens, dref), t1 - t0), flush=True)
+    keep = dens < 0.5
+    S2 = S.take_rows(np.where(keep)[0])
+    t0 = time.time()
+    labels, labels_t, inertia, _ = cs.kmeans(S2, 12)
+    t1 = time.time()
+    lref, iref, _ = cr.kmeans(l2[keep], 12)
+    t2 = time.time()
+    print("big: kmeans equal %s inertia %.6e/%.6e gpu %.2fs oracle %.2fs" % (
+        np.array_equal(labels, lref), inertia, iref, t1 - t0, t2 - t1), flush=True)
+    med = cs.cluster_medians(S2, labels_t, 12)
+    print("big: medians rel %.3e" % rel(med, cr.cluster_medians(l2[keep], lref, 12)), flush=True)
+
+
+if __name__ == "__main__":
+    st = sys.argv[1]
+    if st == "gemm_fp32":
+        stage_gemm("fp32")
+    elif st == "gemm_tf32":
+        stage_gemm("tf32x3")
+    elif st == "nmf_fp32":
+        stage_nmf("fp32")
+    elif st == "nmf_tf32":
+        stage_nmf("tf32x3")
+    elif st == "perf":
+        stage_perf()
+    elif st == "consensus":
+        stage_consensus()
