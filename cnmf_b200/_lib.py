@@ -40,15 +40,19 @@ SIGNATURES = {
     "cnmf_create": (_i, [_pp(_vp), _i]),
     "cnmf_destroy": (_i, [_vp]),
     "cnmf_launch_count": (_ll, [_vp]),
+    "cnmf_profile_enable": (_i, [_vp, _i]),
+    "cnmf_profile_get": (_i, [_vp, _pp(_d), _pp(_ll), _pp(_d)]),
     "cnmf_dataset_create": (_i, [_vp, _vp, _i, _i, _ll, _i, _i, _vp, _pp(_vp)]),
     "cnmf_dataset_from_columns": (_i, [_vp, _vp, _vp, _i, _vp, _pp(_vp)]),
     "cnmf_dataset_destroy": (_i, [_vp]),
     "cnmf_dataset_shape": (_i, [_vp, _pp(_i), _pp(_i)]),
+    "cnmf_dataset_ld": (_i, [_vp, _pp(_i), _pp(_i)]),
     "cnmf_dataset_sums": (_i, [_vp, _pp(_d), _pp(_d)]),
     "cnmf_dataset_col_stats": (_i, [_vp, _vp, _vp, _vp]),
     "cnmf_random_init_host": (_i, [_c.c_uint32, _d, _i, _i, _i, _vp, _ll, _vp, _ll]),
     "cnmf_factorize": (_i, [_vp, _i, _vp, _vp, _pp(NmfParams), _vp, _vp, _vp, _vp, _vp]),
     "cnmf_factorize_init": (_i, [_vp, _i, _vp, _vp, _vp, _pp(NmfParams), _vp, _vp, _vp, _vp, _vp]),
+    "cnmf_factorize_dev": (_i, [_vp, _i, _vp, _vp, _vp, _pp(NmfParams), _vp, _vp, _vp, _vp]),
     "cnmf_refit": (_i, [_vp, _i, _i, _vp, _pp(NmfParams), _vp, _pp(_c.c_int32), _pp(_d), _vp]),
     "cnmf_project_rows": (_i, [_vp, _i, _vp, _vp, _vp]),
     "cnmf_gemm_abt_host": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _pp(_c.c_float), _vp]),

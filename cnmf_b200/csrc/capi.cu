@@ -63,7 +63,40 @@ void* cnmf_handle_s::host_buf(const std::string& name, size_t bytes) {
   return e.first;
 }
 
+int cnmf_handle_s::prof_begin(cudaStream_t s, double flops) {
+  if (!profile) return -1;
+  while (ev_pool.size() < ev_used + 2) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return -1;
+    ev_pool.push_back(e);
+  }
+  const int slot = (int)ev_used;
+  ev_used += 2;
+  cudaEventRecord(ev_pool[slot], s);
+  ev_pending.emplace_back(slot, flops);
+  return slot;
+}
+
+void cnmf_handle_s::prof_end(cudaStream_t s, int slot) {
+  if (slot >= 0) cudaEventRecord(ev_pool[slot + 1], s);
+}
+
+void cnmf_handle_s::prof_collect() {
+  for (auto& pr : ev_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev_pool[pr.first], ev_pool[pr.first + 1]) == cudaSuccess) {
+      prof_gemm_ms += ms;
+      prof_gemm_flops += pr.second;
+      prof_gemm_launches += 1;
+    }
+  }
+  ev_pending.clear();
+  ev_used = 0;
+}
+
 void cnmf_handle_s::release_all() {
+  for (auto e : ev_pool) cudaEventDestroy(e);
+  ev_pool.clear();
   for (auto& kv : ws)
     if (kv.second.first) cudaFree(kv.second.first);
   ws.clear();
@@ -111,6 +144,24 @@ int cnmf_destroy(cnmf_handle_t h) {
 }
 
 long long cnmf_launch_count(cnmf_handle_t h) { return h ? h->launches : 0; }
+
+int cnmf_profile_enable(cnmf_handle_t h, int on) {
+  CNMF_REQUIRE(h, "profile_enable: NULL handle");
+  h->profile = on != 0;
+  h->prof_gemm_ms = h->prof_gemm_flops = 0.0;
+  h->prof_gemm_launches = 0;
+  h->ev_pending.clear();
+  h->ev_used = 0;
+  return 0;
+}
+
+int cnmf_profile_get(cnmf_handle_t h, double* gemm_ms, long long* gemm_launches, double* gemm_flops) {
+  CNMF_REQUIRE(h, "profile_get: NULL handle");
+  if (gemm_ms) *gemm_ms = h->prof_gemm_ms;
+  if (gemm_launches) *gemm_launches = h->prof_gemm_launches;
+  if (gemm_flops) *gemm_flops = h->prof_gemm_flops;
+  return 0;
+}
 
 // ----------------------------------------------------------------------------- dataset
 static int dataset_alloc(cnmf_dataset_s* d, float** p, size_t elems) {
@@ -384,6 +435,54 @@ int cnmf_factorize_init(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, 
   CNMF_CUDA_CHECK(cudaMemcpy2DAsync(fb.Fc, (size_t)d->ld_c * 4, H0_host, (size_t)d->n_cols * 4, (size_t)d->n_cols * 4,
                                     SK, cudaMemcpyHostToDevice, s));
   return run_and_download(d, ks, SK, fb, *p, spectra_host, usages_host, n_iter_host, err_host, s);
+}
+
+int cnmf_factorize_dev(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, const float* Wt0_dev,
+                       const float* H0_dev, const cnmf_nmf_params* p, float* spectra_dev, int32_t* n_iter_host,
+                       double* err_host, void* stream) {
+  CNMF_TRY(check_params(d, p));
+  CNMF_REQUIRE(n_restarts > 0 && ks_in && Wt0_dev && H0_dev && spectra_dev, "factorize_dev: bad arguments");
+  cnmf_handle_s* h = d->h;
+  cudaStream_t s = as_stream(stream);
+  CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  std::vector<int> ks(ks_in, ks_in + n_restarts);
+  int SK = 0;
+  for (int r = 0; r < n_restarts; ++r) {
+    CNMF_REQUIRE(ks[r] >= 1 && ks[r] <= KMAX, "factorize_dev: n_components must be in [1, 32] on the CUDA path");
+    SK += ks[r];
+  }
+  const bool tf32 = p->precision == CNMF_PRECISION_TF32X3;
+  FactorBuffers fb;
+  CNMF_TRY(alloc_factors(h, SK, d->ld_r, d->ld_c, tf32, &fb));
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(fb.Fr, Wt0_dev, (size_t)SK * d->ld_r * 4, cudaMemcpyDeviceToDevice, s));
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(fb.Fc, H0_dev, (size_t)SK * d->ld_c * 4, cudaMemcpyDeviceToDevice, s));
+  if (tf32) {
+    CNMF_TRY(launch_split_tf32(fb.Fr, fb.Fr_hi, fb.Fr_lo, (long long)SK * d->ld_r, s));
+    CNMF_TRY(launch_split_tf32(fb.Fc, fb.Fc_hi, fb.Fc_lo, (long long)SK * d->ld_c, s));
+    h->launches += 2;
+  }
+  DataView v = make_view(d, false);
+  SolveIO io;
+  io.R = n_restarts;
+  io.ks = ks;
+  io.Fr = fb.Fr; io.Fr_hi = fb.Fr_hi; io.Fr_lo = fb.Fr_lo;
+  io.Fc = fb.Fc; io.Fc_hi = fb.Fc_hi; io.Fc_lo = fb.Fc_lo;
+  io.update_cols = true;
+  CNMF_TRY(solve_batched(h, v, io, *p, s));
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(spectra_dev, fb.Fc, (size_t)SK * d->ld_c * 4, cudaMemcpyDeviceToDevice, s));
+  CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  for (int r = 0; r < n_restarts; ++r) {
+    if (n_iter_host) n_iter_host[r] = io.n_iter[r];
+    if (err_host) err_host[r] = io.err[r];
+  }
+  return 0;
+}
+
+int cnmf_dataset_ld(cnmf_dataset_t d, int* ld_rows, int* ld_cols) {
+  CNMF_REQUIRE(d, "dataset_ld: NULL dataset");
+  if (ld_rows) *ld_rows = d->ld_r;
+  if (ld_cols) *ld_cols = d->ld_c;
+  return 0;
 }
 
 }  // extern "C"

@@ -13,6 +13,17 @@ struct cnmf_handle_s {
   int device = 0;
   int sm_count = 148;
   long long launches = 0;                       // kernels launched by this library (bench: gpu_launches)
+  // optional per-launch timing of the dominant kernel (the batched GEMM) with CUDA events on the
+  // launching stream; read back by bench.py for the roofline line
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, double>> ev_pending;   // (index of start event in ev_pool, flops)
+  size_t ev_used = 0;
+  double prof_gemm_ms = 0.0, prof_gemm_flops = 0.0;
+  long long prof_gemm_launches = 0;
+  int prof_begin(cudaStream_t s, double flops);    // records the start event; returns slot or -1
+  void prof_end(cudaStream_t s, int slot);
+  void prof_collect();                              // after a stream sync: fold pending pairs into the totals
   std::map<std::string, std::pair<void*, size_t>> ws;   // named grow-only device buffers
   std::map<std::string, std::pair<void*, size_t>> pinned;  // named grow-only pinned host buffers
 

@@ -15,6 +15,7 @@ struct GemmArgs {
   long long c_split_stride;   // elements between consecutive split-K slices of C
   int splits;                 // requested split-K factor
   int splits_effective;       // gemm_effective_splits(Kd, splits): what the kernel will actually write
+  int chain_kb;               // tf32x3: k-blocks (of 32) accumulated in TMEM before draining to registers (0 -> 1)
 };
 
 // number of non-empty split-K slices for a reduction length Kd (k-blocks of 32)

@@ -13,15 +13,23 @@
 //   X H^T   (sklearn _nmf.py:538, :380)  ->  A = H_batch (SK x G),   B = X   (cells x G)
 //   W^T X   (sklearn _nmf.py:634, :380)  ->  A = W^T_batch (SK x N), B = X^T (G x cells), split-K
 //
-// Structure (one CTA per SM, persistent over a static tile schedule, 192 threads):
+// Structure (one CTA per SM, persistent over a static tile schedule, 320 threads):
 //   warp 0     TMA producer: cp.async.bulk.tensor 2D, 128B-swizzled tiles, mbarrier full/empty ring
 //   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 8, kind::tf32)
-//   warps 2-5  epilogue: tcgen05.ld 32x32b -> registers -> float4 global stores
-//              (TMEM accumulator double-buffered so the epilogue overlaps the next tile's MMAs)
+//   warps 2-9  accumulate/epilogue: tcgen05.ld 32x32b -> fp32 register accumulators -> float4 stores
+//
+// Accumulation accuracy.  The tensor core adds each MMA result into the TMEM accumulator with
+// truncation: measured on B200, a chain of n MMAs on non-negative data is biased low by about
+// n * 3e-8 relative (2.3e-5 at K = 2048), which is far outside the 1e-4 parity budget of an NMF
+// run.  So TMEM only ever holds SHORT chains (`chain_kb` k-blocks = 12 * chain_kb MMAs, default 1):
+// the MMA warp ping-pongs between two TMEM buffers, and the eight accumulate warps drain each
+// finished chain into round-to-nearest fp32 register accumulators (128 per thread) while the next
+// chain is being issued.  Result: ~4e-7 relative, the same class as an FFMA fp32 GEMM.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -34,7 +42,8 @@ namespace {
 constexpr int BM = 128;          // UMMA M (rows of A per tile) -- one TMEM lane per row
 constexpr int BK = 32;           // fp32 elements per k-block = 128 B = one swizzle row
 constexpr int UMMA_K = 8;        // kind::tf32: 32 B of K per instruction
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;                         // two per TMEM lane quadrant (column halves)
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;      // 320
 constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;   // ~2 s: a dead pipeline traps instead of hanging
 
 template <int BN, int STAGES>
@@ -140,7 +149,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    float* __restrict__ C, int M, int N, int ldc, long long c_split_stride,
-                   int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split) {
+                   int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split, int chain_kb) {
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024 B alignment
@@ -164,7 +173,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 32 * NUM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -209,71 +218,85 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       constexpr uint32_t idesc = make_idesc<BN>();
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      int buf = 0;
+      uint32_t buf_phase = 0;
       for (int w = blockIdx.x; w < items; w += gridDim.x) {
         const int z = w / (m_tiles * n_tiles);
         const int kb0 = z * kb_per_split;
         const int kb1 = min(total_kb, kb0 + kb_per_split);
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar(stage), phase, 2);
+        for (int c0 = kb0; c0 < kb1; c0 += chain_kb) {          // one short accumulation chain per TMEM buffer
+          const int c1 = min(kb1, c0 + chain_kb);
+          mbar_wait(tempty_bar(buf), buf_phase ^ 1u, 1);
           tc_fence_after();
-          const uint32_t st = smem_base + stage * L::STAGE_BYTES;
-          const uint64_t a_hi = make_smem_desc(st);
-          const uint64_t a_lo = make_smem_desc(st + L::A_BYTES);
-          const uint64_t b_hi = make_smem_desc(st + 2 * L::A_BYTES);
-          const uint64_t b_lo = make_smem_desc(st + 2 * L::A_BYTES + L::B_BYTES);
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
+          for (int kb = c0; kb < c1; ++kb) {
+            mbar_wait(full_bar(stage), phase, 2);
+            tc_fence_after();
+            const uint32_t st = smem_base + stage * L::STAGE_BYTES;
+            const uint64_t a_hi = make_smem_desc(st);
+            const uint64_t a_lo = make_smem_desc(st + L::A_BYTES);
+            const uint64_t b_hi = make_smem_desc(st + 2 * L::A_BYTES);
+            const uint64_t b_lo = make_smem_desc(st + 2 * L::A_BYTES + L::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 4) >> 4);   // +32 B per k-step inside the swizzle row
-            umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, 1u);
-            umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 4) >> 4);   // +32 B per k-step inside the swizzle row
+              umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, (kb > c0 || k > 0) ? 1u : 0u);   // small terms first
+              umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1u);
+              umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, 1u);
+            }
+            umma_commit(empty_bar(stage));         // smem slot is free once these MMAs have read it
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(empty_bar(stage));           // smem slot is free once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          umma_commit(tfull_bar(buf));             // chain complete -> accumulate warps
+          if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));               // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
-    // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
-    const int q = warp & 3;                        // tcgen05.ld: warp w may touch lanes 32*(w%4) .. +31
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    // ===================== accumulate + epilogue (8 warps) =====================
+    // tcgen05.ld: warp w may touch TMEM lanes 32*(w%4) .. +31.  Warps 2-5 own columns [0, BN/2),
+    // warps 6-9 own [BN/2, BN) of their lane quadrant.
+    constexpr int HALF = BN / 2;
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int buf = 0;
+    uint32_t buf_phase = 0;
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
       const int mt = w % m_tiles;
       const int nt = (w / m_tiles) % n_tiles;
       const int z = w / (m_tiles * n_tiles);
-      mbar_wait(tfull_bar(acc), acc_phase, 3);
-      tc_fence_after();
-      const int row = mt * BM + q * 32 + lane;
-      float* crow = C + static_cast<long long>(z) * c_split_stride + static_cast<long long>(row) * ldc;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c, r);
-        tmem_ld_wait();
-        const int col0 = nt * BN + c;
-        if (row < M) {
+      const int kb0 = z * kb_per_split;
+      const int kb1 = min(total_kb, kb0 + kb_per_split);
+      float acc[HALF];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            if (col0 + i + 3 < ldc) {
-              float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
-                                     __uint_as_float(r[i + 3]));
-              *reinterpret_cast<float4*>(crow + col0 + i) = v;
-            }
-          }
+      for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+      for (int c0 = kb0; c0 < kb1; c0 += chain_kb) {
+        mbar_wait(tfull_bar(buf), buf_phase, 3);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(buf * BN + half * HALF);
+#pragma unroll
+        for (int c = 0; c < HALF; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[c + i] += __uint_as_float(r[i]);     // round-to-nearest fp32
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(buf));
+        if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
+      }
+      const int row = mt * BM + q * 32 + lane;
+      if (row < M) {
+        float* crow = C + static_cast<long long>(z) * c_split_stride + static_cast<long long>(row) * ldc;
+        const int col0 = nt * BN + half * HALF;
+#pragma unroll
+        for (int i = 0; i < HALF; i += 4) {
+          if (col0 + i + 3 < ldc)
+            *reinterpret_cast<float4*>(crow + col0 + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
@@ -351,8 +374,18 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   CNMF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int items = m_tiles * n_tiles * splits;
   const int grid = items < sms ? items : sms;
+  int chain_kb = g.chain_kb;
+  if (chain_kb <= 0) {
+    static const int env_chain = [] {
+      const char* e = std::getenv("CNMF_CHAIN_KB");      // tuning knob; default 1 (12 MMAs per TMEM chain)
+      const int v = e ? std::atoi(e) : 1;
+      return v >= 1 ? v : 1;
+    }();
+    chain_kb = env_chain;
+  }
   kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(mAh, mAl, mBh, mBl, g.C, g.M, g.N, g.ldc, g.c_split_stride,
-                                                    m_tiles, n_tiles, splits, total_kb, kb_per_split);
+                                                    m_tiles, n_tiles, splits, total_kb, kb_per_split,
+                                                    chain_kb);
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -63,12 +63,17 @@ int run_gemm(cnmf_handle_s* h, int precision, const float* A, const float* A_hi,
   g.splits = plan.splits;
   g.splits_effective = plan.splits;
   h->launches += 1;
+  const int slot = h->prof_begin(s, 2.0 * (double)g.M * (double)g.N * (double)g.Kd);
+  int rc;
   if (precision == CNMF_PRECISION_TF32X3) {
     g.A_hi = A_hi; g.A_lo = A_lo; g.B_hi = B.hi; g.B_lo = B.lo;
-    return gemm_tf32x3(g, s);
+    rc = gemm_tf32x3(g, s);
+  } else {
+    g.A_hi = A; g.A_lo = nullptr; g.B_hi = B.full; g.B_lo = nullptr;
+    rc = gemm_fp32_simt(g, s);
   }
-  g.A_hi = A; g.A_lo = nullptr; g.B_hi = B.full; g.B_lo = nullptr;
-  return gemm_fp32_simt(g, s);
+  h->prof_end(s, slot);
+  return rc;
 }
 
 #define CNMF_TRY(expr)            \
@@ -279,6 +284,7 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   CNMF_CUDA_CHECK(cudaMemcpyAsync(io.last.data(), st.last, sizeof(double) * R, cudaMemcpyDeviceToHost, s));
   CNMF_CUDA_CHECK(cudaMemcpyAsync(io.err.data(), d_err, sizeof(double) * R, cudaMemcpyDeviceToHost, s));
   CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  h->prof_collect();
   return 0;
 }
 

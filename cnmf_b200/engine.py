@@ -72,6 +72,16 @@ class Engine:
     def launch_count(self):
         return int(self.lib.cnmf_launch_count(self._h))
 
+    def profile(self, on=True):
+        """Start (and reset) / stop per-launch CUDA-event timing of the batched GEMM."""
+        check(self.lib.cnmf_profile_enable(self._h, 1 if on else 0))
+
+    def profile_get(self):
+        """(total GEMM device ms, GEMM launches, algorithmic FLOPs) since profile(True)."""
+        ms, n, fl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+        check(self.lib.cnmf_profile_get(self._h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
+        return ms.value, int(n.value), fl.value
+
     def dataset(self, X, precision=_DEFAULT_PRECISION, stream=None):
         return Dataset(self, X, precision, stream)
 
@@ -119,6 +129,24 @@ class Dataset:
             self.close()
         except Exception:
             pass
+
+    def ld(self):
+        """(row stride of packed W^T rows, row stride of packed H rows), both padded to 32 floats."""
+        a, b = ctypes.c_int(), ctypes.c_int()
+        check(self.lib.cnmf_dataset_ld(self._d, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def factorize_dev(self, ks, Wt0_ptr, H0_ptr, out_ptr, nmf_kwargs):
+        """Device-resident factorize: raw device pointers (e.g. torch.Tensor.data_ptr()) of the packed,
+        padded initial factors and of the output spectra slab.  Returns (n_iter, err)."""
+        ks = np.ascontiguousarray(ks, dtype=np.int32)
+        R = len(ks)
+        p = self.params(nmf_kwargs)
+        n_iter = np.zeros(R, np.int32)
+        err = np.zeros(R, np.float64)
+        check(self.lib.cnmf_factorize_dev(self._d, R, ptr(ks), ctypes.c_void_p(Wt0_ptr), ctypes.c_void_p(H0_ptr),
+                                          ctypes.byref(p), ctypes.c_void_p(out_ptr), ptr(n_iter), ptr(err), None))
+        return n_iter, err
 
     def sums(self):
         s, q = ctypes.c_double(), ctypes.c_double()

@@ -1,0 +1,557 @@
+"""`cNMF` facade: the reference's class / file ledger / method signatures (cnmf.py:265-1210) over the
+B200 engine.  Host logic only (paths, seeds, job split, DataFrame labelling, file I/O); the numerics of
+factorize and consensus run in libcnmf_b200.so.  Nothing here falls back to scikit-learn.
+
+Drop-in points (reference file:line -> here)
+  cNMF.__init__/_initialize_dirs  cnmf.py:268-330   same directory layout and path templates
+  prepare                         cnmf.py:333-459   host numpy (dense); same outputs and seed rule
+  factorize                       cnmf.py:692-745   ALL of this worker's (k, seed) jobs in one batched GPU solve
+  combine / combine_nmf           cnmf.py:462-483,748-773
+  refit_usage / refit_spectra     cnmf.py:776-820   cnmf_refit
+  consensus                       cnmf.py:823-1082  GPU kernels via cnmf_b200.consensus
+  k_selection_plot                cnmf.py:1119-1158 statistics (+ figure when matplotlib is available)
+  load_results                    cnmf.py:1161-1210
+"""
+import datetime
+import errno
+import itertools
+import os
+import uuid
+import warnings
+
+import numpy as np
+import pandas as pd
+import yaml
+
+from . import io as cio
+from .io import load_df_from_npz, save_df_to_npz, save_df_to_text
+
+_TMP = "cnmf_tmp"
+# (key, in cnmf_tmp?, suffix) -- expands to the path table of cnmf.py:298-330
+_PATH_SPECS = [
+    ("normalized_counts", True, ".norm_counts.h5ad"),
+    ("nmf_replicate_parameters", True, ".nmf_params.df.npz"),
+    ("nmf_run_parameters", True, ".nmf_idvrun_params.yaml"),
+    ("nmf_genes_list", False, ".overdispersed_genes.txt"),
+    ("tpm", True, ".tpm.h5ad"),
+    ("tpm_stats", True, ".tpm_stats.df.npz"),
+    ("iter_spectra", True, ".spectra.k_%d.iter_%d.df.npz"),
+    ("iter_usages", True, ".usages.k_%d.iter_%d.df.npz"),
+    ("merged_spectra", True, ".spectra.k_%d.merged.df.npz"),
+    ("local_density_cache", True, ".local_density_cache.k_%d.merged.df.npz"),
+    ("consensus_spectra", True, ".spectra.k_%d.dt_%s.consensus.df.npz"),
+    ("consensus_spectra__txt", False, ".spectra.k_%d.dt_%s.consensus.txt"),
+    ("consensus_usages", True, ".usages.k_%d.dt_%s.consensus.df.npz"),
+    ("consensus_usages__txt", False, ".usages.k_%d.dt_%s.consensus.txt"),
+    ("consensus_stats", True, ".stats.k_%d.dt_%s.df.npz"),
+    ("clustering_plot", False, ".clustering.k_%d.dt_%s.png"),
+    ("gene_spectra_score", True, ".gene_spectra_score.k_%d.dt_%s.df.npz"),
+    ("gene_spectra_score__txt", False, ".gene_spectra_score.k_%d.dt_%s.txt"),
+    ("gene_spectra_tpm", True, ".gene_spectra_tpm.k_%d.dt_%s.df.npz"),
+    ("gene_spectra_tpm__txt", False, ".gene_spectra_tpm.k_%d.dt_%s.txt"),
+    ("starcat_spectra", True, ".starcat_spectra.k_%d.dt_%s.df.npz"),
+    ("starcat_spectra__txt", False, ".starcat_spectra.k_%d.dt_%s.txt"),
+    ("k_selection_plot", False, ".k_selection.png"),
+    ("k_selection_stats", False, ".k_selection_stats.df.npz"),
+]
+
+
+def worker_filter(iterable, worker_index, total_workers):
+    """cnmf.py:52-53."""
+    return (p for i, p in enumerate(iterable) if (i - worker_index) % total_workers == 0)
+
+
+def _highvar_genes(tpm, numgenes):
+    """V-score overdispersion ranking on dense TPM (cnmf.py:192-242)."""
+    mean = pd.Series(tpm.mean(axis=0).astype(float))
+    var = pd.Series(tpm.var(axis=0, ddof=0).astype(float))
+    fano = var / mean
+    top = mean.sort_values(ascending=False)[:20].index
+    A = (np.sqrt(var) / mean)[top].min()
+    m_lo, m_hi = mean.quantile([0.10, 0.90])
+    f_lo, f_hi = fano.quantile([0.10, 0.90])
+    box = (fano > f_lo) & (fano < f_hi) & (mean > m_lo) & (mean < m_hi)
+    B = np.sqrt(fano[box].median())
+    ratio = fano / ((A ** 2) * mean + (B ** 2))
+    chosen = ratio.sort_values(ascending=False).index[:numgenes]
+    return ratio.index.isin(chosen)
+
+
+class cNMF:
+    """Same constructor, attributes and methods as the reference class (cnmf.py:265)."""
+
+    def __init__(self, output_dir=".", name=None, precision="tf32x3", device=None):
+        self.output_dir = output_dir
+        if name is None:
+            name = "%s_%s" % (datetime.datetime.now().strftime("%Y_%m_%d"), uuid.uuid4().hex[:6])
+        self.name = name
+        self.precision = precision
+        self.device = device
+        self.paths = None
+        self._engine = None
+        self._initialize_dirs()
+
+    # ------------------------------------------------------------------ ledger
+    def _initialize_dirs(self):
+        if self.paths is not None:
+            return
+        base = os.path.join(self.output_dir, self.name)
+        os.makedirs(os.path.join(base, _TMP), exist_ok=True)
+        self.paths = {key: os.path.join(base, _TMP if tmp else "", self.name + suffix) if tmp
+                      else os.path.join(base, self.name + suffix) for key, tmp, suffix in _PATH_SPECS}
+
+    def engine(self):
+        """The GPU engine (created on first use; raises without a B200 -- there is no CPU path)."""
+        if self._engine is None:
+            from .engine import Engine
+            dev = self.device
+            if dev is None:
+                dev = int(os.environ.get("LOCAL_RANK", "0"))
+            self._engine = Engine(dev)
+        return self._engine
+
+    # ------------------------------------------------------------------ prepare
+    def prepare(self, counts_fn, components, n_iter=100, densify=False, tpm_fn=None, seed=None,
+                beta_loss="frobenius", num_highvar_genes=2000, genes_file=None,
+                alpha_usage=0.0, alpha_spectra=0.0, init="random", max_NMF_iter=1000):
+        """Same outputs as reference prepare() (cnmf.py:333-459) for dense inputs.  The CUDA path holds the
+        matrix dense, so sparse inputs are densified (numerically identical to the reference's --densify)."""
+        counts = cio.read_counts(counts_fn)
+        C = counts.dense(np.float64)
+        if tpm_fn is None:
+            tpm_X = C / C.sum(axis=1, keepdims=True) * 1e6           # cnmf.py:245-251
+            tpm = cio.CellGeneMatrix(tpm_X, counts.obs_names, counts.var_names)
+        else:
+            tpm = cio.read_counts(tpm_fn)
+            tpm = cio.CellGeneMatrix(tpm.dense(np.float64), tpm.obs_names, tpm.var_names)
+        cio.write_matrix(self.paths["tpm"], tpm)
+        T = tpm.X
+        stats = pd.DataFrame([T.mean(axis=0), T.std(axis=0, ddof=0)], index=["__mean", "__std"],
+                             columns=tpm.var_names).T                   # cnmf.py:439-445
+        save_df_to_npz(stats, self.paths["tpm_stats"])
+
+        if genes_file is not None:
+            hvgs = open(genes_file).read().rstrip().split("\n")
+        else:
+            hvgs = list(tpm.var_names[_highvar_genes(T, num_highvar_genes)])
+        norm, _ = cio.CellGeneMatrix(C, counts.obs_names, counts.var_names).subset_genes(hvgs)
+        X = norm.X.astype(np.float64)
+        X /= X.std(axis=0, ddof=1)                                     # cnmf.py:542 (no centring)
+        if np.isnan(X).sum() > 0:
+            print("Warning NaNs in normalized counts matrix")
+        norm.X = X
+        with open(self.paths["nmf_genes_list"], "w") as F:
+            F.write("\n".join(hvgs))
+        zero = X.sum(axis=1) == 0
+        if zero.sum() > 0:                                             # cnmf.py:551-554
+            ex = norm.obs_names[np.ravel(zero)]
+            raise Exception("Error: %d cells have zero counts of overdispersed genes. E.g. %s. Filter those cells "
+                            "and re-run or adjust the number of overdispersed genes. Quitting!"
+                            % (zero.sum(), ", ".join(ex[:4])))
+        self.save_norm_counts(norm)
+        rp, run = self.get_nmf_iter_params(ks=components, n_iter=n_iter, random_state_seed=seed, beta_loss=beta_loss,
+                                           alpha_usage=alpha_usage, alpha_spectra=alpha_spectra, init=init,
+                                           max_iter=max_NMF_iter)
+        self.save_nmf_iter_params(rp, run)
+
+    def save_norm_counts(self, norm_counts):
+        self._initialize_dirs()
+        cio.write_matrix(self.paths["normalized_counts"], norm_counts)
+
+    def get_nmf_iter_params(self, ks, n_iter=100, random_state_seed=None, beta_loss="kullback-leibler",
+                            alpha_usage=0.0, alpha_spectra=0.0, init="random", max_iter=1000):
+        """(k, iter, seed, completed) table + solver kwargs; identical seed rule to cnmf.py:593-633."""
+        if type(ks) is int:
+            ks = [ks]
+        k_list = sorted(set(list(ks)))
+        n_runs = len(ks) * n_iter
+        np.random.seed(seed=random_state_seed)
+        nmf_seeds = np.random.randint(low=1, high=(2 ** 31) - 1, size=n_runs)
+        rows = []
+        for i, (k, r) in enumerate(itertools.product(k_list, range(n_iter))):
+            rows.append([k, r, nmf_seeds[i], os.path.exists(self.paths["iter_spectra"] % (k, r))])
+        rp = pd.DataFrame(rows, columns=["n_components", "iter", "nmf_seed", "completed"])
+        if rp["completed"].sum() > 0:
+            warnings.warn("%d runs already appear completed. If this is unexpected, consider re-initializing the "
+                          "cnmf object with a different run name or output directory" % rp["completed"].sum(), UserWarning)
+        kw = dict(alpha_W=alpha_usage, alpha_H=alpha_spectra, l1_ratio=0.0, beta_loss=beta_loss, solver="mu",
+                  tol=1e-4, max_iter=max_iter, init=init)
+        if beta_loss == "frobenius":      # cnmf.py:629-631: the reference's default solver for Frobenius is CD
+            kw["solver"] = "cd"
+        return rp, kw
+
+    def update_nmf_iter_params(self):
+        kw = yaml.load(open(self.paths["nmf_run_parameters"]), Loader=yaml.FullLoader)
+        rp = load_df_from_npz(self.paths["nmf_replicate_parameters"])
+        for i in rp.index:
+            rp.at[i, "completed"] = os.path.exists(self.paths["iter_spectra"] % (rp.at[i, "n_components"], rp.at[i, "iter"]))
+        print("%d NMF runs are currently incomplete" % (rp["completed"] == False).sum())  # noqa: E712
+        self.save_nmf_iter_params(rp, kw)
+
+    def save_nmf_iter_params(self, replicate_params, run_params):
+        self._initialize_dirs()
+        save_df_to_npz(replicate_params, self.paths["nmf_replicate_parameters"])
+        with open(self.paths["nmf_run_parameters"], "w") as F:
+            yaml.dump(run_params, F)
+
+    # ------------------------------------------------------------------ the seam
+    def _dataset(self, X):
+        from .engine import Dataset
+        if isinstance(X, Dataset):
+            return X
+        return self.engine().dataset(X, precision=self.precision)
+
+    def _nmf(self, X, nmf_kwargs):
+        """Drop-in for the reference seam cNMF._nmf (cnmf.py:661-674): one sklearn-style NMF call,
+        returns (spectra, usages).  factorize() uses the batched form _nmf_batched instead."""
+        kw = dict(nmf_kwargs)
+        ds = self._dataset(X)
+        if kw.get("update_H", True) is False:
+            H = np.asarray(kw["H"])
+            W, _, _ = ds.refit(H, kw)
+            return H, W.astype(np.float64)
+        sp, us, _, _ = ds.factorize([int(kw["n_components"])], [int(kw["random_state"])], kw, return_usages=True)
+        return sp[0].astype(np.float64), us[0].astype(np.float64)
+
+    def _nmf_batched(self, X, ks, seeds, nmf_kwargs):
+        """All restarts at once; returns list of spectra (float64) and per-restart iteration counts."""
+        ds = self._dataset(X)
+        sp, _, n_iter, err = ds.factorize(ks, seeds, nmf_kwargs)
+        return [s.astype(np.float64) for s in sp], n_iter, err
+
+    # ------------------------------------------------------------------ factorize / combine
+    def factorize(self, worker_i=0, total_workers=1, skip_completed_runs=False):
+        """cnmf.py:692-745, but every job of this worker goes through ONE batched GPU solve."""
+        run_params = load_df_from_npz(self.paths["nmf_replicate_parameters"])
+        norm = cio.read_matrix(self.paths["normalized_counts"])
+        kw = yaml.load(open(self.paths["nmf_run_parameters"]), Loader=yaml.FullLoader)
+        if not skip_completed_runs:
+            jobs = list(worker_filter(range(len(run_params)), worker_i, total_workers))
+        else:
+            jobs = list(worker_filter(run_params.index[run_params["completed"] == False], worker_i, total_workers))  # noqa: E712
+        if not jobs:
+            return
+        ks = [int(run_params.iloc[j]["n_components"]) for j in jobs]
+        seeds = [int(run_params.iloc[j]["nmf_seed"]) for j in jobs]
+        print("[Worker %d]. Starting %d tasks as one batch." % (worker_i, len(jobs)))
+        spectra, n_iter, _ = self._nmf_batched(norm.X, ks, seeds, kw)
+        if int(np.max(n_iter)) >= int(kw["max_iter"]):
+            from sklearn.exceptions import ConvergenceWarning
+            warnings.warn("Maximum number of iterations %d reached. Increase it to improve convergence." % kw["max_iter"],
+                          ConvergenceWarning)
+        for j, sp in zip(jobs, spectra):
+            p = run_params.iloc[j]
+            df = pd.DataFrame(sp, index=np.arange(1, int(p["n_components"]) + 1), columns=norm.var_names)
+            save_df_to_npz(df, self.paths["iter_spectra"] % (p["n_components"], p["iter"]))
+
+    def combine(self, components=None, skip_missing_files=False):
+        if type(components) is int:
+            ks = [components]
+        elif components is None:
+            ks = sorted(set(load_df_from_npz(self.paths["nmf_replicate_parameters"]).n_components))
+        else:
+            ks = components
+        for k in ks:
+            self.combine_nmf(k, skip_missing_files=skip_missing_files)
+
+    def combine_nmf(self, k, skip_missing_files=False, remove_individual_iterations=False):
+        """cnmf.py:748-773."""
+        run_params = load_df_from_npz(self.paths["nmf_replicate_parameters"])
+        print("Combining factorizations for k=%d." % k)
+        sub = run_params[run_params.n_components == k].sort_values("iter")
+        parts = []
+        for _, p in sub.iterrows():
+            fn = self.paths["iter_spectra"] % (p["n_components"], p["iter"])
+            if not os.path.exists(fn):
+                if not skip_missing_files:
+                    print("Missing file: %s, run with skip_missing=True to override" % fn)
+                    raise FileNotFoundError(errno.ENOENT, os.strerror(errno.ENOENT), fn)
+                print("Missing file: %s. Skipping." % fn)
+                continue
+            sp = load_df_from_npz(fn)
+            sp.index = ["iter%d_topic%d" % (p["iter"], t + 1) for t in range(k)]
+            parts.append(sp)
+        if parts:
+            merged = pd.concat(parts, axis=0)
+            save_df_to_npz(merged, self.paths["merged_spectra"] % k)
+            return merged
+        print("No spectra found for k=%d" % k)
+        return parts
+
+    # ------------------------------------------------------------------ refits
+    def _run_kwargs(self):
+        return yaml.load(open(self.paths["nmf_run_parameters"]), Loader=yaml.FullLoader)
+
+    def refit_usage(self, X, spectra):
+        """cnmf.py:776-802."""
+        H = spectra.values if isinstance(spectra, pd.DataFrame) else np.asarray(spectra)
+        Xv = X.values if isinstance(X, pd.DataFrame) else X
+        W, _, _ = self._dataset(Xv).refit(H, self._run_kwargs())
+        W = W.astype(np.float64)
+        if isinstance(X, pd.DataFrame) and isinstance(spectra, pd.DataFrame):
+            W = pd.DataFrame(W, index=X.index, columns=spectra.index)
+        return W
+
+    def refit_spectra(self, X, usage):
+        """cnmf.py:805-820: refit_usage(X.T, usage.T).T -- the engine solves the transposed problem
+        on the same resident dataset instead of materialising X.T."""
+        U = usage.values if isinstance(usage, pd.DataFrame) else np.asarray(usage)
+        Xv = X.values if isinstance(X, pd.DataFrame) else X
+        Ht, _, _ = self._dataset(Xv).refit(np.ascontiguousarray(U.T), self._run_kwargs(), transposed=True)
+        return Ht.T.astype(np.float64)
+
+    # ------------------------------------------------------------------ consensus
+    def consensus(self, k, density_threshold=0.5, local_neighborhood_size=0.30, show_clustering=True,
+                  build_ref=True, skip_density_and_return_after_stats=False, close_clustergram_fig=False,
+                  refit_usage=True, normalize_tpm_spectra=False, norm_counts=None):
+        """cnmf.py:823-1082 with every numeric step on the GPU (see cnmf_b200/consensus.py)."""
+        from . import consensus as cs
+        eng = self.engine()
+        merged = load_df_from_npz(self.paths["merged_spectra"] % k)
+        if norm_counts is None:
+            norm_counts = cio.read_matrix(self.paths["normalized_counts"])
+        if not hasattr(norm_counts, "_ds"):
+            norm_counts._ds = self._dataset(norm_counts.X)
+        norm_ds = norm_counts._ds
+        kw = self._run_kwargs()
+
+        dt_str = "2" if skip_density_and_return_after_stats else str(density_threshold)
+        dt_repl = dt_str.replace(".", "_")
+        n_neighbors = int(local_neighborhood_size * merged.shape[0] / k)
+
+        S = cs.SpectraMatrix(eng, merged.values).l2_normalize()                    # cnmf.py:882
+        l2_index = merged.index
+        topics_dist = None
+        density_filter = None
+        if not skip_density_and_return_after_stats:
+            cache = self.paths["local_density_cache"] % k
+            if os.path.isfile(cache):                                              # cnmf.py:887-888 (keyed by k only)
+                local_density = load_df_from_npz(cache)
+            else:
+                dens, topics_dist = S.local_density(n_neighbors, return_dist=show_clustering)
+                local_density = pd.DataFrame(dens, columns=["local_density"], index=l2_index)
+                save_df_to_npz(local_density, cache)
+            density_filter = local_density.iloc[:, 0] < density_threshold           # cnmf.py:903
+            keep = np.where(density_filter.values)[0]
+            if len(keep) == 0:
+                raise RuntimeError("Zero components remain after density filtering. Consider increasing density threshold")
+            if len(keep) < S.R:
+                S = S.take_rows(keep)
+            l2_index = l2_index[keep]
+
+        labels0, labels_t, _, _ = cs.kmeans(S, k)                                   # cnmf.py:908-910
+        cluster_labels = pd.Series(labels0 + 1, index=l2_index)
+        med = cs.cluster_medians(S, labels_t, k)                                    # cnmf.py:913-916
+        median_spectra = pd.DataFrame(med, index=np.arange(1, k + 1), columns=merged.columns)
+        median_spectra.index.name = None
+
+        rf, _, err = norm_ds.refit(median_spectra.values, kw)                       # cnmf.py:919
+        rf_usages = pd.DataFrame(rf.astype(np.float64), index=norm_counts.obs_names, columns=median_spectra.index)
+
+        if skip_density_and_return_after_stats:                                     # cnmf.py:922-936
+            from sklearn.metrics import silhouette_score
+            l2_host = S.numpy()
+            silhouette = silhouette_score(l2_host, cluster_labels.values, metric="euclidean")
+            if kw.get("solver") == "mu":
+                prediction_error = err ** 2
+            else:
+                prediction_error = err ** 2
+            return pd.DataFrame([k, density_threshold, silhouette, prediction_error],
+                                index=["k", "local_density_threshold", "silhouette", "prediction_error"],
+                                columns=["stats"])
+
+        norm_usages = rf_usages.div(rf_usages.sum(axis=1), axis=0)                  # cnmf.py:939-946
+        reorder = norm_usages.sum(axis=0).sort_values(ascending=False)
+        rf_usages = rf_usages.loc[:, reorder.index]
+        norm_usages = norm_usages.loc[:, reorder.index]
+        median_spectra = median_spectra.loc[reorder.index, :]
+        rf_usages.columns = np.arange(1, rf_usages.shape[1] + 1)
+        norm_usages.columns = rf_usages.columns
+        median_spectra.index = rf_usages.columns
+
+        tpm = cio.read_matrix(self.paths["tpm"])                                    # cnmf.py:950-953
+        tpm_stats = load_df_from_npz(self.paths["tpm_stats"])
+        tpm_ds = self._dataset(tpm.X)
+        spectra_tpm = self.refit_spectra(tpm_ds, norm_usages.values)
+        spectra_tpm = pd.DataFrame(spectra_tpm, index=rf_usages.columns, columns=tpm.var_names)
+        if normalize_tpm_spectra:
+            spectra_tpm = spectra_tpm.div(spectra_tpm.sum(axis=1), axis=0) * 1e6
+
+        usage_coef = cs.ols_zscore(rf_usages.values, tpm_ds)                        # cnmf.py:958
+        usage_coef = pd.DataFrame(usage_coef, index=rf_usages.columns, columns=tpm.var_names)
+
+        if refit_usage:                                                             # cnmf.py:961-975
+            hvgs = open(self.paths["nmf_genes_list"]).read().split("\n")
+            hv_idx = tpm.var_names.get_indexer(hvgs)
+            _, var = tpm_ds.col_stats()
+            n = tpm.shape[0]
+            std1 = np.sqrt(var[hv_idx] * n / (n - 1.0))                             # std(ddof=1)
+            norm_tpm_ds = tpm_ds.from_columns(hv_idx, 1.0 / std1)
+            sp_rf = spectra_tpm.loc[:, hvgs].div(tpm_stats.loc[hvgs, "__std"], axis=1)
+            rf2, _, _ = norm_tpm_ds.refit(sp_rf.values, kw)
+            rf_usages = pd.DataFrame(rf2.astype(np.float64), index=norm_counts.obs_names, columns=sp_rf.index)
+            norm_tpm_ds.close()
+        tpm_ds.close()
+
+        tag = (k, dt_repl)
+        save_df_to_npz(median_spectra, self.paths["consensus_spectra"] % tag)
+        save_df_to_npz(rf_usages, self.paths["consensus_usages"] % tag)
+        save_df_to_text(median_spectra, self.paths["consensus_spectra__txt"] % tag)
+        save_df_to_text(rf_usages, self.paths["consensus_usages__txt"] % tag)
+        save_df_to_npz(spectra_tpm, self.paths["gene_spectra_tpm"] % tag)
+        save_df_to_text(spectra_tpm, self.paths["gene_spectra_tpm__txt"] % tag)
+        save_df_to_npz(usage_coef, self.paths["gene_spectra_score"] % tag)
+        save_df_to_text(usage_coef, self.paths["gene_spectra_score__txt"] % tag)
+        if show_clustering:
+            self._clustergram(S, topics_dist, density_filter, cluster_labels, local_density, density_threshold, tag,
+                              close_clustergram_fig)
+        if build_ref:
+            self.build_reference(k, density_threshold)
+
+    def _clustergram(self, S, topics_dist, density_filter, labels, local_density, density_threshold, tag, close_fig):
+        """Figure of cnmf.py:986-1079 -- visualisation, outside the accelerated path; needs matplotlib."""
+        try:
+            import matplotlib.pyplot as plt
+            from scipy.cluster.hierarchy import leaves_list, linkage
+            from scipy.spatial.distance import squareform
+        except Exception:
+            warnings.warn("matplotlib is not installed: skipping the clustergram figure", UserWarning)
+            return
+        if topics_dist is None:
+            _, topics_dist = S.local_density(1, return_dist=True)
+        else:
+            keep = density_filter.values
+            topics_dist = topics_dist[keep, :][:, keep]
+        order = []
+        for cl in sorted(set(labels)):
+            f = (labels == cl).values
+            if f.sum() > 1:
+                d = squareform(topics_dist[f, :][:, f], checks=False)
+                d[d < 0] = 0
+                order += list(np.where(f)[0][leaves_list(linkage(d, "average"))])
+            else:
+                order += list(np.where(f)[0])
+        fig = plt.figure(figsize=(10, 9.5))
+        ax = fig.add_axes([0.08, 0.05, 0.6, 0.85])
+        D = topics_dist[order, :][:, order]
+        im = ax.imshow(D, interpolation="none", cmap="viridis", aspect="auto", rasterized=True)
+        ax.set_xticks([]); ax.set_yticks([])
+        hax = fig.add_axes([0.75, 0.6, 0.22, 0.3])
+        hax.hist(local_density.values, bins=np.linspace(0, 1, 50))
+        hax.axvline(density_threshold, linestyle="--", color="k")
+        hax.set_title("Local density histogram")
+        fig.colorbar(im, cax=fig.add_axes([0.75, 0.45, 0.22, 0.02]), orientation="horizontal")
+        fig.savefig(self.paths["clustering_plot"] % tag, dpi=250)
+        if close_fig:
+            plt.close(fig)
+
+    def build_reference(self, k, density_threshold=0.5, target_sum=1e6):
+        """cnmf.py:1085-1116 (small pandas post-step)."""
+        dt_repl = str(density_threshold).replace(".", "_")
+        spectra_tpm = pd.read_csv(self.paths["gene_spectra_tpm__txt"] % (k, dt_repl), index_col=0, sep="\t")
+        hvgs = open(self.paths["nmf_genes_list"]).read().split("\n")
+        tpm_stats = load_df_from_npz(self.paths["tpm_stats"])
+        tpm_stats.index = spectra_tpm.columns
+        renorm = spectra_tpm.div(spectra_tpm.sum(axis=1), axis=0) * target_sum
+        ref = renorm.div(tpm_stats["__std"])[hvgs].copy()
+        ref.index = "GEP" + ref.index.astype("str")
+        save_df_to_npz(ref, self.paths["starcat_spectra"] % (k, dt_repl))
+        save_df_to_text(ref, self.paths["starcat_spectra__txt"] % (k, dt_repl))
+
+    def k_selection_plot(self, close_fig=False):
+        """cnmf.py:1119-1158: stability (silhouette) and prediction error for every K."""
+        run_params = load_df_from_npz(self.paths["nmf_replicate_parameters"])
+        norm_counts = cio.read_matrix(self.paths["normalized_counts"])
+        stats = []
+        for k in sorted(set(run_params.n_components)):
+            stats.append(self.consensus(int(k), skip_density_and_return_after_stats=True, show_clustering=False,
+                                        close_clustergram_fig=True, norm_counts=norm_counts).stats)
+        stats = pd.DataFrame(stats)
+        stats.reset_index(drop=True, inplace=True)
+        save_df_to_npz(stats, self.paths["k_selection_stats"])
+        try:
+            import matplotlib.pyplot as plt
+        except Exception:
+            warnings.warn("matplotlib is not installed: k_selection statistics saved, figure skipped", UserWarning)
+            return stats
+        fig = plt.figure(figsize=(6, 4))
+        ax1 = fig.add_subplot(111)
+        ax2 = ax1.twinx()
+        ax1.plot(stats.k, stats.silhouette, "o-", color="b")
+        ax1.set_ylabel("Stability", color="b", fontsize=15)
+        ax2.plot(stats.k, stats.prediction_error, "o-", color="r")
+        ax2.set_ylabel("Error", color="r", fontsize=15)
+        ax1.set_xlabel("Number of Components", fontsize=15)
+        ax1.grid("on")
+        plt.tight_layout()
+        fig.savefig(self.paths["k_selection_plot"], dpi=250)
+        if close_fig:
+            plt.close(fig)
+        return stats
+
+    def load_results(self, K, density_threshold, n_top_genes=100, norm_usage=True):
+        """cnmf.py:1161-1210."""
+        dt = str(density_threshold).replace(".", "_")
+        scores = pd.read_csv(self.paths["gene_spectra_score__txt"] % (K, dt), sep="\t", index_col=0).T
+        tpm = pd.read_csv(self.paths["gene_spectra_tpm__txt"] % (K, dt), sep="\t", index_col=0).T
+        usage = pd.read_csv(self.paths["consensus_usages__txt"] % (K, dt), sep="\t", index_col=0)
+        if norm_usage:
+            usage = usage.div(usage.sum(axis=1), axis=0)
+        try:
+            usage.columns = [int(x) for x in usage.columns]
+        except Exception:
+            print("Usage matrix columns include non integer values")
+        top = [list(scores.sort_values(by=g, ascending=False).index[:n_top_genes]) for g in scores.columns]
+        top_genes = pd.DataFrame(top, index=scores.columns).T
+        return usage, scores, tpm, top_genes
+
+
+def main():
+    """`cnmf {prepare,factorize,combine,consensus,k_selection_plot}` with the reference's flags (cnmf.py:1213-1294)."""
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("command", type=str, choices=["prepare", "factorize", "combine", "consensus", "k_selection_plot"])
+    ap.add_argument("--name", type=str, nargs="?", default="cNMF")
+    ap.add_argument("--output-dir", type=str, nargs="?", default=".")
+    ap.add_argument("-c", "--counts", type=str)
+    ap.add_argument("-k", "--components", type=int, nargs="+")
+    ap.add_argument("-n", "--n-iter", type=int, default=100)
+    ap.add_argument("--total-workers", type=int, default=1)
+    ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--genes-file", type=str, default=None)
+    ap.add_argument("--numgenes", type=int, default=2000)
+    ap.add_argument("--tpm", type=str, default=None)
+    ap.add_argument("--max-nmf-iter", type=int, default=1000)
+    ap.add_argument("--beta-loss", type=str, choices=["frobenius", "kullback-leibler", "itakura-saito"], default="frobenius")
+    ap.add_argument("--init", type=str, choices=["random", "nndsvd"], default="random")
+    ap.add_argument("--densify", dest="densify", action="store_true", default=False)
+    ap.add_argument("--worker-index", type=int, default=0)
+    ap.add_argument("--skip-completed-runs", action="store_true", default=False)
+    ap.add_argument("--local-density-threshold", type=float, default=0.5)
+    ap.add_argument("--local-neighborhood-size", type=float, default=0.30)
+    ap.add_argument("--show-clustering", dest="show_clustering", action="store_true")
+    ap.add_argument("--build-reference", dest="build_reference", action="store_true", default=True)
+    ap.add_argument("--precision", type=str, choices=["tf32x3", "fp32"], default="tf32x3",
+                    help="[cnmf_b200] GEMM arithmetic: tcgen05 3xTF32 (default) or FFMA fp32")
+    a = ap.parse_args()
+    obj = cNMF(output_dir=a.output_dir, name=a.name, precision=a.precision)
+    if a.command == "prepare":
+        obj.prepare(a.counts, components=a.components, n_iter=a.n_iter, densify=a.densify, tpm_fn=a.tpm, seed=a.seed,
+                    beta_loss=a.beta_loss, max_NMF_iter=a.max_nmf_iter, num_highvar_genes=a.numgenes,
+                    genes_file=a.genes_file, init=a.init)
+    elif a.command == "factorize":
+        obj.factorize(worker_i=a.worker_index, total_workers=a.total_workers, skip_completed_runs=a.skip_completed_runs)
+    elif a.command == "combine":
+        obj.combine(components=a.components)
+    elif a.command == "consensus":
+        rp = load_df_from_npz(obj.paths["nmf_replicate_parameters"])
+        ks = sorted(set(rp.n_components)) if a.components is None else a.components
+        for k in ks:
+            obj.consensus(int(k), a.local_density_threshold, a.local_neighborhood_size, a.show_clustering,
+                          a.build_reference, close_clustergram_fig=True)
+    elif a.command == "k_selection_plot":
+        obj.k_selection_plot(close_fig=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,12 @@ int cnmf_destroy(cnmf_handle_t h);
 /* number of kernels this library has launched through the handle since creation */
 long long cnmf_launch_count(cnmf_handle_t h);
 
+/* per-launch CUDA-event timing of the dominant kernel (the batched GEMM) on its launching stream:
+ * enable (resets the counters), run, then read total device ms, launches and algorithmic FLOPs
+ * (2*M*N*K per launch, counted once -- not 3x for the 3xTF32 passes) */
+int cnmf_profile_enable(cnmf_handle_t h, int on);
+int cnmf_profile_get(cnmf_handle_t h, double* gemm_ms, long long* gemm_launches, double* gemm_flops);
+
 /* ---- dataset: a cells x genes matrix made resident on the device ------------------- */
 /* Replaces `norm_counts.X` / `tpm.X` handed to _nmf (cnmf.py:726,741,873,919,950-952).
  * Builds the device-side forms both GEMM orientations need (X, X^T, tf32 pieces) and
@@ -67,6 +73,8 @@ int cnmf_dataset_from_columns(cnmf_dataset_t src, const int32_t* cols_host, cons
                               int n_cols, void* stream, cnmf_dataset_t* out);
 int cnmf_dataset_destroy(cnmf_dataset_t d);
 int cnmf_dataset_shape(cnmf_dataset_t d, int* n_rows, int* n_cols);
+/* padded row strides of the packed factor layout: W^T rows (ld_rows >= n_rows), H rows (ld_cols >= n_cols) */
+int cnmf_dataset_ld(cnmf_dataset_t d, int* ld_rows, int* ld_cols);
 int cnmf_dataset_sums(cnmf_dataset_t d, double* sum, double* sum_sq);
 /* per-column mean and population variance (StandardScaler(with_mean=False), cnmf.py:131-134) */
 int cnmf_dataset_col_stats(cnmf_dataset_t d, double* mean_host, double* var_host, void* stream);
@@ -94,6 +102,12 @@ int cnmf_factorize(cnmf_dataset_t d, int n_restarts, const int32_t* ks, const ui
 int cnmf_factorize_init(cnmf_dataset_t d, int n_restarts, const int32_t* ks, const float* Wt0_host,
                         const float* H0_host, const cnmf_nmf_params* params, float* spectra_host,
                         float* usages_host, int32_t* n_iter_host, double* err_host, void* stream);
+
+/* Device-resident form: initial factors and the output stay on the GPU (packed, padded strides from
+ * cnmf_dataset_ld): Wt0_dev (sum ks) x ld_rows, H0_dev / spectra_dev (sum ks) x ld_cols. */
+int cnmf_factorize_dev(cnmf_dataset_t d, int n_restarts, const int32_t* ks, const float* Wt0_dev,
+                       const float* H0_dev, const cnmf_nmf_params* params, float* spectra_dev,
+                       int32_t* n_iter_host, double* err_host, void* stream);
 
 /* ---- NNLS refit: replaces cNMF.refit_usage / refit_spectra (cnmf.py:776-820) ------- */
 /* NMF with one factor fixed (sklearn update_H=False), same solver as factorize (cnmf.py:792).

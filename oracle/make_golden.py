@@ -18,6 +18,9 @@ Fixture ``<tag>.npz`` (one per solver, tags ``sim_mu`` / ``sim_cd``) holds
   density_k<K>    reference local_density_cache
   cspectra_k<K>, cusages_k<K>, score_k<K>, tpmspec_k<K>   reference consensus() outputs
   stats_k<K>      [k, dt, silhouette, prediction_error] from consensus(skip_density...=True)
+  fp32dev_k<K>    per restart: rel-L2 between scikit-learn's OWN float32 path and the reference (float64)
+                  spectra for the same seed -- a conditioning yardstick for fp32-class implementations
+                  (computed with a direct sklearn call; the reference itself always runs float64)
 Everything derives from RandomState seeds, so the script is reproducible bit for bit on the
 same library versions (numpy 2.3.5, scikit-learn 1.9.0, pandas 3.0.2).
 """
@@ -74,6 +77,18 @@ def run_case(tag, spec):
         for k in ks:
             merged = ref.load_df_from_npz(obj.paths["merged_spectra"] % k)
             out["merged_k%d" % k] = merged.values
+            from sklearn.decomposition import non_negative_factorization
+            norm = refshim._read(obj.paths["normalized_counts"])
+            dev = []
+            for _, p in table[table.n_components == k].sort_values("iter").iterrows():
+                kw = dict(run_params)
+                kw.update(n_components=int(k), random_state=int(p["nmf_seed"]))
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    _, H32, _ = non_negative_factorization(np.asarray(norm.X, dtype=np.float32), **kw)
+                ref_H = merged.values[int(p["iter"]) * k:(int(p["iter"]) + 1) * k]
+                dev.append(np.linalg.norm(H32 - ref_H) / np.linalg.norm(ref_H))
+            out["fp32dev_k%d" % k] = np.array(dev)
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
                 stats = obj.consensus(k, skip_density_and_return_after_stats=True, show_clustering=False)

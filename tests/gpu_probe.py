@@ -72,6 +72,18 @@ def stage_nmf(precision):
             it, itr, rel(W, Wr), e, nmf_ref.frobenius_error(g["X"], Wr, H)), flush=True)
 
 
+def stage_gemmperf():
+    eng = Engine()
+    rng = np.random.RandomState(0)
+    for name, (M, N, K, sp) in {"XHt_c2": (1000, 20000, 2000, 1), "WtX_c2": (1000, 2000, 20000, 9)}.items():
+        A = np.abs(rng.randn(M, K)).astype(np.float32)
+        B = np.abs(rng.randn(N, K)).astype(np.float32)
+        C, ms = eng.gemm_abt(A, B, precision="tf32x3", splits=sp, reps=10)
+        ref = A.astype(np.float64) @ B.astype(np.float64).T
+        print("gemmperf chain=%s %s: %.3f ms %.1f algo TFLOP/s rel=%.3e" % (
+            os.environ.get("CNMF_CHAIN_KB", "1"), name, ms, 2.0 * M * N * K / ms / 1e9, rel(C, ref)), flush=True)
+
+
 def stage_perf():
     eng = Engine()
     rng = np.random.RandomState(0)
@@ -178,3 +190,5 @@ if __name__ == "__main__":
         stage_perf()
     elif st == "consensus":
         stage_consensus()
+    elif st == "gemmperf":
+        stage_gemmperf()

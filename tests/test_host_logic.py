@@ -1,0 +1,143 @@
+"""CPU tests: C-ABI surface, host RNG, file ledger, prepare(), job sharding, gloo all-gather."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from cnmf_b200 import _lib, cNMF, load_df_from_npz, save_df_to_npz  # noqa: E402
+from cnmf_b200.parallel import shard_jobs  # noqa: E402
+from cnmf_b200.pipeline import worker_filter  # noqa: E402
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "cnmf_b200.h")).read()
+    declared = set(re.findall(r"\b(cnmf_[a-z0-9_]+)\s*\(", header))
+    declared -= {"cnmf_nmf_params"}
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libcnmf_b200.so does not export %s" % name
+    # and the Python binding table covers exactly the header
+    assert set(_lib.SIGNATURES) == declared
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cnmf_b200.engine import Engine
+    with pytest.raises(_lib.CnmfError, match="no CPU fallback"):
+        Engine()
+
+
+def test_host_rng_bit_exact_with_numpy_legacy_stream():
+    lib = _lib.load()
+    for seed, n, g, k in ((1, 50, 30, 3), (2 ** 31 - 2, 333, 77, 7), (123456789, 1000, 300, 13)):
+        avg = 0.731
+        ldw, ldh = n + 5, g + 3
+        Wt = np.zeros((k, ldw), np.float32)
+        H = np.zeros((k, ldh), np.float32)
+        rc = lib.cnmf_random_init_host(seed, avg, n, g, k, _lib.ptr(Wt), ldw, _lib.ptr(H), ldh)
+        assert rc == 0
+        rng = np.random.RandomState(seed)        # sklearn _nmf.py:296-307: H first, then W
+        H2 = np.abs(avg * rng.standard_normal((k, g))).astype(np.float32)
+        W2 = np.abs(avg * rng.standard_normal((n, k))).astype(np.float32)
+        assert np.array_equal(H[:, :g], H2)
+        assert np.array_equal(Wt[:, :n], W2.T)
+        assert not Wt[:, n:].any() and not H[:, g:].any()
+
+
+def test_df_npz_codec_layout(tmp_path):
+    df = pd.DataFrame(np.arange(6.0).reshape(2, 3), index=[1, 2], columns=["a", "b", "c"])
+    fn = str(tmp_path / "x.df.npz")
+    save_df_to_npz(df, fn)
+    with np.load(fn, allow_pickle=True) as f:
+        assert sorted(f.files) == ["columns", "data", "index"]      # cnmf.py:31-32
+    back = load_df_from_npz(fn)
+    assert back.equals(df)
+
+
+def test_path_table_matches_reference(tmp_path):
+    obj = cNMF(output_dir=str(tmp_path), name="run")
+    assert obj.paths["iter_spectra"] % (7, 3) == os.path.join(str(tmp_path), "run", "cnmf_tmp", "run.spectra.k_7.iter_3.df.npz")
+    assert obj.paths["consensus_usages__txt"] % (7, "0_1") == os.path.join(str(tmp_path), "run", "run.usages.k_7.dt_0_1.consensus.txt")
+    ref_file = "/root/reference/src/cnmf/cnmf.py"
+    if os.path.exists(ref_file):          # build container only: compare against the reference's own table
+        from oracle import refshim
+        ref = refshim.load_reference().cNMF(output_dir=str(tmp_path), name="run")
+        assert ref.paths == obj.paths
+
+
+def test_worker_split_rules():
+    assert list(worker_filter(range(10), 1, 3)) == [1, 4, 7]          # cnmf.py:52-53
+    jobs = [shard_jobs(23, r, 4) for r in range(4)]
+    assert sorted(sum(jobs, [])) == list(range(23))
+    assert jobs[2] == list(worker_filter(range(23), 2, 4))
+
+
+def test_prepare_matches_reference_outputs(tmp_path, golden):
+    """prepare() on the golden counts reproduces what the reference wrote: HVG choice, seed table, solver."""
+    counts = golden["counts"].astype(np.float64)
+    df = pd.DataFrame(counts, index=["c%d" % i for i in range(counts.shape[0])],
+                      columns=["g%d" % i for i in range(counts.shape[1])])
+    fn = str(tmp_path / "counts.df.npz")
+    save_df_to_npz(df, fn)
+    obj = cNMF(output_dir=str(tmp_path), name="p")
+    beta = 2.0 if golden["solver"] == "mu" else "frobenius"
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        obj.prepare(fn, components=list(golden["ks"]), n_iter=int(golden["n_iter"]), seed=int(golden["seed"]),
+                    beta_loss=beta, num_highvar_genes=len(golden["hvg_idx"]), densify=True)
+    hvgs = open(obj.paths["nmf_genes_list"]).read().split("\n")
+    assert [int(g[1:]) for g in hvgs] == list(golden["hvg_idx"])
+    table = load_df_from_npz(obj.paths["nmf_replicate_parameters"])
+    assert np.array_equal(table[["n_components", "iter", "nmf_seed"]].values.astype(np.int64), golden["table"])
+    import yaml
+    kw = yaml.load(open(obj.paths["nmf_run_parameters"]), Loader=yaml.FullLoader)
+    assert kw["solver"] == golden["solver"] and kw["tol"] == 1e-4 and kw["max_iter"] == 1000
+    from cnmf_b200 import io as cio
+    norm = cio.read_matrix(obj.paths["normalized_counts"])
+    assert np.allclose(norm.X, golden["X"], rtol=1e-12, atol=0)
+    stats = load_df_from_npz(obj.paths["tpm_stats"])
+    assert np.allclose(stats["__std"].values, golden["tpm_std"], rtol=1e-12)
+
+
+_GLOO_SCRIPT = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+from cnmf_b200.parallel import init_process_group, allgather_spectra, shard_jobs, dist_info
+dist = init_process_group("gloo")
+rank, world, _ = dist_info()
+ks = [3, 3, 3, 4, 4, 4, 5]
+G = 11
+def spec(j):   # deterministic content per job
+    return (np.arange(ks[j] * G, dtype=np.float32).reshape(ks[j], G) + 1000 * j)
+jobs = shard_jobs(len(ks), rank, world)
+full = allgather_spectra([spec(j) for j in jobs], jobs, ks, G)
+ok = all(np.array_equal(full[j], spec(j)) for j in range(len(ks)))
+dist.barrier()
+print("RANK%%d_OK=%%s" %% (rank, ok))
+dist.destroy_process_group()
+"""
+
+
+def test_allgather_spectra_gloo_world2(tmp_path):
+    script = tmp_path / "gloo_case.py"
+    script.write_text(_GLOO_SCRIPT % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
+    procs = []
+    for r in range(2):
+        e = dict(env, RANK=str(r), LOCAL_RANK=str(r))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    for r, o in enumerate(outs):
+        assert "RANK%d_OK=True" % r in o, o
