@@ -85,141 +85,270 @@ int run_gemm(cnmf_handle_s* h, int precision, const float* A, const float* A_hi,
 }  // namespace
 
 int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_nmf_params& p, cudaStream_t s) {
-  const int R = io.R;
-  CNMF_REQUIRE(R > 0 && (int)io.ks.size() == R, "solve: bad restart list");
+  const int R0 = io.R;
+  CNMF_REQUIRE(R0 > 0 && (int)io.ks.size() == R0, "solve: bad restart list");
   CNMF_REQUIRE(p.solver == CNMF_SOLVER_MU || p.solver == CNMF_SOLVER_CD, "solve: unknown solver");
   CNMF_REQUIRE(p.max_iter >= 1, "solve: max_iter must be >= 1");
   const bool tf32 = p.precision == CNMF_PRECISION_TF32X3;
   const bool mu = p.solver == CNMF_SOLVER_MU;
 
-  std::vector<int> off(R);
-  int SK = 0, kmax = 0;
-  for (int r = 0; r < R; ++r) {
+  // ---- slot tables (host mirrors); slot s holds restart rid[s] at packed rows [off[s], off[s]+k[s])
+  std::vector<int> off0(R0), s_off(R0), s_k(io.ks), s_rid(R0);
+  int SK0 = 0, kmax = 0;
+  for (int r = 0; r < R0; ++r) {
     CNMF_REQUIRE(io.ks[r] >= 1 && io.ks[r] <= KMAX, "solve: n_components must be in [1, 32] on the CUDA path");
-    off[r] = SK;
-    SK += io.ks[r];
+    off0[r] = s_off[r] = SK0;
+    s_rid[r] = r;
+    SK0 += io.ks[r];
     kmax = std::max(kmax, io.ks[r]);
   }
+  int R = R0, SK = SK0;     // live slots / live packed rows
   const int kp = kmax <= 8 ? 8 : (kmax <= 16 ? 16 : 32);
   const int chunks_r = col_chunks(v.n_r), chunks_c = col_chunks(v.n_c);
   const int chunks_max = std::max(chunks_r, chunks_c);
 
   // ---- workspace
-  int* d_meta = static_cast<int*>(h->dev_buf("solve.meta", sizeof(int) * 4 * R));
-  double* d_state = static_cast<double*>(h->dev_buf("solve.state", sizeof(double) * 8 * R));
-  double* d_gram = static_cast<double*>(h->dev_buf("solve.gram", sizeof(double) * 2 * R * KMAX * KMAX));
+  int* d_meta = static_cast<int*>(h->dev_buf("solve.meta", sizeof(int) * 8 * R0));
+  double* d_state = static_cast<double*>(h->dev_buf("solve.state", sizeof(double) * 8 * R0));
+  double* d_gram = static_cast<double*>(h->dev_buf("solve.gram", sizeof(double) * 2 * R0 * KMAX * KMAX));
   double* d_gram_part =
-      static_cast<double*>(h->dev_buf("solve.gram_part", sizeof(double) * (size_t)R * chunks_max * kp * kp));
-  double* d_scal_part = static_cast<double*>(h->dev_buf("solve.scal_part", sizeof(double) * 2 * (size_t)R * chunks_max));
+      static_cast<double*>(h->dev_buf("solve.gram_part", sizeof(double) * (size_t)R0 * chunks_max * kp * kp));
+  double* d_scal_part = static_cast<double*>(h->dev_buf("solve.scal_part", sizeof(double) * 2 * (size_t)R0 * chunks_max));
   if (!d_meta || !d_state || !d_gram || !d_gram_part || !d_scal_part) return -2;
 
   GemmPlan plan_r, plan_c;   // plan_r: NUM_r = Fc * B_rows^T (reduce over n_c); plan_c: NUM_c = Fr * B_cols^T
-  plan_r.splits = pick_splits(h->sm_count, SK, v.n_r, v.n_c);
-  plan_r.split_stride = (long long)SK * v.ld_r;
-  plan_c.splits = pick_splits(h->sm_count, SK, v.n_c, v.n_r);
-  plan_c.split_stride = (long long)SK * v.ld_c;
-  float* NUMr = static_cast<float*>(h->dev_buf("solve.NUMr", sizeof(float) * plan_r.splits * (size_t)plan_r.split_stride));
-  float* NUMc = io.update_cols
-                    ? static_cast<float*>(h->dev_buf("solve.NUMc", sizeof(float) * plan_c.splits * (size_t)plan_c.split_stride))
-                    : nullptr;
-  if (!NUMr || (io.update_cols && !NUMc)) return -2;
-
-  int* d_off = d_meta;
-  int* d_k = d_meta + R;
-  int* d_done = d_meta + 2 * R;
-  int* d_niter = d_meta + 3 * R;
+  float *NUMr = nullptr, *NUMc = nullptr;
+  auto plan_gemms = [&]() -> int {
+    plan_r.splits = pick_splits(h->sm_count, SK, v.n_r, v.n_c);
+    plan_r.split_stride = (long long)SK * v.ld_r;
+    plan_c.splits = pick_splits(h->sm_count, SK, v.n_c, v.n_r);
+    plan_c.split_stride = (long long)SK * v.ld_c;
+    return 0;
+  };
+  plan_gemms();
+  // size the product buffers for the worst case over all compaction states (splits <= 32 but bounded by SK0 rows)
   {
-    std::vector<int> hm(4 * R, 0);
-    std::memcpy(hm.data(), off.data(), sizeof(int) * R);
-    std::memcpy(hm.data() + R, io.ks.data(), sizeof(int) * R);
-    CNMF_CUDA_CHECK(cudaMemcpyAsync(d_meta, hm.data(), sizeof(int) * 4 * R, cudaMemcpyHostToDevice, s));
-    CNMF_CUDA_CHECK(cudaStreamSynchronize(s));   // hm goes out of scope
+    size_t need_r = 0, need_c = 0;
+    for (int sk = SK0; sk >= 1; sk = (sk > 128 ? sk - 128 : 0)) {
+      need_r = std::max(need_r, (size_t)pick_splits(h->sm_count, sk, v.n_r, v.n_c) * (size_t)sk * v.ld_r);
+      need_c = std::max(need_c, (size_t)pick_splits(h->sm_count, sk, v.n_c, v.n_r) * (size_t)sk * v.ld_c);
+      if (sk <= 128) break;
+    }
+    need_r = std::max(need_r, (size_t)plan_r.splits * (size_t)plan_r.split_stride);
+    need_c = std::max(need_c, (size_t)plan_c.splits * (size_t)plan_c.split_stride);
+    NUMr = static_cast<float*>(h->dev_buf("solve.NUMr", sizeof(float) * need_r));
+    NUMc = io.update_cols ? static_cast<float*>(h->dev_buf("solve.NUMc", sizeof(float) * need_c)) : nullptr;
+    if (!NUMr || (io.update_cols && !NUMc)) return -2;
   }
-  CNMF_CUDA_CHECK(cudaMemsetAsync(d_state, 0, sizeof(double) * 8 * R, s));
-  ConvState st{d_state, d_state + R, d_state + 2 * R, d_done, d_niter};
-  double* d_crossA = d_state + 3 * R;   // finalised scalars: cross / violation of the row half
-  double* d_crossB = d_state + 4 * R;   // ... of the column half
-  double* d_gramR = d_gram;                           // Gram of Fr (e.g. W^T W)
-  double* d_gramC = d_gram + (size_t)R * KMAX * KMAX; // Gram of Fc (e.g. H H^T)
+
+  int* d_off = d_meta;             // [slots]
+  int* d_k = d_meta + R0;          // [slots]
+  int* d_rid = d_meta + 2 * R0;    // [slots]
+  int* d_done = d_meta + 3 * R0;   // [rid]
+  int* d_niter = d_meta + 4 * R0;  // [rid]
+  int* d_tmp = d_meta + 5 * R0;    // 3 * R0 scratch ints for row gathers
+  auto upload_slots = [&]() -> int {
+    std::vector<int> hm(3 * R0, 0);
+    std::memcpy(hm.data(), s_off.data(), sizeof(int) * R);
+    std::memcpy(hm.data() + R0, s_k.data(), sizeof(int) * R);
+    std::memcpy(hm.data() + 2 * R0, s_rid.data(), sizeof(int) * R);
+    CNMF_CUDA_CHECK(cudaMemcpyAsync(d_meta, hm.data(), sizeof(int) * 3 * R0, cudaMemcpyHostToDevice, s));
+    CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+    return 0;
+  };
+  CNMF_TRY(upload_slots());
+  CNMF_CUDA_CHECK(cudaMemsetAsync(d_done, 0, sizeof(int) * 2 * R0, s));
+  CNMF_CUDA_CHECK(cudaMemsetAsync(d_state, 0, sizeof(double) * 8 * R0, s));
+  ConvState st{d_state, d_state + R0, d_state + 2 * R0, d_done, d_niter};
+  double* d_crossA = d_state + 3 * R0;   // finalised scalars: cross / violation of the row half
+  double* d_crossB = d_state + 4 * R0;   // ... of the column half
+  double* d_gramR = d_gram;                            // Gram of Fr (e.g. W^T W), by rid
+  double* d_gramC = d_gram + (size_t)R0 * KMAX * KMAX; // Gram of Fc (e.g. H H^T), by rid
   double* d_scalA = d_scal_part;
-  double* d_scalB = d_scal_part + (size_t)R * chunks_max;
+  double* d_scalB = d_scal_part + (size_t)R0 * chunks_max;
 
-  BatchMeta bm{d_off, d_k, d_done, R, kp};
-  FactorView fr{io.Fr, tf32 ? io.Fr_hi : nullptr, tf32 ? io.Fr_lo : nullptr, v.n_r, v.ld_r};
-  FactorView fc{io.Fc, tf32 ? io.Fc_hi : nullptr, tf32 ? io.Fc_lo : nullptr, v.n_c, v.ld_c};
-  if (!io.update_cols) { fc.F_hi = nullptr; fc.F_lo = nullptr; }   // never rewritten
+  // working factor arrays (start in the caller's buffers; compaction ping-pongs to "solve.alt.*")
+  float *wFr = io.Fr, *wFr_hi = io.Fr_hi, *wFr_lo = io.Fr_lo, *wFc = io.Fc, *wFc_hi = io.Fc_hi, *wFc_lo = io.Fc_lo;
+  float *aFr = nullptr, *aFr_hi = nullptr, *aFr_lo = nullptr, *aFc = nullptr, *aFc_hi = nullptr, *aFc_lo = nullptr;
+  float *resFr = nullptr, *resFc = nullptr;   // final factors of restarts that were compacted away (original offsets)
+  bool compacted = false;
 
+  auto bm = [&]() { return BatchMeta{d_off, d_k, d_rid, d_done, R, kp}; };
+  auto fr = [&]() { return FactorView{wFr, tf32 ? wFr_hi : nullptr, tf32 ? wFr_lo : nullptr, v.n_r, v.ld_r}; };
+  auto fc = [&]() {
+    FactorView f{wFc, tf32 ? wFc_hi : nullptr, tf32 ? wFc_lo : nullptr, v.n_c, v.ld_c};
+    if (!io.update_cols) { f.F_hi = nullptr; f.F_lo = nullptr; }   // never rewritten
+    return f;
+  };
   auto gram_of = [&](const FactorView& f, double* gram_out, int chunks) -> int {
     h->launches += 2;
-    CNMF_TRY(launch_gram_partial(f, bm, d_gram_part, s));
-    return launch_finalize(d_gram_part, gram_out, nullptr, nullptr, chunks, bm, s);
+    CNMF_TRY(launch_gram_partial(f, bm(), d_gram_part, s));
+    return launch_finalize(d_gram_part, gram_out, nullptr, nullptr, chunks, bm(), s);
   };
   auto finalize_scal = [&](const double* part, double* out, int chunks) -> int {
     h->launches += 1;
-    return launch_finalize(nullptr, nullptr, part, out, chunks, bm, s);
+    return launch_finalize(nullptr, nullptr, part, out, chunks, bm(), s);
   };
   auto gemm_rows = [&]() -> int {   // NUM_r = Fc * B_rows^T
-    return run_gemm(h, p.precision, io.Fc, io.Fc_hi, io.Fc_lo, SK, v.ld_c, v.B_rows, NUMr, v.ld_r, plan_r, s);
+    return run_gemm(h, p.precision, wFc, wFc_hi, wFc_lo, SK, v.ld_c, v.B_rows, NUMr, v.ld_r, plan_r, s);
   };
   auto gemm_cols = [&]() -> int {   // NUM_c = Fr * B_cols^T
-    return run_gemm(h, p.precision, io.Fr, io.Fr_hi, io.Fr_lo, SK, v.ld_r, v.B_cols, NUMc, v.ld_c, plan_c, s);
+    return run_gemm(h, p.precision, wFr, wFr_hi, wFr_lo, SK, v.ld_r, v.B_cols, NUMc, v.ld_c, plan_c, s);
   };
 
-  std::vector<int> h_done(R, 0);
+  // gathers `cnt` restarts' rows: dst[dst_off[i] ..] <- src[src_off[i] ..]
+  auto gather = [&](const float* src, float* dst, const std::vector<int>& so, const std::vector<int>& dof,
+                    const std::vector<int>& kk, int ld) -> int {
+    const int cnt = (int)kk.size();
+    if (cnt == 0 || !src || !dst) return 0;
+    std::vector<int> hm(3 * R0, 0);
+    std::memcpy(hm.data(), so.data(), sizeof(int) * cnt);
+    std::memcpy(hm.data() + R0, dof.data(), sizeof(int) * cnt);
+    std::memcpy(hm.data() + 2 * R0, kk.data(), sizeof(int) * cnt);
+    CNMF_CUDA_CHECK(cudaMemcpyAsync(d_tmp, hm.data(), sizeof(int) * 3 * R0, cudaMemcpyHostToDevice, s));
+    h->launches += 1;
+    CNMF_TRY(launch_gather_rows(src, d_tmp, dst, d_tmp + R0, d_tmp + 2 * R0, cnt, ld, s));
+    CNMF_CUDA_CHECK(cudaStreamSynchronize(s));   // hm is reused by the next gather
+    return 0;
+  };
+
+  const double normX2 = v.sum_sq;
+  double* d_cd_err = d_state + 7 * R0;
+  auto cd_final_error = [&]() -> int {
+    int* d_zero = static_cast<int*>(h->dev_buf("solve.zero", sizeof(int) * 2 * R0));
+    if (!d_zero) return -2;
+    CNMF_CUDA_CHECK(cudaMemsetAsync(d_zero, 0, sizeof(int) * 2 * R0, s));
+    BatchMeta bm0{d_off, d_k, d_rid, d_zero, R, kp};
+    h->launches += 7;
+    CNMF_TRY(launch_gram_partial(fr(), bm0, d_gram_part, s));
+    CNMF_TRY(launch_finalize(d_gram_part, d_gramR, nullptr, nullptr, chunks_r, bm0, s));
+    CNMF_TRY(launch_gram_partial(fc(), bm0, d_gram_part, s));
+    CNMF_TRY(launch_finalize(d_gram_part, d_gramC, nullptr, nullptr, chunks_c, bm0, s));
+    if (io.update_cols) {
+      CNMF_TRY(launch_cross(fc(), NUMc, plan_c.splits, plan_c.split_stride, bm0, d_scalB, s));
+      CNMF_TRY(launch_finalize(nullptr, nullptr, d_scalB, d_crossB, chunks_c, bm0, s));
+    } else {
+      CNMF_TRY(launch_cross(fr(), NUMr, plan_r.splits, plan_r.split_stride, bm0, d_scalA, s));
+      CNMF_TRY(launch_finalize(nullptr, nullptr, d_scalA, d_crossB, chunks_r, bm0, s));
+    }
+    ConvState scratch{d_state + 5 * R0, d_state + 6 * R0, d_cd_err, d_zero, d_zero + R0};
+    return launch_mu_check(scratch, d_crossB, d_gramR, d_gramC, normX2, bm0, 0, 0.0, p.max_iter, s);
+  };
+
+  std::vector<int> h_done(R0, 0);
+  // Drop converged restarts from the packed arrays when that saves a 128-row GEMM tile (or >= 1/8 of the rows).
+  auto maybe_compact = [&]() -> int {
+    if (!io.update_cols) return 0;
+    int live_rows = 0;
+    for (int sl = 0; sl < R; ++sl)
+      if (!h_done[s_rid[sl]]) live_rows += s_k[sl];
+    if (live_rows == SK || live_rows == 0) return 0;
+    const bool saves_tile = (live_rows + 127) / 128 < (SK + 127) / 128;
+    if (!saves_tile && live_rows > SK - SK / 8) return 0;
+    if (!mu) CNMF_TRY(cd_final_error());    // restarts leaving the packed arrays get their ||X - WH||_F now
+    if (!aFr) {
+      const size_t nr = (size_t)SK0 * v.ld_r, nc = (size_t)SK0 * v.ld_c;
+      aFr = static_cast<float*>(h->dev_buf("solve.alt.Fr", nr * 4));
+      aFc = static_cast<float*>(h->dev_buf("solve.alt.Fc", nc * 4));
+      resFr = static_cast<float*>(h->dev_buf("solve.res.Fr", nr * 4));
+      resFc = static_cast<float*>(h->dev_buf("solve.res.Fc", nc * 4));
+      if (!aFr || !aFc || !resFr || !resFc) return -2;
+      if (tf32) {
+        aFr_hi = static_cast<float*>(h->dev_buf("solve.alt.Fr_hi", nr * 4));
+        aFr_lo = static_cast<float*>(h->dev_buf("solve.alt.Fr_lo", nr * 4));
+        aFc_hi = static_cast<float*>(h->dev_buf("solve.alt.Fc_hi", nc * 4));
+        aFc_lo = static_cast<float*>(h->dev_buf("solve.alt.Fc_lo", nc * 4));
+        if (!aFr_hi || !aFr_lo || !aFc_hi || !aFc_lo) return -2;
+      }
+    }
+    std::vector<int> f_src, f_dst, f_k, l_src, l_dst, l_k, n_off, n_k, n_rid;
+    int pos = 0;
+    for (int sl = 0; sl < R; ++sl) {
+      const int rid = s_rid[sl];
+      if (h_done[rid]) {
+        f_src.push_back(s_off[sl]); f_dst.push_back(off0[rid]); f_k.push_back(s_k[sl]);
+      } else {
+        l_src.push_back(s_off[sl]); l_dst.push_back(pos); l_k.push_back(s_k[sl]);
+        n_off.push_back(pos); n_k.push_back(s_k[sl]); n_rid.push_back(rid);
+        pos += s_k[sl];
+      }
+    }
+    CNMF_TRY(gather(wFr, resFr, f_src, f_dst, f_k, v.ld_r));       // finished restarts -> result slabs
+    CNMF_TRY(gather(wFc, resFc, f_src, f_dst, f_k, v.ld_c));
+    CNMF_TRY(gather(wFr, aFr, l_src, l_dst, l_k, v.ld_r));          // live restarts -> packed front of the alt buffers
+    CNMF_TRY(gather(wFc, aFc, l_src, l_dst, l_k, v.ld_c));
+    if (tf32) {
+      CNMF_TRY(gather(wFr_hi, aFr_hi, l_src, l_dst, l_k, v.ld_r));
+      CNMF_TRY(gather(wFr_lo, aFr_lo, l_src, l_dst, l_k, v.ld_r));
+      CNMF_TRY(gather(wFc_hi, aFc_hi, l_src, l_dst, l_k, v.ld_c));
+      CNMF_TRY(gather(wFc_lo, aFc_lo, l_src, l_dst, l_k, v.ld_c));
+    }
+    std::swap(wFr, aFr); std::swap(wFr_hi, aFr_hi); std::swap(wFr_lo, aFr_lo);
+    std::swap(wFc, aFc); std::swap(wFc_hi, aFc_hi); std::swap(wFc_lo, aFc_lo);
+    R = (int)n_k.size();
+    SK = pos;
+    std::copy(n_off.begin(), n_off.end(), s_off.begin());
+    std::copy(n_k.begin(), n_k.end(), s_k.begin());
+    std::copy(n_rid.begin(), n_rid.end(), s_rid.begin());
+    CNMF_TRY(upload_slots());
+    plan_gemms();
+    compacted = true;
+    return 0;
+  };
+
   auto poll_all_done = [&]() -> int {   // 1 = all done, 0 = not yet, <0 error
-    CNMF_CUDA_CHECK(cudaMemcpyAsync(h_done.data(), d_done, sizeof(int) * R, cudaMemcpyDeviceToHost, s));
+    CNMF_CUDA_CHECK(cudaMemcpyAsync(h_done.data(), d_done, sizeof(int) * R0, cudaMemcpyDeviceToHost, s));
     CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
-    for (int r = 0; r < R; ++r)
-      if (!h_done[r]) return 0;
+    for (int sl = 0; sl < R; ++sl)
+      if (!h_done[s_rid[sl]]) return maybe_compact();
     return 1;
   };
 
   const float l1W = (float)p.l1_reg_W, l2W = (float)p.l2_reg_W, l1H = (float)p.l1_reg_H, l2H = (float)p.l2_reg_H;
-  const double normX2 = v.sum_sq;
   int it = 0;
 
   if (mu) {
     // ---------------- multiplicative update (sklearn _nmf.py:726-888) ----------------
-    CNMF_TRY(gram_of(fc, d_gramC, chunks_c));
-    CNMF_TRY(gram_of(fr, d_gramR, chunks_r));
+    CNMF_TRY(gram_of(fc(), d_gramC, chunks_c));
+    CNMF_TRY(gram_of(fr(), d_gramR, chunks_r));
     if (io.update_cols) {
       CNMF_TRY(gemm_cols());
       h->launches += 1;
-      CNMF_TRY(launch_cross(fc, NUMc, plan_c.splits, plan_c.split_stride, bm, d_scalB, s));
+      CNMF_TRY(launch_cross(fc(), NUMc, plan_c.splits, plan_c.split_stride, bm(), d_scalB, s));
       CNMF_TRY(finalize_scal(d_scalB, d_crossB, chunks_c));
     } else {
       CNMF_TRY(gemm_rows());          // H fixed: X H^T is computed once (sklearn caches XHt, _nmf.py:537-548)
       h->launches += 1;
-      CNMF_TRY(launch_cross(fr, NUMr, plan_r.splits, plan_r.split_stride, bm, d_scalA, s));
+      CNMF_TRY(launch_cross(fr(), NUMr, plan_r.splits, plan_r.split_stride, bm(), d_scalA, s));
       CNMF_TRY(finalize_scal(d_scalA, d_crossB, chunks_r));
     }
     h->launches += 1;
-    CNMF_TRY(launch_mu_check(st, d_crossB, d_gramR, d_gramC, normX2, bm, 0, p.tol, p.max_iter, s));
+    CNMF_TRY(launch_mu_check(st, d_crossB, d_gramR, d_gramC, normX2, bm(), 0, p.tol, p.max_iter, s));
 
     for (it = 1; it <= p.max_iter; ++it) {
       if (io.update_cols) CNMF_TRY(gemm_rows());
       h->launches += 1;
-      CNMF_TRY(launch_mu_update(fr, NUMr, plan_r.splits, plan_r.split_stride, d_gramC, bm, l1W, l2W,
+      CNMF_TRY(launch_mu_update(fr(), NUMr, plan_r.splits, plan_r.split_stride, d_gramC, bm(), l1W, l2W,
                                 io.update_cols ? nullptr : d_scalA, s));
       if (io.update_cols) {
-        CNMF_TRY(gram_of(fr, d_gramR, chunks_r));
+        CNMF_TRY(gram_of(fr(), d_gramR, chunks_r));
         CNMF_TRY(gemm_cols());
         h->launches += 1;
-        CNMF_TRY(launch_mu_update(fc, NUMc, plan_c.splits, plan_c.split_stride, d_gramR, bm, l1H, l2H, d_scalB, s));
-        CNMF_TRY(gram_of(fc, d_gramC, chunks_c));
+        CNMF_TRY(launch_mu_update(fc(), NUMc, plan_c.splits, plan_c.split_stride, d_gramR, bm(), l1H, l2H, d_scalB, s));
+        CNMF_TRY(gram_of(fc(), d_gramC, chunks_c));
       }
       const bool check = (p.tol > 0 && it % 10 == 0) || it == p.max_iter;
       if (check) {
         if (io.update_cols) {
           CNMF_TRY(finalize_scal(d_scalB, d_crossB, chunks_c));
         } else {
-          CNMF_TRY(gram_of(fr, d_gramR, chunks_r));
+          CNMF_TRY(gram_of(fr(), d_gramR, chunks_r));
           CNMF_TRY(finalize_scal(d_scalA, d_crossB, chunks_r));
         }
         h->launches += 1;
         // at it == max_iter with it % 10 != 0 sklearn does not test; tol = -1 makes the test never fire
         const double tol_eff = (p.tol > 0 && it % 10 == 0) ? p.tol : -1.0;
-        CNMF_TRY(launch_mu_check(st, d_crossB, d_gramR, d_gramC, normX2, bm, it, tol_eff, p.max_iter, s));
+        CNMF_TRY(launch_mu_check(st, d_crossB, d_gramR, d_gramC, normX2, bm(), it, tol_eff, p.max_iter, s));
         const int all = poll_all_done();
         if (all < 0) return all;
         if (all) break;
@@ -230,21 +359,21 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     const int poll_every = 4;
     for (it = 1; it <= p.max_iter; ++it) {
       if (io.update_cols || it == 1) {
-        CNMF_TRY(gram_of(fc, d_gramC, chunks_c));
+        CNMF_TRY(gram_of(fc(), d_gramC, chunks_c));
         CNMF_TRY(gemm_rows());
       }
       h->launches += 1;
-      CNMF_TRY(launch_cd_update(fr, NUMr, plan_r.splits, plan_r.split_stride, d_gramC, bm, l1W, l2W, d_scalA, s));
+      CNMF_TRY(launch_cd_update(fr(), NUMr, plan_r.splits, plan_r.split_stride, d_gramC, bm(), l1W, l2W, d_scalA, s));
       CNMF_TRY(finalize_scal(d_scalA, d_crossA, chunks_r));
       if (io.update_cols) {
-        CNMF_TRY(gram_of(fr, d_gramR, chunks_r));
+        CNMF_TRY(gram_of(fr(), d_gramR, chunks_r));
         CNMF_TRY(gemm_cols());
         h->launches += 1;
-        CNMF_TRY(launch_cd_update(fc, NUMc, plan_c.splits, plan_c.split_stride, d_gramR, bm, l1H, l2H, d_scalB, s));
+        CNMF_TRY(launch_cd_update(fc(), NUMc, plan_c.splits, plan_c.split_stride, d_gramR, bm(), l1H, l2H, d_scalB, s));
         CNMF_TRY(finalize_scal(d_scalB, d_crossB, chunks_c));
       }
       h->launches += 1;
-      CNMF_TRY(launch_cd_check(st, d_crossA, io.update_cols ? d_crossB : nullptr, bm, it, p.tol, p.max_iter, s));
+      CNMF_TRY(launch_cd_check(st, d_crossA, io.update_cols ? d_crossB : nullptr, bm(), it, p.tol, p.max_iter, s));
       if (it % poll_every == 0 || it == p.max_iter) {
         const int all = poll_all_done();
         if (all < 0) return all;
@@ -253,36 +382,31 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     }
   }
 
-  // final ||X - Fr^T Fc||_F for every restart (MU already holds it in st.last from its last check;
-  // CD tracks the projected-gradient violation instead, so evaluate the trace form once here)
+  // final ||X - Fr^T Fc||_F: MU holds it in st.last from each restart's last check; CD tracks the
+  // projected-gradient violation instead, so the trace form is evaluated here for the restarts still
+  // packed (those compacted away earlier were evaluated just before they left)
   double* d_err = st.last;
   if (!mu) {
-    int* d_zero = static_cast<int*>(h->dev_buf("solve.zero", sizeof(int) * 2 * R));
-    if (!d_zero) return -2;
-    CNMF_CUDA_CHECK(cudaMemsetAsync(d_zero, 0, sizeof(int) * 2 * R, s));
-    BatchMeta bm0{d_off, d_k, d_zero, R, kp};
-    h->launches += 7;
-    CNMF_TRY(launch_gram_partial(fr, bm0, d_gram_part, s));
-    CNMF_TRY(launch_finalize(d_gram_part, d_gramR, nullptr, nullptr, chunks_r, bm0, s));
-    CNMF_TRY(launch_gram_partial(fc, bm0, d_gram_part, s));
-    CNMF_TRY(launch_finalize(d_gram_part, d_gramC, nullptr, nullptr, chunks_c, bm0, s));
-    if (io.update_cols) {
-      CNMF_TRY(launch_cross(fc, NUMc, plan_c.splits, plan_c.split_stride, bm0, d_scalB, s));
-      CNMF_TRY(launch_finalize(nullptr, nullptr, d_scalB, d_crossB, chunks_c, bm0, s));
-    } else {
-      CNMF_TRY(launch_cross(fr, NUMr, plan_r.splits, plan_r.split_stride, bm0, d_scalA, s));
-      CNMF_TRY(launch_finalize(nullptr, nullptr, d_scalA, d_crossB, chunks_r, bm0, s));
-    }
-    ConvState scratch{d_state + 5 * R, d_state + 6 * R, d_state + 7 * R, d_zero, d_zero + R};
-    CNMF_TRY(launch_mu_check(scratch, d_crossB, d_gramR, d_gramC, normX2, bm0, 0, 0.0, p.max_iter, s));
-    d_err = scratch.last;
+    CNMF_TRY(cd_final_error());
+    d_err = d_cd_err;
   }
-  io.n_iter.assign(R, 0);
-  io.last.assign(R, 0.0);
-  io.err.assign(R, 0.0);
-  CNMF_CUDA_CHECK(cudaMemcpyAsync(io.n_iter.data(), d_niter, sizeof(int) * R, cudaMemcpyDeviceToHost, s));
-  CNMF_CUDA_CHECK(cudaMemcpyAsync(io.last.data(), st.last, sizeof(double) * R, cudaMemcpyDeviceToHost, s));
-  CNMF_CUDA_CHECK(cudaMemcpyAsync(io.err.data(), d_err, sizeof(double) * R, cudaMemcpyDeviceToHost, s));
+
+  // ---- put every restart's final factors back at its original rows of the caller's buffers
+  if (compacted) {
+    std::vector<int> so(s_off.begin(), s_off.begin() + R), ko(s_k.begin(), s_k.begin() + R), dof(R);
+    for (int sl = 0; sl < R; ++sl) dof[sl] = off0[s_rid[sl]];
+    CNMF_TRY(gather(wFr, resFr, so, dof, ko, v.ld_r));
+    CNMF_TRY(gather(wFc, resFc, so, dof, ko, v.ld_c));
+    CNMF_CUDA_CHECK(cudaMemcpyAsync(io.Fr, resFr, (size_t)SK0 * v.ld_r * 4, cudaMemcpyDeviceToDevice, s));
+    CNMF_CUDA_CHECK(cudaMemcpyAsync(io.Fc, resFc, (size_t)SK0 * v.ld_c * 4, cudaMemcpyDeviceToDevice, s));
+  }
+
+  io.n_iter.assign(R0, 0);
+  io.last.assign(R0, 0.0);
+  io.err.assign(R0, 0.0);
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(io.n_iter.data(), d_niter, sizeof(int) * R0, cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(io.last.data(), st.last, sizeof(double) * R0, cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(io.err.data(), d_err, sizeof(double) * R0, cudaMemcpyDeviceToHost, s));
   CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
   h->prof_collect();
   return 0;

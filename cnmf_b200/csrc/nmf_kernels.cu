@@ -100,9 +100,10 @@ template <int KP>
 __global__ void __launch_bounds__(UPD_THREADS)
 mu_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
                  const double* __restrict__ gram, BatchMeta b, float l1, float l2, double* __restrict__ cross_partial) {
-  const int r = blockIdx.y;
+  const int slot = blockIdx.y;
+  const int r = b.rid[slot];
   if (b.done[r]) return;
-  const int K = b.k[r], o = b.off[r];
+  const int K = b.k[slot], o = b.off[slot];
   __shared__ float G[KP][KP + 1];
   __shared__ double red[32];
   for (int idx = threadIdx.x; idx < KP * KP; idx += UPD_THREADS) {
@@ -152,9 +153,10 @@ template <int KP>
 __global__ void __launch_bounds__(UPD_THREADS)
 cd_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
                  const double* __restrict__ gram, BatchMeta b, float l1, float l2, double* __restrict__ viol_partial) {
-  const int r = blockIdx.y;
+  const int slot = blockIdx.y;
+  const int r = b.rid[slot];
   if (b.done[r]) return;
-  const int K = b.k[r], o = b.off[r];
+  const int K = b.k[slot], o = b.off[slot];
   __shared__ float G[KP][KP + 1];
   __shared__ double red[32];
   for (int idx = threadIdx.x; idx < KP * KP; idx += UPD_THREADS) {
@@ -210,9 +212,10 @@ cd_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long l
 __global__ void __launch_bounds__(UPD_THREADS)
 cross_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride, BatchMeta b,
              double* __restrict__ cross_partial) {
-  const int r = blockIdx.y;
+  const int slot = blockIdx.y;
+  const int r = b.rid[slot];
   if (b.done[r]) return;
-  const int K = b.k[r], o = b.off[r];
+  const int K = b.k[slot], o = b.off[slot];
   __shared__ double red[32];
   const int col_begin = blockIdx.x * UPD_COLS_PER_BLOCK;
   const int col_end = min(f.n, col_begin + UPD_COLS_PER_BLOCK);
@@ -234,9 +237,10 @@ template <int KP>
 __global__ void __launch_bounds__(KP * KP)
 gram_partial_kernel(FactorView f, BatchMeta b, double* __restrict__ gram_partial) {
   constexpr int TILE = 128;
-  const int r = blockIdx.y;
+  const int slot = blockIdx.y;
+  const int r = b.rid[slot];
   if (b.done[r]) return;
-  const int K = b.k[r], o = b.off[r];
+  const int K = b.k[slot], o = b.off[slot];
   __shared__ float s[KP][TILE + 1];
   const int c = threadIdx.x / KP, i = threadIdx.x % KP;
   const int col_begin = blockIdx.x * UPD_COLS_PER_BLOCK;
@@ -261,7 +265,7 @@ gram_partial_kernel(FactorView f, BatchMeta b, double* __restrict__ gram_partial
 __global__ void finalize_kernel(const double* __restrict__ gram_partial, double* __restrict__ gram,
                                 const double* __restrict__ scal_partial, double* __restrict__ scal, int chunks,
                                 BatchMeta b) {
-  const int r = blockIdx.x;
+  const int r = b.rid[blockIdx.x];
   if (b.done[r]) return;
   const int KP = b.kp;
   if (gram_partial) {
@@ -283,9 +287,11 @@ __global__ void finalize_kernel(const double* __restrict__ gram_partial, double*
 __global__ void mu_check_kernel(ConvState st, const double* __restrict__ cross, const double* __restrict__ gramA,
                                 const double* __restrict__ gramB, double normX2, BatchMeta b, int it, double tol,
                                 int max_iter) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= b.R || st.done[r]) return;
-  const int K = b.k[r];
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= b.R) return;
+  const int r = b.rid[slot];
+  if (st.done[r]) return;
+  const int K = b.k[slot];
   double dot = 0.0;
   for (int c = 0; c < K; ++c)
     for (int i = 0; i < K; ++i)
@@ -311,8 +317,10 @@ __global__ void mu_check_kernel(ConvState st, const double* __restrict__ cross, 
 
 __global__ void cd_check_kernel(ConvState st, const double* __restrict__ violA, const double* __restrict__ violB,
                                 BatchMeta b, int it, double tol, int max_iter) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= b.R || st.done[r]) return;
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= b.R) return;
+  const int r = b.rid[slot];
+  if (st.done[r]) return;
   const double viol = violA[r] + (violB ? violB[r] : 0.0);
   st.last[r] = viol;
   if (it == 1) st.err0[r] = viol;

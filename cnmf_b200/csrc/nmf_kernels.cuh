@@ -23,11 +23,15 @@ struct FactorView {
   int ld;
 };
 
+// "slot" = position of a live restart in the packed arrays (changes when converged restarts are
+// compacted away); "rid" = its index in the caller's restart list (never changes).  Packed factor
+// rows are addressed by slot, every per-restart state array (done, n_iter, Gram, scalars) by rid.
 struct BatchMeta {
-  const int* off;  // [R] first packed row of restart r
-  const int* k;    // [R] n_components of restart r
-  const int* done; // [R] 1 = converged, frozen
-  int R;
+  const int* off;  // [slots] first packed row of the restart in slot s
+  const int* k;    // [slots] its n_components
+  const int* rid;  // [slots] its restart id
+  const int* done; // [n restarts] 1 = converged, frozen (indexed by rid)
+  int R;           // live slots
   int kp;          // 8, 16 or 32: >= max k in the batch (template dispatch)
 };
 
@@ -86,7 +90,7 @@ int launch_mu_check(const ConvState& st, const double* cross, const double* gram
 int launch_cd_check(const ConvState& st, const double* violA, const double* violB, const BatchMeta& b, int it,
                     double tol, int max_iter, cudaStream_t s);
 
-// packed-row gather: dst rows [dst_off[r], +k[r]) <- src rows [src_off[r], +k[r])  for r < R (compaction / output)
+// packed-row gather: dst rows [dst_off[i], +k[i]) <- src rows [src_off[i], +k[i])  for i < R (compaction / output)
 int launch_gather_rows(const float* src, const int* src_off, float* dst, const int* dst_off, const int* k, int R,
                        int n_ld, cudaStream_t s);
 
