@@ -122,10 +122,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
-template <int BN>
-__device__ __forceinline__ constexpr uint32_t make_idesc() {
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
   // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major A and B, N>>3 @17, M>>4 @24
-  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
          (static_cast<uint32_t>(BM >> 4) << 24);
 }
 
@@ -149,7 +148,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    float* __restrict__ C, int M, int N, int ldc, long long c_split_stride,
-                   int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split, int chain_kb) {
+                   int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split, int chain_kb, int bn) {
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024 B alignment
@@ -203,11 +202,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 0);
           const uint32_t st = smem_base + stage * L::STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), L::STAGE_BYTES);
+          mbar_arrive_expect_tx(full_bar(stage), 2u * L::A_BYTES + 2u * static_cast<uint32_t>(bn) * BK * 4u);
           tma_load_2d(st, &tmA_hi, full_bar(stage), kb * BK, mt * BM);
           tma_load_2d(st + L::A_BYTES, &tmA_lo, full_bar(stage), kb * BK, mt * BM);
-          tma_load_2d(st + 2 * L::A_BYTES, &tmB_hi, full_bar(stage), kb * BK, nt * BN);
-          tma_load_2d(st + 2 * L::A_BYTES + L::B_BYTES, &tmB_lo, full_bar(stage), kb * BK, nt * BN);
+          tma_load_2d(st + 2 * L::A_BYTES, &tmB_hi, full_bar(stage), kb * BK, nt * bn);
+          tma_load_2d(st + 2 * L::A_BYTES + L::B_BYTES, &tmB_lo, full_bar(stage), kb * BK, nt * bn);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -215,7 +214,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<BN>();
+      const uint32_t idesc = make_idesc(bn);               // UMMA N = bn (multiple of 16, <= BN)
       int stage = 0;
       uint32_t phase = 0;
       int buf = 0;
@@ -277,11 +276,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                                static_cast<uint32_t>(buf * BN + half * HALF);
 #pragma unroll
         for (int c = 0; c < HALF; c += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c, r);
-          tmem_ld_wait();
+          if (half * HALF + c < bn) {                  // warp-uniform: columns >= bn were not computed
+            uint32_t r[32];
+            tmem_ld32(taddr + c, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[c + i] += __uint_as_float(r[i]);     // round-to-nearest fp32
+            for (int i = 0; i < 32; ++i) acc[c + i] += __uint_as_float(r[i]);   // round-to-nearest fp32
+          }
         }
         tc_fence_before();
         mbar_arrive(tempty_bar(buf));
@@ -290,10 +291,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       const int row = mt * BM + q * 32 + lane;
       if (row < M) {
         float* crow = C + static_cast<long long>(z) * c_split_stride + static_cast<long long>(row) * ldc;
-        const int col0 = nt * BN + half * HALF;
+        const int col0 = nt * bn + half * HALF;
 #pragma unroll
         for (int i = 0; i < HALF; i += 4) {
-          if (col0 + i + 3 < ldc)
+          if (half * HALF + i < bn && col0 + i + 3 < ldc)
             *reinterpret_cast<float4*>(crow + col0 + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
         }
       }
@@ -351,11 +352,28 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   int rc;
   if ((rc = make_map(&mAh, g.A_hi, g.M, g.Kd, g.lda, BM))) return rc;
   if ((rc = make_map(&mAl, g.A_lo, g.M, g.Kd, g.lda, BM))) return rc;
-  if ((rc = make_map(&mBh, g.B_hi, g.N, g.Kd, g.ldb, BN))) return rc;
-  if ((rc = make_map(&mBl, g.B_lo, g.N, g.Kd, g.ldb, BN))) return rc;
-
+  int dev = 0, sms = 0;
+  CNMF_CUDA_CHECK(cudaGetDevice(&dev));
+  CNMF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int m_tiles = (g.M + BM - 1) / BM;
-  const int n_tiles = (g.N + BN - 1) / BN;
+  // Tile width: the UMMA N is a runtime value (multiple of 16, <= BN).  Pick the width that minimises
+  // (waves of the persistent grid) x (tile width), i.e. the wave-quantisation loss; ties go to the widest.
+  int bn = BN;
+  {
+    const int sp = gemm_effective_splits(g.Kd, g.splits);
+    long long best = -1;
+    for (int cand = BN; cand >= 128; cand -= 16) {
+      const long long tiles = (long long)m_tiles * ((g.N + cand - 1) / cand) * sp;
+      const long long cost = ((tiles + sms - 1) / sms) * cand;
+      if (best < 0 || cost < best) { best = cost; bn = cand; }
+    }
+    static const int env_bn = [] { const char* e = std::getenv("CNMF_GEMM_BN"); return e ? std::atoi(e) : 0; }();
+    if (env_bn >= 16 && env_bn <= BN && env_bn % 16 == 0) bn = env_bn;
+  }
+  if ((rc = make_map(&mBh, g.B_hi, g.N, g.Kd, g.ldb, bn))) return rc;
+  if ((rc = make_map(&mBl, g.B_lo, g.N, g.Kd, g.ldb, bn))) return rc;
+
+  const int n_tiles = (g.N + bn - 1) / bn;
   const int total_kb = (g.Kd + BK - 1) / BK;
   int splits = g.splits < 1 ? 1 : g.splits;
   if (splits > total_kb) splits = total_kb;
@@ -369,9 +387,6 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
     CNMF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     attr_set = true;
   }
-  int dev = 0, sms = 0;
-  CNMF_CUDA_CHECK(cudaGetDevice(&dev));
-  CNMF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int items = m_tiles * n_tiles * splits;
   const int grid = items < sms ? items : sms;
   int chain_kb = g.chain_kb;
@@ -385,7 +400,7 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   }
   kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(mAh, mAl, mBh, mBl, g.C, g.M, g.N, g.ldc, g.c_split_stride,
                                                     m_tiles, n_tiles, splits, total_kb, kb_per_split,
-                                                    chain_kb);
+                                                    chain_kb, bn);
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

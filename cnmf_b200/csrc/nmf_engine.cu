@@ -180,10 +180,10 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     if (!io.update_cols) { f.F_hi = nullptr; f.F_lo = nullptr; }   // never rewritten
     return f;
   };
-  auto gram_of = [&](const FactorView& f, double* gram_out, int chunks) -> int {
+  auto gram_of = [&](const FactorView& f, double* gram_out, int /*scalar chunks, unused*/) -> int {
     h->launches += 2;
     CNMF_TRY(launch_gram_partial(f, bm(), d_gram_part, s));
-    return launch_finalize(d_gram_part, gram_out, nullptr, nullptr, chunks, bm(), s);
+    return launch_finalize(d_gram_part, gram_out, nullptr, nullptr, gram_chunks(f.n), bm(), s);
   };
   auto finalize_scal = [&](const double* part, double* out, int chunks) -> int {
     h->launches += 1;
@@ -221,9 +221,9 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     BatchMeta bm0{d_off, d_k, d_rid, d_zero, R, kp};
     h->launches += 7;
     CNMF_TRY(launch_gram_partial(fr(), bm0, d_gram_part, s));
-    CNMF_TRY(launch_finalize(d_gram_part, d_gramR, nullptr, nullptr, chunks_r, bm0, s));
+    CNMF_TRY(launch_finalize(d_gram_part, d_gramR, nullptr, nullptr, gram_chunks(v.n_r), bm0, s));
     CNMF_TRY(launch_gram_partial(fc(), bm0, d_gram_part, s));
-    CNMF_TRY(launch_finalize(d_gram_part, d_gramC, nullptr, nullptr, chunks_c, bm0, s));
+    CNMF_TRY(launch_finalize(d_gram_part, d_gramC, nullptr, nullptr, gram_chunks(v.n_c), bm0, s));
     if (io.update_cols) {
       CNMF_TRY(launch_cross(fc(), NUMc, plan_c.splits, plan_c.split_stride, bm0, d_scalB, s));
       CNMF_TRY(launch_finalize(nullptr, nullptr, d_scalB, d_crossB, chunks_c, bm0, s));

@@ -114,31 +114,43 @@ mu_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long l
   const int col_begin = blockIdx.x * UPD_COLS_PER_BLOCK;
   const int col_end = min(f.n, col_begin + UPD_COLS_PER_BLOCK);
   double cross = 0.0;
+  float* __restrict__ Fp = f.F;
+  float* __restrict__ Fhi = f.F_hi;
+  float* __restrict__ Flo = f.F_lo;
   for (int col = col_begin + threadIdx.x; col < col_end; col += UPD_THREADS) {
-    float fv[KP];
+    // all loads of this column first (2K independent requests in flight per thread), then math, then stores
+    float fv[KP], nv[KP];
 #pragma unroll
-    for (int i = 0; i < KP; ++i) fv[i] = (i < K) ? f.F[(long long)(o + i) * f.ld + col] : 0.f;
+    for (int i = 0; i < KP; ++i) {
+      const long long e = (long long)(o + i) * f.ld + col;
+      fv[i] = (i < K) ? Fp[e] : 0.f;
+      float num = (i < K) ? NUM[e] : 0.f;
+      for (int s = 1; s < nsplit; ++s) num += (i < K) ? NUM[s * sstride + e] : 0.f;
+      nv[i] = num;
+    }
+    float fn[KP];
+#pragma unroll
+    for (int c = 0; c < KP; ++c) {
+      float den = 0.f;
+#pragma unroll
+      for (int i = 0; i < KP; ++i) den = fmaf(G[c][i], fv[i], den);
+      if (l1 > 0.f) den += l1;
+      if (l2 > 0.f) den += l2 * fv[c];
+      if (den == 0.f) den = EPSILON_F32;
+      fn[c] = fv[c] * (nv[c] / den);
+    }
 #pragma unroll
     for (int c = 0; c < KP; ++c) {
       if (c < K) {
         const long long e = (long long)(o + c) * f.ld + col;
-        float num = NUM[e];
-        for (int s = 1; s < nsplit; ++s) num += NUM[s * sstride + e];
-        float den = 0.f;
-#pragma unroll
-        for (int i = 0; i < KP; ++i) den = fmaf(G[c][i], fv[i], den);
-        if (l1 > 0.f) den += l1;
-        if (l2 > 0.f) den += l2 * fv[c];
-        if (den == 0.f) den = EPSILON_F32;
-        const float fn = fv[c] * (num / den);
-        f.F[e] = fn;
-        if (f.F_hi) {
+        Fp[e] = fn[c];
+        if (Fhi) {
           float h, l;
-          split_tf32(fn, h, l);
-          f.F_hi[e] = h;
-          f.F_lo[e] = l;
+          split_tf32(fn[c], h, l);
+          Fhi[e] = h;
+          Flo[e] = l;
         }
-        cross += (double)num * (double)fn;
+        cross += (double)nv[c] * (double)fn[c];
       }
     }
   }
@@ -169,17 +181,23 @@ cd_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long l
   const int col_begin = blockIdx.x * UPD_COLS_PER_BLOCK;
   const int col_end = min(f.n, col_begin + UPD_COLS_PER_BLOCK);
   double viol = 0.0;
+  float* __restrict__ Fp = f.F;
+  float* __restrict__ Fhi = f.F_hi;
+  float* __restrict__ Flo = f.F_lo;
   for (int col = col_begin + threadIdx.x; col < col_end; col += UPD_THREADS) {
-    float fv[KP];
+    float fv[KP], nv[KP];
 #pragma unroll
-    for (int i = 0; i < KP; ++i) fv[i] = (i < K) ? f.F[(long long)(o + i) * f.ld + col] : 0.f;
+    for (int i = 0; i < KP; ++i) {
+      const long long e = (long long)(o + i) * f.ld + col;
+      fv[i] = (i < K) ? Fp[e] : 0.f;
+      float num = (i < K) ? NUM[e] : 0.f;
+      for (int s = 1; s < nsplit; ++s) num += (i < K) ? NUM[s * sstride + e] : 0.f;
+      nv[i] = num;
+    }
 #pragma unroll
     for (int t = 0; t < KP; ++t) {
       if (t < K) {
-        const long long e = (long long)(o + t) * f.ld + col;
-        float num = NUM[e];
-        for (int s = 1; s < nsplit; ++s) num += NUM[s * sstride + e];
-        float g = l1 - num;                             // -(XHt - l1), sklearn _nmf.py:386-388
+        float g = l1 - nv[t];                           // -(XHt - l1), sklearn _nmf.py:386-388
 #pragma unroll
         for (int i = 0; i < KP; ++i) g = fmaf(G[t][i], fv[i], g);
         const float pg = (fv[t] == 0.f) ? fminf(0.f, g) : g;
@@ -192,12 +210,12 @@ cd_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long l
     for (int t = 0; t < KP; ++t) {
       if (t < K) {
         const long long e = (long long)(o + t) * f.ld + col;
-        f.F[e] = fv[t];
-        if (f.F_hi) {
+        Fp[e] = fv[t];
+        if (Fhi) {
           float h, l;
           split_tf32(fv[t], h, l);
-          f.F_hi[e] = h;
-          f.F_lo[e] = l;
+          Fhi[e] = h;
+          Flo[e] = l;
         }
       }
     }
@@ -233,33 +251,78 @@ cross_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long 
 }
 
 // ------------------------------------------------------------------ K x K Gram partials
+// Register-tiled: a thread owns RB rows x KP columns of the K x K Gram and walks over columns of F,
+// so every loaded value feeds RB FMAs straight from registers (no shared-memory operand traffic).
+// KP/RB threads cooperate on one column; partial sums are fp32 over <= GRAM_COLS_PER_THREAD columns,
+// then fp64 through a fixed-order shared-memory reduction (deterministic).
 template <int KP>
-__global__ void __launch_bounds__(KP * KP)
+struct GramCfg {
+  static constexpr int RB = KP == 32 ? 4 : 8;          // rows of the Gram per thread
+  static constexpr int TPC = KP / RB;                  // threads per column (1, 2, 8)
+  static constexpr int THREADS = 256;
+  static constexpr int COLS_PER_ITER = THREADS / TPC;  // columns advanced per block iteration
+};
+
+template <int KP>
+__global__ void __launch_bounds__(256)
 gram_partial_kernel(FactorView f, BatchMeta b, double* __restrict__ gram_partial) {
-  constexpr int TILE = 128;
+  using C = GramCfg<KP>;
   const int slot = blockIdx.y;
   const int r = b.rid[slot];
   if (b.done[r]) return;
   const int K = b.k[slot], o = b.off[slot];
-  __shared__ float s[KP][TILE + 1];
-  const int c = threadIdx.x / KP, i = threadIdx.x % KP;
-  const int col_begin = blockIdx.x * UPD_COLS_PER_BLOCK;
-  const int col_end = min(f.n, col_begin + UPD_COLS_PER_BLOCK);
-  double acc = 0.0;
-  for (int c0 = col_begin; c0 < col_end; c0 += TILE) {
-    for (int idx = threadIdx.x; idx < KP * TILE; idx += KP * KP) {
-      const int row = idx / TILE, cc = idx % TILE;
-      const int col = c0 + cc;
-      s[row][cc] = (row < K && col < col_end) ? f.F[(long long)(o + row) * f.ld + col] : 0.f;
+  const int rb = threadIdx.x % C::TPC;                 // which row block of the Gram
+  const int cl = threadIdx.x / C::TPC;                 // column lane inside the block
+  const int col_begin = blockIdx.x * GRAM_COLS_PER_BLOCK;
+  const int col_end = min(f.n, col_begin + GRAM_COLS_PER_BLOCK);
+  float acc[C::RB][KP];
+#pragma unroll
+  for (int a = 0; a < C::RB; ++a)
+#pragma unroll
+    for (int i = 0; i < KP; ++i) acc[a][i] = 0.f;
+  const float* __restrict__ Fp = f.F;
+  for (int col = col_begin + cl; col < col_end; col += C::COLS_PER_ITER) {
+    float fv[KP];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) fv[i] = (i < K) ? Fp[(long long)(o + i) * f.ld + col] : 0.f;
+#pragma unroll
+    for (int a = 0; a < C::RB; ++a) {
+      float fa = 0.f;                                   // fv[rb * RB + a] without dynamic register indexing
+#pragma unroll
+      for (int t = 0; t < C::TPC; ++t)
+        if (t == rb) fa = fv[t * C::RB + a];
+#pragma unroll
+      for (int i = 0; i < KP; ++i) acc[a][i] = fmaf(fa, fv[i], acc[a][i]);
+    }
+  }
+  // reduction over the column lanes: xor-shuffles among the lanes that share a row block (lane % TPC),
+  // then the 8 warps' partials are summed in fixed order through shared memory -- all in fp64
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ double part[8][C::TPC][KP];
+  double* out = gram_partial + ((long long)r * gridDim.x + blockIdx.x) * (KP * KP);
+#pragma unroll
+  for (int a = 0; a < C::RB; ++a) {
+    double v[KP];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) v[i] = (double)acc[a][i];
+#pragma unroll
+    for (int sh = 16; sh >= C::TPC; sh >>= 1)
+#pragma unroll
+      for (int i = 0; i < KP; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], sh);
+    __syncthreads();
+    if (lane < C::TPC) {
+#pragma unroll
+      for (int i = 0; i < KP; ++i) part[warp][lane][i] = v[i];
     }
     __syncthreads();
-    float a = 0.f;
-#pragma unroll 16
-    for (int j = 0; j < TILE; ++j) a = fmaf(s[c][j], s[i][j], a);
-    acc += (double)a;
-    __syncthreads();
+    if (threadIdx.x < C::TPC * KP) {
+      const int rbb = threadIdx.x / KP, i = threadIdx.x % KP;
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += part[w][rbb][i];
+      out[(rbb * C::RB + a) * KP + i] = sum;
+    }
   }
-  gram_partial[((long long)r * gridDim.x + blockIdx.x) * (KP * KP) + threadIdx.x] = acc;
 }
 
 __global__ void finalize_kernel(const double* __restrict__ gram_partial, double* __restrict__ gram,
@@ -409,8 +472,8 @@ int launch_cross(const FactorView& f, const float* NUM, int nsplit, long long ss
 }
 
 int launch_gram_partial(const FactorView& f, const BatchMeta& b, double* gram_partial, cudaStream_t s) {
-  dim3 grid(col_chunks(f.n), b.R);
-  CNMF_DISPATCH_KP(b.kp, (gram_partial_kernel<KP><<<grid, KP * KP, 0, s>>>(f, b, gram_partial)));
+  dim3 grid(gram_chunks(f.n), b.R);
+  CNMF_DISPATCH_KP(b.kp, (gram_partial_kernel<KP><<<grid, 256, 0, s>>>(f, b, gram_partial)));
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -13,7 +13,8 @@
 namespace cnmf {
 
 constexpr int UPD_THREADS = 256;
-constexpr int UPD_COLS_PER_BLOCK = 2048;   // columns handled by one block of the update / gram kernels
+constexpr int UPD_COLS_PER_BLOCK = 2048;   // columns handled by one block of the update kernels
+constexpr int GRAM_COLS_PER_BLOCK = 8192;  // columns handled by one block of the Gram kernel
 
 struct FactorView {
   float* F;        // SK x ld, in/out
@@ -36,6 +37,7 @@ struct BatchMeta {
 };
 
 inline int col_chunks(int n) { return (n + UPD_COLS_PER_BLOCK - 1) / UPD_COLS_PER_BLOCK; }
+inline int gram_chunks(int n) { return (n + GRAM_COLS_PER_BLOCK - 1) / GRAM_COLS_PER_BLOCK; }
 
 // x -> (hi, lo) tf32 pieces, elementwise over rows x ld (padding included)
 int launch_split_tf32(const float* src, float* hi, float* lo, long long n_elems, cudaStream_t s);
@@ -66,7 +68,7 @@ int launch_cd_update(const FactorView& f, const float* NUM, int nsplit, long lon
 int launch_cross(const FactorView& f, const float* NUM, int nsplit, long long num_split_stride, const BatchMeta& b,
                  double* cross_partial, cudaStream_t s);
 
-// gram_partial[(r*chunks+chunk)*kp*kp + c*kp + i] = sum_j F[c,j] F[i,j] over the chunk's columns
+// gram_partial[(rid*gram_chunks+chunk)*kp*kp + c*kp + i] = sum_j F[c,j] F[i,j] over the chunk's columns
 int launch_gram_partial(const FactorView& f, const BatchMeta& b, double* gram_partial, cudaStream_t s);
 
 // gram[r][c*KMAX+i] = sum over chunks (fixed order -> deterministic); scal[r] = sum over chunks of scal_partial
