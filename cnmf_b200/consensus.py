@@ -196,6 +196,25 @@ def cluster_medians(S, labels_t, k):
     return M[:, :S.G].cpu().numpy().astype(np.float64)
 
 
+def silhouette(S, labels, labels_t, k):
+    """sklearn.metrics.silhouette_score(l2_spectra, labels, metric='euclidean') (cnmf.py:923): the R x R
+    distances and the per-sample per-cluster distance sums come from the GPU, the O(R*K) rest is numpy."""
+    sums = np.empty((S.R, k), np.float64)
+    check(S.lib.cnmf_cluster_dist_sums(S.engine._h, S.p, S.R, S.G, S.ld, ctypes.c_void_p(labels_t.data_ptr()), k,
+                                       ptr(sums), None))
+    counts = np.bincount(labels, minlength=k).astype(np.float64)
+    own = counts[labels]
+    idx = np.arange(S.R)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        a = sums[idx, labels] / (own - 1.0)
+        mean_other = sums / counts[None, :]
+        mean_other[idx, labels] = np.inf
+        b = mean_other.min(axis=1)
+        sil = (b - a) / np.maximum(a, b)
+    sil[own == 1] = 0.0
+    return float(np.nan_to_num(sil).mean())
+
+
 def ols_zscore(usages, tpm_ds):
     """efficient_ols_all_cols(rf_usages, tpm.X, normalize_y=True) (cnmf.py:55-125).
     U^T Z with Z = (T - mean)/std equals (U - mean(U))^T T / std because the columns of T - mean sum to

@@ -270,6 +270,37 @@ __global__ void row_normalize_sum_kernel(float* __restrict__ M, int G, int ldm) 
   for (int g = threadIdx.x; g < G; g += blockDim.x) row[g] = (float)((double)row[g] / s);
 }
 
+// per-row sums of distances to the members of every cluster (silhouette_score, cnmf.py:923):
+// one block per row; per-warp cluster bins in shared memory, folded in warp order (deterministic)
+__global__ void __launch_bounds__(256)
+cluster_dist_sums_kernel(const float* __restrict__ D, int R, const int32_t* __restrict__ labels, int K,
+                         double* __restrict__ out /* R x K */) {
+  extern __shared__ double bins[];        // 8 warps x K
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) bins[i] = 0.0;
+  __syncthreads();
+  const float* row = D + (long long)blockIdx.x * R;
+  // each warp owns a contiguous slice of columns and walks it in order, lane by lane
+  const int per = (R + 7) / 8;
+  const int j0 = warp * per, j1 = min(R, j0 + per);
+  for (int jb = j0; jb < j1; jb += 32) {
+    const int j = jb + lane;
+    const double v = (j < j1) ? (double)row[j] : 0.0;
+    const int lab = (j < j1) ? labels[j] : -1;
+    for (int l = 0; l < 32; ++l) {        // serialise the lanes: fixed summation order
+      const double vl = __shfl_sync(0xffffffffu, v, l);
+      const int ll = __shfl_sync(0xffffffffu, lab, l);
+      if (lane == 0 && ll >= 0) bins[warp * K + ll] += vl;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < K; c += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += bins[w * K + c];
+    out[(long long)blockIdx.x * K + c] = s;
+  }
+}
+
 __global__ void col_stats_dev_kernel(const float* __restrict__ X, int rows, int cols, int ld, double* __restrict__ sum,
                                     double* __restrict__ sq) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -339,6 +370,24 @@ int cnmf_col_stats_dev(cnmf_handle_t h, const float* S, int R, int G, int ld, do
     mean_host[c] = m;
     var_host[c] = std::max(var_host[c] / R - m * m, 0.0);
   }
+  return 0;
+}
+
+int cnmf_cluster_dist_sums(cnmf_handle_t h, const float* S, int R, int G, int ld, const int32_t* labels_dev, int K,
+                           double* sums_host, void* stream) {
+  CNMF_REQUIRE(h && S && labels_dev && sums_host && R > 0 && K >= 1 && K <= 512, "cluster_dist_sums: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  float* D = static_cast<float*>(h->dev_buf("consensus.D", (size_t)R * R * 4));
+  double* out = static_cast<double*>(h->dev_buf("consensus.dsums", sizeof(double) * (size_t)R * K));
+  if (!D || !out) return -2;
+  dim3 grid((R + 63) / 64, (R + 63) / 64);
+  pair_dist_kernel<true><<<grid, 256, 0, s>>>(S, R, ld, S, R, ld, G, D, R);
+  cluster_dist_sums_kernel<<<R, 256, sizeof(double) * 8 * K, s>>>(D, R, labels_dev, K, out);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  h->launches += 2;
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(sums_host, out, sizeof(double) * (size_t)R * K, cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
   return 0;
 }
 

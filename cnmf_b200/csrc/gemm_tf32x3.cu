@@ -362,7 +362,7 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   {
     const int sp = gemm_effective_splits(g.Kd, g.splits);
     long long best = -1;
-    for (int cand = BN; cand >= 128; cand -= 16) {
+    for (int cand = BN; cand >= 16; cand -= 16) {
       const long long tiles = (long long)m_tiles * ((g.N + cand - 1) / cand) * sp;
       const long long cost = ((tiles + sms - 1) / sms) * cand;
       if (best < 0 || cost < best) { best = cost; bn = cand; }

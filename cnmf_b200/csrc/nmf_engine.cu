@@ -146,7 +146,6 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   int* d_rid = d_meta + 2 * R0;    // [slots]
   int* d_done = d_meta + 3 * R0;   // [rid]
   int* d_niter = d_meta + 4 * R0;  // [rid]
-  int* d_tmp = d_meta + 5 * R0;    // 3 * R0 scratch ints for row gathers
   auto upload_slots = [&]() -> int {
     std::vector<int> hm(3 * R0, 0);
     std::memcpy(hm.data(), s_off.data(), sizeof(int) * R);
@@ -196,20 +195,31 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     return run_gemm(h, p.precision, wFr, wFr_hi, wFr_lo, SK, v.ld_r, v.B_cols, NUMc, v.ld_c, plan_c, s);
   };
 
-  // gathers `cnt` restarts' rows: dst[dst_off[i] ..] <- src[src_off[i] ..]
+  // gathers `cnt` restarts' rows: dst[dst_off[i] ..] <- src[src_off[i] ..].  Index triples go through a pinned
+  // ring of GATHER_SLOTS entries so that consecutive gathers need no host synchronisation in between; the
+  // caller synchronises the stream before the ring wraps (upload_slots / the final sync do).
+  constexpr int GATHER_SLOTS = 12;
+  int* h_gidx = static_cast<int*>(h->host_buf("solve.gather_idx", sizeof(int) * 3 * (size_t)R0 * GATHER_SLOTS));
+  int* d_gidx = static_cast<int*>(h->dev_buf("solve.gather_didx", sizeof(int) * 3 * (size_t)R0 * GATHER_SLOTS));
+  if (!h_gidx || !d_gidx) return -2;
+  int gslot = 0;
   auto gather = [&](const float* src, float* dst, const std::vector<int>& so, const std::vector<int>& dof,
                     const std::vector<int>& kk, int ld) -> int {
     const int cnt = (int)kk.size();
     if (cnt == 0 || !src || !dst) return 0;
-    std::vector<int> hm(3 * R0, 0);
-    std::memcpy(hm.data(), so.data(), sizeof(int) * cnt);
-    std::memcpy(hm.data() + R0, dof.data(), sizeof(int) * cnt);
-    std::memcpy(hm.data() + 2 * R0, kk.data(), sizeof(int) * cnt);
-    CNMF_CUDA_CHECK(cudaMemcpyAsync(d_tmp, hm.data(), sizeof(int) * 3 * R0, cudaMemcpyHostToDevice, s));
+    if (gslot == GATHER_SLOTS) {
+      CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+      gslot = 0;
+    }
+    int* hm = h_gidx + (size_t)gslot * 3 * R0;
+    int* dm = d_gidx + (size_t)gslot * 3 * R0;
+    ++gslot;
+    std::memcpy(hm, so.data(), sizeof(int) * cnt);
+    std::memcpy(hm + R0, dof.data(), sizeof(int) * cnt);
+    std::memcpy(hm + 2 * R0, kk.data(), sizeof(int) * cnt);
+    CNMF_CUDA_CHECK(cudaMemcpyAsync(dm, hm, sizeof(int) * 3 * R0, cudaMemcpyHostToDevice, s));
     h->launches += 1;
-    CNMF_TRY(launch_gather_rows(src, d_tmp, dst, d_tmp + R0, d_tmp + 2 * R0, cnt, ld, s));
-    CNMF_CUDA_CHECK(cudaStreamSynchronize(s));   // hm is reused by the next gather
-    return 0;
+    return launch_gather_rows(src, dm, dst, dm + R0, dm + 2 * R0, cnt, ld, s);
   };
 
   const double normX2 = v.sum_sq;
@@ -290,7 +300,8 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     std::copy(n_off.begin(), n_off.end(), s_off.begin());
     std::copy(n_k.begin(), n_k.end(), s_k.begin());
     std::copy(n_rid.begin(), n_rid.end(), s_rid.begin());
-    CNMF_TRY(upload_slots());
+    CNMF_TRY(upload_slots());      // synchronises the stream: the gather ring can be reused
+    gslot = 0;
     plan_gemms();
     compacted = true;
     return 0;

@@ -96,21 +96,25 @@ __global__ void sums_final_kernel(const double* __restrict__ part, int nblocks, 
 }
 
 // ------------------------------------------------------------------ multiplicative update
+// Thread = one item (cell / gene) column.  Register budget is kept small (3 blocks of 256 threads per SM):
+// the K x K Gram is re-read from shared memory for every column through a volatile pointer (broadcast
+// LDS.128) instead of being cached in 256 registers -- a 255-register version of this kernel ran at ~1 TB/s.
 template <int KP>
-__global__ void __launch_bounds__(UPD_THREADS)
+__global__ void __launch_bounds__(UPD_THREADS, KP == 32 ? 2 : 3)
 mu_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
                  const double* __restrict__ gram, BatchMeta b, float l1, float l2, double* __restrict__ cross_partial) {
   const int slot = blockIdx.y;
   const int r = b.rid[slot];
   if (b.done[r]) return;
   const int K = b.k[slot], o = b.off[slot];
-  __shared__ float G[KP][KP + 1];
+  __shared__ __align__(16) float G[KP * KP];
   __shared__ double red[32];
   for (int idx = threadIdx.x; idx < KP * KP; idx += UPD_THREADS) {
     const int c = idx / KP, i = idx % KP;
-    G[c][i] = (c < K && i < K) ? (float)gram[(long long)r * KMAX * KMAX + c * KMAX + i] : 0.f;
+    G[idx] = (c < K && i < K) ? (float)gram[(long long)r * KMAX * KMAX + c * KMAX + i] : 0.f;
   }
   __syncthreads();
+  const volatile float4* Gv = reinterpret_cast<const volatile float4*>(G);
   const int col_begin = blockIdx.x * UPD_COLS_PER_BLOCK;
   const int col_end = min(f.n, col_begin + UPD_COLS_PER_BLOCK);
   double cross = 0.0;
@@ -128,29 +132,31 @@ mu_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long l
       for (int s = 1; s < nsplit; ++s) num += (i < K) ? NUM[s * sstride + e] : 0.f;
       nv[i] = num;
     }
-    float fn[KP];
-#pragma unroll
-    for (int c = 0; c < KP; ++c) {
-      float den = 0.f;
-#pragma unroll
-      for (int i = 0; i < KP; ++i) den = fmaf(G[c][i], fv[i], den);
-      if (l1 > 0.f) den += l1;
-      if (l2 > 0.f) den += l2 * fv[c];
-      if (den == 0.f) den = EPSILON_F32;
-      fn[c] = fv[c] * (nv[c] / den);
-    }
 #pragma unroll
     for (int c = 0; c < KP; ++c) {
       if (c < K) {
+        float den = 0.f;
+#pragma unroll
+        for (int i4 = 0; i4 < KP / 4; ++i4) {
+          const volatile float4& gq = Gv[c * (KP / 4) + i4];
+          den = fmaf(gq.x, fv[4 * i4 + 0], den);
+          den = fmaf(gq.y, fv[4 * i4 + 1], den);
+          den = fmaf(gq.z, fv[4 * i4 + 2], den);
+          den = fmaf(gq.w, fv[4 * i4 + 3], den);
+        }
+        if (l1 > 0.f) den += l1;
+        if (l2 > 0.f) den += l2 * fv[c];
+        if (den == 0.f) den = EPSILON_F32;
+        const float fn = fv[c] * (nv[c] / den);
         const long long e = (long long)(o + c) * f.ld + col;
-        Fp[e] = fn[c];
+        Fp[e] = fn;
         if (Fhi) {
           float h, l;
-          split_tf32(fn[c], h, l);
+          split_tf32(fn, h, l);
           Fhi[e] = h;
           Flo[e] = l;
         }
-        cross += (double)nv[c] * (double)fn[c];
+        cross += (double)nv[c] * (double)fn;
       }
     }
   }
@@ -162,22 +168,24 @@ mu_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long l
 
 // ------------------------------------------------------------------ coordinate descent sweep
 template <int KP>
-__global__ void __launch_bounds__(UPD_THREADS)
+__global__ void __launch_bounds__(UPD_THREADS, KP == 32 ? 2 : 3)
 cd_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
                  const double* __restrict__ gram, BatchMeta b, float l1, float l2, double* __restrict__ viol_partial) {
   const int slot = blockIdx.y;
   const int r = b.rid[slot];
   if (b.done[r]) return;
   const int K = b.k[slot], o = b.off[slot];
-  __shared__ float G[KP][KP + 1];
+  __shared__ __align__(16) float G[KP * KP];
   __shared__ double red[32];
   for (int idx = threadIdx.x; idx < KP * KP; idx += UPD_THREADS) {
     const int c = idx / KP, i = idx % KP;
     float g = (c < K && i < K) ? (float)gram[(long long)r * KMAX * KMAX + c * KMAX + i] : 0.f;
     if (c == i && c < K) g += l2;                       // sklearn _nmf.py:383-385
-    G[c][i] = g;
+    G[idx] = g;
   }
   __syncthreads();
+  const volatile float4* Gv = reinterpret_cast<const volatile float4*>(G);
+  const volatile float* Gs = G;
   const int col_begin = blockIdx.x * UPD_COLS_PER_BLOCK;
   const int col_end = min(f.n, col_begin + UPD_COLS_PER_BLOCK);
   double viol = 0.0;
@@ -199,23 +207,24 @@ cd_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long l
       if (t < K) {
         float g = l1 - nv[t];                           // -(XHt - l1), sklearn _nmf.py:386-388
 #pragma unroll
-        for (int i = 0; i < KP; ++i) g = fmaf(G[t][i], fv[i], g);
+        for (int i4 = 0; i4 < KP / 4; ++i4) {           // same summation order as the Cython loop (r = 0..K-1)
+          const volatile float4& gq = Gv[t * (KP / 4) + i4];
+          g = fmaf(gq.x, fv[4 * i4 + 0], g);
+          g = fmaf(gq.y, fv[4 * i4 + 1], g);
+          g = fmaf(gq.z, fv[4 * i4 + 2], g);
+          g = fmaf(gq.w, fv[4 * i4 + 3], g);
+        }
         const float pg = (fv[t] == 0.f) ? fminf(0.f, g) : g;
         viol += (double)fabsf(pg);
-        const float h = G[t][t];
+        const float h = Gs[t * KP + t];
         if (h != 0.f) fv[t] = fmaxf(fv[t] - g / h, 0.f);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < KP; ++t) {
-      if (t < K) {
         const long long e = (long long)(o + t) * f.ld + col;
         Fp[e] = fv[t];
         if (Fhi) {
-          float h, l;
-          split_tf32(fv[t], h, l);
-          Fhi[e] = h;
-          Flo[e] = l;
+          float hh, ll;
+          split_tf32(fv[t], hh, ll);
+          Fhi[e] = hh;
+          Flo[e] = ll;
         }
       }
     }
@@ -252,15 +261,31 @@ cross_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long 
 
 // ------------------------------------------------------------------ K x K Gram partials
 // Register-tiled: a thread owns RB rows x KP columns of the K x K Gram and walks over columns of F,
-// so every loaded value feeds RB FMAs straight from registers (no shared-memory operand traffic).
-// KP/RB threads cooperate on one column; partial sums are fp32 over <= GRAM_COLS_PER_THREAD columns,
-// then fp64 through a fixed-order shared-memory reduction (deterministic).
+// VEC columns at a time through 8/16-byte loads (KP*VEC values in flight per thread: the first version
+// of this kernel, one 4-byte column per step, was latency-bound at ~0.6 TB/s with one block per SM).
+// KP/RB threads cooperate on one column group; partial sums are fp32 over the thread's columns, then
+// fp64 through shuffles + a fixed-order shared-memory reduction (deterministic).
 template <int KP>
 struct GramCfg {
   static constexpr int RB = KP == 32 ? 4 : 8;          // rows of the Gram per thread
-  static constexpr int TPC = KP / RB;                  // threads per column (1, 2, 8)
+  static constexpr int TPC = KP / RB;                  // threads per column group (1, 2, 8)
+  static constexpr int VEC = KP == 32 ? 2 : 4;         // consecutive columns per load
   static constexpr int THREADS = 256;
-  static constexpr int COLS_PER_ITER = THREADS / TPC;  // columns advanced per block iteration
+  static constexpr int COLS_PER_ITER = (THREADS / TPC) * VEC;   // columns advanced per block iteration
+};
+
+template <int VEC> struct VecLoad;
+template <> struct VecLoad<4> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+};
+template <> struct VecLoad<2> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[2]) {
+    const float2 q = *reinterpret_cast<const float2*>(p);
+    v[0] = q.x; v[1] = q.y;
+  }
 };
 
 template <int KP>
@@ -272,27 +297,37 @@ gram_partial_kernel(FactorView f, BatchMeta b, double* __restrict__ gram_partial
   if (b.done[r]) return;
   const int K = b.k[slot], o = b.off[slot];
   const int rb = threadIdx.x % C::TPC;                 // which row block of the Gram
-  const int cl = threadIdx.x / C::TPC;                 // column lane inside the block
+  const int cl = threadIdx.x / C::TPC;                 // column-group lane inside the block
   const int col_begin = blockIdx.x * GRAM_COLS_PER_BLOCK;
-  const int col_end = min(f.n, col_begin + GRAM_COLS_PER_BLOCK);
+  const int col_end = min(f.n, col_begin + GRAM_COLS_PER_BLOCK);   // padding columns (< ld) hold zeros
   float acc[C::RB][KP];
 #pragma unroll
   for (int a = 0; a < C::RB; ++a)
 #pragma unroll
     for (int i = 0; i < KP; ++i) acc[a][i] = 0.f;
   const float* __restrict__ Fp = f.F;
-  for (int col = col_begin + cl; col < col_end; col += C::COLS_PER_ITER) {
-    float fv[KP];
+  for (int col = col_begin + cl * C::VEC; col < col_end; col += C::COLS_PER_ITER) {
+    float fv[KP][C::VEC];
 #pragma unroll
-    for (int i = 0; i < KP; ++i) fv[i] = (i < K) ? Fp[(long long)(o + i) * f.ld + col] : 0.f;
+    for (int i = 0; i < KP; ++i) {
+      if (i < K) {
+        VecLoad<C::VEC>::ld(Fp + (long long)(o + i) * f.ld + col, fv[i]);
+      } else {
 #pragma unroll
-    for (int a = 0; a < C::RB; ++a) {
-      float fa = 0.f;                                   // fv[rb * RB + a] without dynamic register indexing
+        for (int u = 0; u < C::VEC; ++u) fv[i][u] = 0.f;
+      }
+    }
 #pragma unroll
-      for (int t = 0; t < C::TPC; ++t)
-        if (t == rb) fa = fv[t * C::RB + a];
+    for (int u = 0; u < C::VEC; ++u) {
 #pragma unroll
-      for (int i = 0; i < KP; ++i) acc[a][i] = fmaf(fa, fv[i], acc[a][i]);
+      for (int a = 0; a < C::RB; ++a) {
+        float fa = 0.f;                                 // fv[rb * RB + a][u] without dynamic register indexing
+#pragma unroll
+        for (int t = 0; t < C::TPC; ++t)
+          if (t == rb) fa = fv[t * C::RB + a][u];
+#pragma unroll
+        for (int i = 0; i < KP; ++i) acc[a][i] = fmaf(fa, fv[i][u], acc[a][i]);
+      }
     }
   }
   // reduction over the column lanes: xor-shuffles among the lanes that share a row block (lane % TPC),

@@ -349,13 +349,8 @@ class cNMF:
         rf_usages = pd.DataFrame(rf.astype(np.float64), index=norm_counts.obs_names, columns=median_spectra.index)
 
         if skip_density_and_return_after_stats:                                     # cnmf.py:922-936
-            from sklearn.metrics import silhouette_score
-            l2_host = S.numpy()
-            silhouette = silhouette_score(l2_host, cluster_labels.values, metric="euclidean")
-            if kw.get("solver") == "mu":
-                prediction_error = err ** 2
-            else:
-                prediction_error = err ** 2
+            silhouette = cs.silhouette(S, labels0, labels_t, k)
+            prediction_error = err ** 2
             return pd.DataFrame([k, density_threshold, silhouette, prediction_error],
                                 index=["k", "local_density_threshold", "silhouette", "prediction_error"],
                                 columns=["stats"])

@@ -151,6 +151,10 @@ int cnmf_sq_dists_to_rows(cnmf_handle_t h, const float* S_dev, int R, int G, int
 int cnmf_kmeans_assign(cnmf_handle_t h, const float* S_dev, int R, int G, int ld, const float* centers_host, int K,
                        int32_t* labels_dev, double* sums_host, int32_t* counts_host, float* mind_dev,
                        int32_t* n_changed_host, double* inertia_host, void* stream);
+/* sums_host[i*K + c] = sum over rows j with label c of ||S_i - S_j||_2 : the per-sample cluster distance sums
+ * from which sklearn.metrics.silhouette_score(metric='euclidean') is formed (cnmf.py:923, k_selection) */
+int cnmf_cluster_dist_sums(cnmf_handle_t h, const float* S_dev, int R, int G, int ld, const int32_t* labels_dev,
+                           int K, double* sums_host, void* stream);
 /* per-cluster per-gene median (pandas groupby().median(), cnmf.py:913), rows then divided by their sum
  * (cnmf.py:916) -> M_dev (K x ldm). Asynchronous on `stream`. */
 int cnmf_cluster_median(cnmf_handle_t h, const float* S_dev, int R, int G, int ld, const int32_t* labels_dev, int K,

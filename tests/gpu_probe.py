@@ -84,6 +84,35 @@ def stage_gemmperf():
             os.environ.get("CNMF_CHAIN_KB", "1"), name, ms, 2.0 * M * N * K / ms / 1e9, rel(C, ref)), flush=True)
 
 
+def stage_c3():
+    """BASELINE configs[2] on ONE GPU: 50k x 2k, K = 5..13 x 100 restarts (mixed K in one batch)."""
+    from cnmf_b200.synth import make_counts, normalise, restart_table
+    from oracle import nmf_ref
+    eng = Engine()
+    t0 = time.time()
+    X, _ = normalise(make_counts(50000, 2000, k_true=12))
+    rows = restart_table(list(range(5, 14)), 100)
+    print("c3 data %s in %.1fs, %d restarts, sum K = %d" % (X.shape, time.time() - t0, len(rows), sum(r[0] for r in rows)), flush=True)
+    kw = dict(solver="mu", tol=1e-4, max_iter=1000)
+    ds = eng.dataset(X, precision="tf32x3")
+    for rep in range(2):
+        eng.profile(True)
+        l0 = eng.launch_count
+        t1 = time.time()
+        sp, _, n_iter, err = ds.factorize([r[0] for r in rows], [r[2] for r in rows], kw)
+        dt = time.time() - t1
+        ms, nl, fl = eng.profile_get()
+        print("c3 rep %d: factorize %.2fs -> %.1f restarts/s; n_iter mean %.1f max %d; gemm %.0f ms (%d launches, %.1f algo TF/s); %d launches" % (
+            rep, dt, len(rows) / dt, n_iter.mean(), n_iter.max(), ms, nl, fl / ms / 1e9 if ms else 0, eng.launch_count - l0), flush=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for r in (0, 450, 899):
+            t3 = time.time()
+            W, H, it = nmf_ref.nmf(X.astype(np.float64), rows[r][0], rows[r][2], solver="mu")
+            print("   oracle restart %d (K=%d): n_iter %d (gpu %d) rel-L2 %.3e  cpu %.1fs" % (
+                r, rows[r][0], it, n_iter[r], rel(sp[r], H), time.time() - t3), flush=True)
+
+
 def stage_perf():
     eng = Engine()
     rng = np.random.RandomState(0)
@@ -192,3 +221,5 @@ if __name__ == "__main__":
         stage_consensus()
     elif st == "gemmperf":
         stage_gemmperf()
+    elif st == "c3":
+        stage_c3()
