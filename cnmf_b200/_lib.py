@@ -42,6 +42,7 @@ SIGNATURES = {
     "cnmf_launch_count": (_ll, [_vp]),
     "cnmf_profile_enable": (_i, [_vp, _i]),
     "cnmf_profile_get": (_i, [_vp, _pp(_d), _pp(_ll), _pp(_d)]),
+    "cnmf_last_timing": (_i, [_vp, _pp(_d), _pp(_d), _pp(_d), _pp(_d)]),
     "cnmf_dataset_create": (_i, [_vp, _vp, _i, _i, _ll, _i, _i, _vp, _pp(_vp)]),
     "cnmf_dataset_from_columns": (_i, [_vp, _vp, _vp, _i, _vp, _pp(_vp)]),
     "cnmf_dataset_destroy": (_i, [_vp]),

@@ -1,6 +1,7 @@
 // extern "C" entry points declared in include/cnmf_b200.h (handle, dataset, factorize, refit).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -339,13 +340,17 @@ int run_and_download(cnmf_dataset_s* d, const std::vector<int>& ks, int SK, Fact
   io.Fr = fb.Fr; io.Fr_hi = fb.Fr_hi; io.Fr_lo = fb.Fr_lo;
   io.Fc = fb.Fc; io.Fc_hi = fb.Fc_hi; io.Fc_lo = fb.Fc_lo;
   io.update_cols = true;
+  auto t_solve = std::chrono::steady_clock::now();
   CNMF_TRY(solve_batched(h, v, io, p, s));
+  h->t_solve_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_solve).count();
+  auto t_d2h = std::chrono::steady_clock::now();
   CNMF_CUDA_CHECK(cudaMemcpy2DAsync(spectra_host, (size_t)d->n_cols * 4, fb.Fc, (size_t)d->ld_c * 4,
                                     (size_t)d->n_cols * 4, SK, cudaMemcpyDeviceToHost, s));
   if (usages_host)
     CNMF_CUDA_CHECK(cudaMemcpy2DAsync(usages_host, (size_t)d->n_rows * 4, fb.Fr, (size_t)d->ld_r * 4,
                                       (size_t)d->n_rows * 4, SK, cudaMemcpyDeviceToHost, s));
   CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  h->t_d2h_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_d2h).count();
   for (size_t r = 0; r < ks.size(); ++r) {
     if (n_iter_host) n_iter_host[r] = io.n_iter[r];
     if (err_host) err_host[r] = io.err[r];
@@ -379,6 +384,9 @@ int cnmf_factorize(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, const
   FactorBuffers fb;
   CNMF_TRY(alloc_factors(h, SK, d->ld_r, d->ld_c, p->precision == CNMF_PRECISION_TF32X3, &fb));
 
+  using clk = std::chrono::steady_clock;
+  auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
+  h->t_rng_ms = h->t_h2d_ms = h->t_solve_ms = h->t_d2h_ms = 0;
   // host RNG (bit-exact numpy legacy stream) in groups through a pinned staging buffer
   const double mean = d->sum / ((double)d->n_rows * (double)d->n_cols);
   const size_t group_budget = (size_t)256 << 20;   // bytes of W^T staged per group
@@ -394,22 +402,38 @@ int cnmf_factorize(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, const
     float* stW = static_cast<float*>(h->host_buf("stage.W", (size_t)rows * d->ld_r * 4));
     float* stH = static_cast<float*>(h->host_buf("stage.H", (size_t)rows * d->ld_c * 4));
     if (!stW || !stH) return -2;
-    std::memset(stW, 0, (size_t)rows * d->ld_r * 4);
-    std::memset(stH, 0, (size_t)rows * d->ld_c * 4);
+    auto t_rng = clk::now();
     parallel_for(r1 - r0, [&](int i) {
       const int r = r0 + i;
       const double avg = std::sqrt(mean / ks[r]);
-      nmf_random_init(seeds[r], avg, d->n_rows, d->n_cols, ks[r], stW + (size_t)(off[r] - off[r0]) * d->ld_r, d->ld_r,
-                      stH + (size_t)(off[r] - off[r0]) * d->ld_c, d->ld_c);
+      float* w = stW + (size_t)(off[r] - off[r0]) * d->ld_r;
+      float* hh = stH + (size_t)(off[r] - off[r0]) * d->ld_c;
+      nmf_random_init(seeds[r], avg, d->n_rows, d->n_cols, ks[r], w, d->ld_r, hh, d->ld_c);
+      for (int c = 0; c < ks[r]; ++c) {                  // zero the row padding (each worker its own rows)
+        std::memset(w + (size_t)c * d->ld_r + d->n_rows, 0, (size_t)(d->ld_r - d->n_rows) * 4);
+        std::memset(hh + (size_t)c * d->ld_c + d->n_cols, 0, (size_t)(d->ld_c - d->n_cols) * 4);
+      }
     });
+    h->t_rng_ms += ms_since(t_rng);
+    auto t_h2d = clk::now();
     CNMF_CUDA_CHECK(cudaMemcpyAsync(fb.Fr + (size_t)off[r0] * d->ld_r, stW, (size_t)rows * d->ld_r * 4,
                                     cudaMemcpyHostToDevice, s));
     CNMF_CUDA_CHECK(cudaMemcpyAsync(fb.Fc + (size_t)off[r0] * d->ld_c, stH, (size_t)rows * d->ld_c * 4,
                                     cudaMemcpyHostToDevice, s));
     CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+    h->t_h2d_ms += ms_since(t_h2d);
     r0 = r1;
   }
   return run_and_download(d, ks, SK, fb, *p, spectra_host, usages_host, n_iter_host, err_host, s);
+}
+
+int cnmf_last_timing(cnmf_handle_t h, double* rng_ms, double* h2d_ms, double* solve_ms, double* d2h_ms) {
+  CNMF_REQUIRE(h, "last_timing: NULL handle");
+  if (rng_ms) *rng_ms = h->t_rng_ms;
+  if (h2d_ms) *h2d_ms = h->t_h2d_ms;
+  if (solve_ms) *solve_ms = h->t_solve_ms;
+  if (d2h_ms) *d2h_ms = h->t_d2h_ms;
+  return 0;
 }
 
 int cnmf_factorize_init(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, const float* Wt0_host,

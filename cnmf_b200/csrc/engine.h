@@ -21,6 +21,7 @@ struct cnmf_handle_s {
   size_t ev_used = 0;
   double prof_gemm_ms = 0.0, prof_gemm_flops = 0.0;
   long long prof_gemm_launches = 0;
+  double t_rng_ms = 0, t_h2d_ms = 0, t_solve_ms = 0, t_d2h_ms = 0;   // host wall-clock phases of the last cnmf_factorize
   int prof_begin(cudaStream_t s, double flops);    // records the start event; returns slot or -1
   void prof_end(cudaStream_t s, int slot);
   void prof_collect();                              // after a stream sync: fold pending pairs into the totals

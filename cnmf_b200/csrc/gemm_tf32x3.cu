@@ -356,16 +356,22 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   CNMF_CUDA_CHECK(cudaGetDevice(&dev));
   CNMF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int m_tiles = (g.M + BM - 1) / BM;
-  // Tile width: the UMMA N is a runtime value (multiple of 16, <= BN).  Pick the width that minimises
-  // (waves of the persistent grid) x (tile width), i.e. the wave-quantisation loss; ties go to the widest.
+  // Tile width: the UMMA N is a runtime value (multiple of 16, <= BN).  With more than one tile column,
+  // pick among {256..192} the width that minimises (waves of the persistent grid) x (tile cost), where the
+  // tile cost bn + 64 charges the per-tile A-operand traffic and pipeline fill that do not shrink with bn
+  // (a pure waves x bn model picked 16-column tiles: 7x slower).  A single tile column uses just N rounded up.
   int bn = BN;
   {
     const int sp = gemm_effective_splits(g.Kd, g.splits);
-    long long best = -1;
-    for (int cand = BN; cand >= 16; cand -= 16) {
-      const long long tiles = (long long)m_tiles * ((g.N + cand - 1) / cand) * sp;
-      const long long cost = ((tiles + sms - 1) / sms) * cand;
-      if (best < 0 || cost < best) { best = cost; bn = cand; }
+    if (g.N <= BN) {
+      bn = ((g.N + 15) / 16) * 16;
+    } else {
+      long long best = -1;
+      for (int cand = BN; cand >= 192; cand -= 16) {
+        const long long tiles = (long long)m_tiles * ((g.N + cand - 1) / cand) * sp;
+        const long long cost = ((tiles + sms - 1) / sms) * (cand + 64);
+        if (best < 0 || cost < best) { best = cost; bn = cand; }
+      }
     }
     static const int env_bn = [] { const char* e = std::getenv("CNMF_GEMM_BN"); return e ? std::atoi(e) : 0; }();
     if (env_bn >= 16 && env_bn <= BN && env_bn % 16 == 0) bn = env_bn;

@@ -82,6 +82,12 @@ class Engine:
         check(self.lib.cnmf_profile_get(self._h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
         return ms.value, int(n.value), fl.value
 
+    def last_timing(self):
+        """Host wall-clock phases (ms) of the last factorize: dict(rng, h2d, solve, d2h)."""
+        v = [ctypes.c_double() for _ in range(4)]
+        check(self.lib.cnmf_last_timing(self._h, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("rng_ms", "h2d_ms", "solve_ms", "d2h_ms"), [x.value for x in v]))
+
     def dataset(self, X, precision=_DEFAULT_PRECISION, stream=None):
         return Dataset(self, X, precision, stream)
 

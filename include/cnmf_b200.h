@@ -62,6 +62,10 @@ long long cnmf_launch_count(cnmf_handle_t h);
 int cnmf_profile_enable(cnmf_handle_t h, int on);
 int cnmf_profile_get(cnmf_handle_t h, double* gemm_ms, long long* gemm_launches, double* gemm_flops);
 
+/* host wall-clock phases (ms) of the last cnmf_factorize on this handle: host RNG, H2D of the initial
+ * factors, batched solve, D2H of the results */
+int cnmf_last_timing(cnmf_handle_t h, double* rng_ms, double* h2d_ms, double* solve_ms, double* d2h_ms);
+
 /* ---- dataset: a cells x genes matrix made resident on the device ------------------- */
 /* Replaces `norm_counts.X` / `tpm.X` handed to _nmf (cnmf.py:726,741,873,919,950-952).
  * Builds the device-side forms both GEMM orientations need (X, X^T, tf32 pieces) and
