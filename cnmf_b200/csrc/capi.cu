@@ -95,7 +95,29 @@ void cnmf_handle_s::prof_collect() {
   ev_used = 0;
 }
 
+void* cnmf_handle_s::pool_take(size_t bytes) {
+  auto it = pool.find(bytes);
+  if (it == pool.end()) return nullptr;
+  void* p = it->second;
+  pool.erase(it);
+  pool_bytes -= bytes;
+  return p;
+}
+
+void cnmf_handle_s::pool_give(void* p, size_t bytes) {
+  constexpr size_t POOL_CAP = (size_t)16 << 30;     // keep at most 16 GB parked
+  if (pool_bytes + bytes > POOL_CAP) {
+    cudaFree(p);
+    return;
+  }
+  pool.emplace(bytes, p);
+  pool_bytes += bytes;
+}
+
 void cnmf_handle_s::release_all() {
+  for (auto& kv : pool) cudaFree(kv.second);
+  pool.clear();
+  pool_bytes = 0;
   for (auto e : ev_pool) cudaEventDestroy(e);
   ev_pool.clear();
   for (auto& kv : ws)
@@ -166,16 +188,21 @@ int cnmf_profile_get(cnmf_handle_t h, double* gemm_ms, long long* gemm_launches,
 
 // ----------------------------------------------------------------------------- dataset
 static int dataset_alloc(cnmf_dataset_s* d, float** p, size_t elems) {
-  void* q = nullptr;
-  cudaError_t e = cudaMalloc(&q, std::max<size_t>(elems, 64) * sizeof(float));
-  if (e != cudaSuccess) {
-    set_last_error(std::string("dataset cudaMalloc failed: ") + cudaGetErrorString(e));
-    return -2;
+  const size_t bytes = std::max<size_t>(elems, 64) * sizeof(float);
+  void* q = d->h->pool_take(bytes);
+  if (!q) {
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) {
+      set_last_error(std::string("dataset cudaMalloc failed: ") + cudaGetErrorString(e));
+      return -2;
+    }
   }
-  d->owned.push_back(q);
+  d->owned.emplace_back(q, bytes);
   *p = static_cast<float*>(q);
   return 0;
 }
+
+int cnmf_dataset_alloc_internal(cnmf_dataset_t d, float** p, size_t elems) { return dataset_alloc(d, p, elems); }
 
 // builds Xt / tf32 pieces / sums from d->X (already resident, padding zeroed)
 static int dataset_finish(cnmf_dataset_s* d, cudaStream_t s) {
@@ -249,7 +276,7 @@ int cnmf_dataset_finish_internal(cnmf_dataset_t d, void* stream) { return datase
 
 int cnmf_dataset_destroy(cnmf_dataset_t d) {
   if (!d) return 0;
-  for (void* p : d->owned) cudaFree(p);
+  for (auto& pr : d->owned) d->h->pool_give(pr.first, pr.second);
   delete d;
   return 0;
 }

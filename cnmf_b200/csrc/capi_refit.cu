@@ -49,18 +49,6 @@ __global__ void gather_cols_kernel(const float* __restrict__ src, int rows, int 
   dst[(long long)r * ld_dst + c] = src[(long long)r * ld_src + cols[c]] * scale[c];
 }
 
-int dataset_alloc2(cnmf_dataset_s* d, float** p, size_t elems) {
-  void* q = nullptr;
-  cudaError_t e = cudaMalloc(&q, std::max<size_t>(elems, 64) * sizeof(float));
-  if (e != cudaSuccess) {
-    set_last_error(std::string("dataset cudaMalloc failed: ") + cudaGetErrorString(e));
-    return -2;
-  }
-  d->owned.push_back(q);
-  *p = static_cast<float*>(q);
-  return 0;
-}
-
 }  // namespace
 
 extern "C" {
@@ -91,6 +79,7 @@ int cnmf_dataset_col_stats(cnmf_dataset_t d, double* mean_host, double* var_host
 
 // defined in capi.cu (internal; not in the public header)
 int cnmf_dataset_finish_internal(cnmf_dataset_t d, void* stream);
+int cnmf_dataset_alloc_internal(cnmf_dataset_t d, float** p, size_t elems);
 
 int cnmf_dataset_from_columns(cnmf_dataset_t src, const int32_t* cols_host, const float* col_scale_host, int n_cols,
                               void* stream, cnmf_dataset_t* out) {
@@ -112,7 +101,7 @@ int cnmf_dataset_from_columns(cnmf_dataset_t src, const int32_t* cols_host, cons
   d->ld_c = pad_ld(n_cols);
   d->ld_r = pad_ld(src->n_rows);
   d->precision = src->precision;
-  int rc = dataset_alloc2(d, &d->X, (size_t)d->n_rows * d->ld_c);
+  int rc = cnmf_dataset_alloc_internal(d, &d->X, (size_t)d->n_rows * d->ld_c);
   if (rc == 0) {
     cudaError_t e = cudaMemsetAsync(d->X, 0, (size_t)d->n_rows * d->ld_c * sizeof(float), s);
     if (e != cudaSuccess) rc = -2;

@@ -28,6 +28,12 @@ struct cnmf_handle_s {
   std::map<std::string, std::pair<void*, size_t>> ws;   // named grow-only device buffers
   std::map<std::string, std::pair<void*, size_t>> pinned;  // named grow-only pinned host buffers
 
+  // size-keyed pool of dataset buffers: cudaMalloc / cudaFree of several 160 MB arrays per dataset
+  // cost tens of ms (cudaFree synchronises); datasets of a repeated shape reuse their buffers
+  std::multimap<size_t, void*> pool;
+  size_t pool_bytes = 0;
+  void* pool_take(size_t bytes);
+  void pool_give(void* p, size_t bytes);
   void* dev_buf(const std::string& name, size_t bytes);      // nullptr on failure (error set)
   void* host_buf(const std::string& name, size_t bytes);
   void release_all();
@@ -46,7 +52,7 @@ struct cnmf_dataset_s {
   float *X = nullptr, *Xt = nullptr;
   float *X_hi = nullptr, *X_lo = nullptr, *Xt_hi = nullptr, *Xt_lo = nullptr;
   double sum = 0.0, sum_sq = 0.0;
-  std::vector<void*> owned;
+  std::vector<std::pair<void*, size_t>> owned;
 };
 
 namespace cnmf {
