@@ -103,16 +103,20 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     kmax = std::max(kmax, io.ks[r]);
   }
   int R = R0, SK = SK0;     // live slots / live packed rows
-  const int kp = kmax <= 8 ? 8 : (kmax <= 16 ? 16 : 32);
-  const int chunks_r = col_chunks(v.n_r), chunks_c = col_chunks(v.n_c);
+  const int kp = kmax <= 16 ? 16 : 32;
+  // block granularity of the streaming kernels, fixed for the whole solve (partial buffers are sized by it)
+  const int cpb_r = pick_cols_per_block(v.n_r, R0, 2048, 256), cpb_c = pick_cols_per_block(v.n_c, R0, 2048, 256);
+  const int gcpb_r = pick_cols_per_block(v.n_r, R0, 8192, 1024), gcpb_c = pick_cols_per_block(v.n_c, R0, 8192, 1024);
+  const int chunks_r = (v.n_r + cpb_r - 1) / cpb_r, chunks_c = (v.n_c + cpb_c - 1) / cpb_c;
   const int chunks_max = std::max(chunks_r, chunks_c);
+  const int gchunks_max = std::max((v.n_r + gcpb_r - 1) / gcpb_r, (v.n_c + gcpb_c - 1) / gcpb_c);
 
   // ---- workspace
   int* d_meta = static_cast<int*>(h->dev_buf("solve.meta", sizeof(int) * 8 * R0));
   double* d_state = static_cast<double*>(h->dev_buf("solve.state", sizeof(double) * 8 * R0));
   double* d_gram = static_cast<double*>(h->dev_buf("solve.gram", sizeof(double) * 2 * R0 * KMAX * KMAX));
   double* d_gram_part =
-      static_cast<double*>(h->dev_buf("solve.gram_part", sizeof(double) * (size_t)R0 * chunks_max * kp * kp));
+      static_cast<double*>(h->dev_buf("solve.gram_part", sizeof(double) * (size_t)R0 * gchunks_max * kp * kp));
   double* d_scal_part = static_cast<double*>(h->dev_buf("solve.scal_part", sizeof(double) * 2 * (size_t)R0 * chunks_max));
   if (!d_meta || !d_state || !d_gram || !d_gram_part || !d_scal_part) return -2;
 
@@ -173,16 +177,16 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   bool compacted = false;
 
   auto bm = [&]() { return BatchMeta{d_off, d_k, d_rid, d_done, R, kp}; };
-  auto fr = [&]() { return FactorView{wFr, tf32 ? wFr_hi : nullptr, tf32 ? wFr_lo : nullptr, v.n_r, v.ld_r}; };
+  auto fr = [&]() { return FactorView{wFr, tf32 ? wFr_hi : nullptr, tf32 ? wFr_lo : nullptr, v.n_r, v.ld_r, cpb_r, gcpb_r}; };
   auto fc = [&]() {
-    FactorView f{wFc, tf32 ? wFc_hi : nullptr, tf32 ? wFc_lo : nullptr, v.n_c, v.ld_c};
+    FactorView f{wFc, tf32 ? wFc_hi : nullptr, tf32 ? wFc_lo : nullptr, v.n_c, v.ld_c, cpb_c, gcpb_c};
     if (!io.update_cols) { f.F_hi = nullptr; f.F_lo = nullptr; }   // never rewritten
     return f;
   };
   auto gram_of = [&](const FactorView& f, double* gram_out, int /*scalar chunks, unused*/) -> int {
     h->launches += 2;
     CNMF_TRY(launch_gram_partial(f, bm(), d_gram_part, s));
-    return launch_finalize(d_gram_part, gram_out, nullptr, nullptr, gram_chunks(f.n), bm(), s);
+    return launch_finalize(d_gram_part, gram_out, nullptr, nullptr, gram_chunks(f), bm(), s);
   };
   auto finalize_scal = [&](const double* part, double* out, int chunks) -> int {
     h->launches += 1;
@@ -231,9 +235,9 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     BatchMeta bm0{d_off, d_k, d_rid, d_zero, R, kp};
     h->launches += 7;
     CNMF_TRY(launch_gram_partial(fr(), bm0, d_gram_part, s));
-    CNMF_TRY(launch_finalize(d_gram_part, d_gramR, nullptr, nullptr, gram_chunks(v.n_r), bm0, s));
+    CNMF_TRY(launch_finalize(d_gram_part, d_gramR, nullptr, nullptr, gram_chunks(fr()), bm0, s));
     CNMF_TRY(launch_gram_partial(fc(), bm0, d_gram_part, s));
-    CNMF_TRY(launch_finalize(d_gram_part, d_gramC, nullptr, nullptr, gram_chunks(v.n_c), bm0, s));
+    CNMF_TRY(launch_finalize(d_gram_part, d_gramC, nullptr, nullptr, gram_chunks(fc()), bm0, s));
     if (io.update_cols) {
       CNMF_TRY(launch_cross(fc(), NUMc, plan_c.splits, plan_c.split_stride, bm0, d_scalB, s));
       CNMF_TRY(launch_finalize(nullptr, nullptr, d_scalB, d_crossB, chunks_c, bm0, s));

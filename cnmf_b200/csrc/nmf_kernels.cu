@@ -95,43 +95,57 @@ __global__ void sums_final_kernel(const double* __restrict__ part, int nblocks, 
   }
 }
 
-// ------------------------------------------------------------------ multiplicative update
-// Thread = one item (cell / gene) column.  Register budget is kept small (3 blocks of 256 threads per SM):
-// the K x K Gram is re-read from shared memory for every column through a volatile pointer (broadcast
-// LDS.128) instead of being cached in 256 registers -- a 255-register version of this kernel ran at ~1 TB/s.
-template <int KP>
-__global__ void __launch_bounds__(UPD_THREADS, KP == 32 ? 2 : 3)
-mu_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
-                 const double* __restrict__ gram, BatchMeta b, float l1, float l2, double* __restrict__ cross_partial) {
-  const int slot = blockIdx.y;
-  const int r = b.rid[slot];
-  if (b.done[r]) return;
-  const int K = b.k[slot], o = b.off[slot];
-  __shared__ __align__(16) float G[KP * KP];
-  __shared__ double red[32];
-  for (int idx = threadIdx.x; idx < KP * KP; idx += UPD_THREADS) {
+// ------------------------------------------------------------------ update kernels
+// Thread = one item (cell / gene) column of one restart.  The unrolled K x K work is instantiated at a
+// granularity of 4 components (KP = K rounded up to a multiple of 4) and dispatched per restart INSIDE the
+// kernel (block-uniform switch), so a K = 10 restart runs the 12 x 12 body even when the batch also holds
+// K = 13 restarts.  KPMAX (16 or 32, from the batch maximum) only bounds which bodies exist, i.e. the
+// kernel's register budget: 80 registers / 3 blocks per SM for KPMAX = 16.  The K x K Gram is re-read
+// from shared memory for every column through a volatile pointer (broadcast LDS.128) instead of being
+// hoisted into ~256 registers (that version ran at ~1 TB/s).
+__device__ __forceinline__ void load_gram_smem(float* G, const double* __restrict__ gram, int r, int K, int KP,
+                                               float diag_add) {
+  for (int idx = threadIdx.x; idx < KP * KP; idx += blockDim.x) {
     const int c = idx / KP, i = idx % KP;
-    G[idx] = (c < K && i < K) ? (float)gram[(long long)r * KMAX * KMAX + c * KMAX + i] : 0.f;
+    float g = (c < K && i < K) ? (float)gram[(long long)r * KMAX * KMAX + c * KMAX + i] : 0.f;
+    if (c == i && c < K) g += diag_add;
+    G[idx] = g;
   }
   __syncthreads();
-  const volatile float4* Gv = reinterpret_cast<const volatile float4*>(G);
-  const int col_begin = blockIdx.x * UPD_COLS_PER_BLOCK;
-  const int col_end = min(f.n, col_begin + UPD_COLS_PER_BLOCK);
-  double cross = 0.0;
-  float* __restrict__ Fp = f.F;
-  float* __restrict__ Fhi = f.F_hi;
-  float* __restrict__ Flo = f.F_lo;
-  for (int col = col_begin + threadIdx.x; col < col_end; col += UPD_THREADS) {
-    // all loads of this column first (2K independent requests in flight per thread), then math, then stores
-    float fv[KP], nv[KP];
+}
+
+template <int KP>
+__device__ __forceinline__ void load_column(const FactorView& f, const float* __restrict__ NUM, int nsplit,
+                                            long long sstride, int K, int o, int col, float (&fv)[KP], float (&nv)[KP]) {
+  // all loads of this column first (2K independent requests in flight per thread)
 #pragma unroll
-    for (int i = 0; i < KP; ++i) {
-      const long long e = (long long)(o + i) * f.ld + col;
-      fv[i] = (i < K) ? Fp[e] : 0.f;
-      float num = (i < K) ? NUM[e] : 0.f;
-      for (int s = 1; s < nsplit; ++s) num += (i < K) ? NUM[s * sstride + e] : 0.f;
-      nv[i] = num;
-    }
+  for (int i = 0; i < KP; ++i) {
+    const long long e = (long long)(o + i) * f.ld + col;
+    fv[i] = (i < K) ? f.F[e] : 0.f;
+    float num = (i < K) ? NUM[e] : 0.f;
+    for (int s = 1; s < nsplit; ++s) num += (i < K) ? NUM[s * sstride + e] : 0.f;
+    nv[i] = num;
+  }
+}
+
+__device__ __forceinline__ void store_elem(const FactorView& f, long long e, float v) {
+  f.F[e] = v;
+  if (f.F_hi) {
+    float h, l;
+    split_tf32(v, h, l);
+    f.F_hi[e] = h;
+    f.F_lo[e] = l;
+  }
+}
+
+template <int KP>
+__device__ __forceinline__ double mu_body(const FactorView& f, const float* __restrict__ NUM, int nsplit, long long sstride,
+                                          const float* G, int K, int o, float l1, float l2, int col_begin, int col_end) {
+  const volatile float4* Gv = reinterpret_cast<const volatile float4*>(G);
+  double cross = 0.0;
+  for (int col = col_begin + threadIdx.x; col < col_end; col += UPD_THREADS) {
+    float fv[KP], nv[KP];
+    load_column<KP>(f, NUM, nsplit, sstride, K, o, col, fv, nv);
 #pragma unroll
     for (int c = 0; c < KP; ++c) {
       if (c < K) {
@@ -148,60 +162,23 @@ mu_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long l
         if (l2 > 0.f) den += l2 * fv[c];
         if (den == 0.f) den = EPSILON_F32;
         const float fn = fv[c] * (nv[c] / den);
-        const long long e = (long long)(o + c) * f.ld + col;
-        Fp[e] = fn;
-        if (Fhi) {
-          float h, l;
-          split_tf32(fn, h, l);
-          Fhi[e] = h;
-          Flo[e] = l;
-        }
+        store_elem(f, (long long)(o + c) * f.ld + col, fn);
         cross += (double)nv[c] * (double)fn;
       }
     }
   }
-  if (cross_partial) {
-    cross = block_sum(cross, red);
-    if (threadIdx.x == 0) cross_partial[(long long)r * gridDim.x + blockIdx.x] = cross;
-  }
+  return cross;
 }
 
-// ------------------------------------------------------------------ coordinate descent sweep
 template <int KP>
-__global__ void __launch_bounds__(UPD_THREADS, KP == 32 ? 2 : 3)
-cd_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
-                 const double* __restrict__ gram, BatchMeta b, float l1, float l2, double* __restrict__ viol_partial) {
-  const int slot = blockIdx.y;
-  const int r = b.rid[slot];
-  if (b.done[r]) return;
-  const int K = b.k[slot], o = b.off[slot];
-  __shared__ __align__(16) float G[KP * KP];
-  __shared__ double red[32];
-  for (int idx = threadIdx.x; idx < KP * KP; idx += UPD_THREADS) {
-    const int c = idx / KP, i = idx % KP;
-    float g = (c < K && i < K) ? (float)gram[(long long)r * KMAX * KMAX + c * KMAX + i] : 0.f;
-    if (c == i && c < K) g += l2;                       // sklearn _nmf.py:383-385
-    G[idx] = g;
-  }
-  __syncthreads();
+__device__ __forceinline__ double cd_body(const FactorView& f, const float* __restrict__ NUM, int nsplit, long long sstride,
+                                          const float* G, int K, int o, float l1, int col_begin, int col_end) {
   const volatile float4* Gv = reinterpret_cast<const volatile float4*>(G);
   const volatile float* Gs = G;
-  const int col_begin = blockIdx.x * UPD_COLS_PER_BLOCK;
-  const int col_end = min(f.n, col_begin + UPD_COLS_PER_BLOCK);
   double viol = 0.0;
-  float* __restrict__ Fp = f.F;
-  float* __restrict__ Fhi = f.F_hi;
-  float* __restrict__ Flo = f.F_lo;
   for (int col = col_begin + threadIdx.x; col < col_end; col += UPD_THREADS) {
     float fv[KP], nv[KP];
-#pragma unroll
-    for (int i = 0; i < KP; ++i) {
-      const long long e = (long long)(o + i) * f.ld + col;
-      fv[i] = (i < K) ? Fp[e] : 0.f;
-      float num = (i < K) ? NUM[e] : 0.f;
-      for (int s = 1; s < nsplit; ++s) num += (i < K) ? NUM[s * sstride + e] : 0.f;
-      nv[i] = num;
-    }
+    load_column<KP>(f, NUM, nsplit, sstride, K, o, col, fv, nv);
 #pragma unroll
     for (int t = 0; t < KP; ++t) {
       if (t < K) {
@@ -218,17 +195,61 @@ cd_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long l
         viol += (double)fabsf(pg);
         const float h = Gs[t * KP + t];
         if (h != 0.f) fv[t] = fmaxf(fv[t] - g / h, 0.f);
-        const long long e = (long long)(o + t) * f.ld + col;
-        Fp[e] = fv[t];
-        if (Fhi) {
-          float hh, ll;
-          split_tf32(fv[t], hh, ll);
-          Fhi[e] = hh;
-          Flo[e] = ll;
-        }
+        store_elem(f, (long long)(o + t) * f.ld + col, fv[t]);
       }
     }
   }
+  return viol;
+}
+
+#define CNMF_KP_SWITCH(K, KPMAX, CALL)                                            \
+  switch (((K) + 3) / 4) {                                                        \
+    case 1: { constexpr int KP = 4; CALL; } break;                                \
+    case 2: { constexpr int KP = 8; CALL; } break;                                \
+    case 3: { constexpr int KP = 12; CALL; } break;                               \
+    case 4: { constexpr int KP = 16; CALL; } break;                               \
+    case 5: if constexpr (KPMAX >= 20) { constexpr int KP = 20; CALL; } break;    \
+    case 6: if constexpr (KPMAX >= 24) { constexpr int KP = 24; CALL; } break;    \
+    case 7: if constexpr (KPMAX >= 28) { constexpr int KP = 28; CALL; } break;    \
+    default: if constexpr (KPMAX >= 32) { constexpr int KP = 32; CALL; } break;   \
+  }
+
+template <int KPMAX>
+__global__ void __launch_bounds__(UPD_THREADS, KPMAX == 32 ? 2 : 3)
+mu_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
+                 const double* __restrict__ gram, BatchMeta b, float l1, float l2, double* __restrict__ cross_partial) {
+  const int slot = blockIdx.y;
+  const int r = b.rid[slot];
+  if (b.done[r]) return;
+  const int K = b.k[slot], o = b.off[slot];
+  __shared__ __align__(16) float G[KPMAX * KPMAX];
+  __shared__ double red[32];
+  const int col_begin = blockIdx.x * f.cpb;
+  const int col_end = min(f.n, col_begin + f.cpb);
+  double cross = 0.0;
+  CNMF_KP_SWITCH(K, KPMAX, (load_gram_smem(G, gram, r, K, KP, 0.f),
+                            cross = mu_body<KP>(f, NUM, nsplit, sstride, G, K, o, l1, l2, col_begin, col_end)));
+  if (cross_partial) {
+    cross = block_sum(cross, red);
+    if (threadIdx.x == 0) cross_partial[(long long)r * gridDim.x + blockIdx.x] = cross;
+  }
+}
+
+template <int KPMAX>
+__global__ void __launch_bounds__(UPD_THREADS, KPMAX == 32 ? 2 : 3)
+cd_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
+                 const double* __restrict__ gram, BatchMeta b, float l1, float l2, double* __restrict__ viol_partial) {
+  const int slot = blockIdx.y;
+  const int r = b.rid[slot];
+  if (b.done[r]) return;
+  const int K = b.k[slot], o = b.off[slot];
+  __shared__ __align__(16) float G[KPMAX * KPMAX];
+  __shared__ double red[32];
+  const int col_begin = blockIdx.x * f.cpb;
+  const int col_end = min(f.n, col_begin + f.cpb);
+  double viol = 0.0;
+  CNMF_KP_SWITCH(K, KPMAX, (load_gram_smem(G, gram, r, K, KP, l2),   // l2 on the diagonal: sklearn _nmf.py:383-385
+                            viol = cd_body<KP>(f, NUM, nsplit, sstride, G, K, o, l1, col_begin, col_end)));
   if (viol_partial) {
     viol = block_sum(viol, red);
     if (threadIdx.x == 0) viol_partial[(long long)r * gridDim.x + blockIdx.x] = viol;
@@ -244,8 +265,8 @@ cross_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long 
   if (b.done[r]) return;
   const int K = b.k[slot], o = b.off[slot];
   __shared__ double red[32];
-  const int col_begin = blockIdx.x * UPD_COLS_PER_BLOCK;
-  const int col_end = min(f.n, col_begin + UPD_COLS_PER_BLOCK);
+  const int col_begin = blockIdx.x * f.cpb;
+  const int col_end = min(f.n, col_begin + f.cpb);
   double cross = 0.0;
   for (int col = col_begin + threadIdx.x; col < col_end; col += UPD_THREADS) {
     for (int c = 0; c < K; ++c) {
@@ -261,17 +282,16 @@ cross_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long 
 
 // ------------------------------------------------------------------ K x K Gram partials
 // Register-tiled: a thread owns RB rows x KP columns of the K x K Gram and walks over columns of F,
-// VEC columns at a time through 8/16-byte loads (KP*VEC values in flight per thread: the first version
-// of this kernel, one 4-byte column per step, was latency-bound at ~0.6 TB/s with one block per SM).
-// KP/RB threads cooperate on one column group; partial sums are fp32 over the thread's columns, then
-// fp64 through shuffles + a fixed-order shared-memory reduction (deterministic).
+// VEC columns at a time through 8/16-byte loads (KP*VEC values in flight per thread; a first version with
+// one 4-byte column per step was latency-bound at ~0.6 TB/s).  TPC threads cooperate on one column group;
+// partial sums are fp32 over the thread's columns, then fp64 through shuffles + a fixed-order
+// shared-memory reduction (deterministic).  Same per-restart KP dispatch as the update kernels.
 template <int KP>
 struct GramCfg {
-  static constexpr int RB = KP == 32 ? 4 : 8;          // rows of the Gram per thread
-  static constexpr int TPC = KP / RB;                  // threads per column group (1, 2, 8)
-  static constexpr int VEC = KP == 32 ? 2 : 4;         // consecutive columns per load
-  static constexpr int THREADS = 256;
-  static constexpr int COLS_PER_ITER = (THREADS / TPC) * VEC;   // columns advanced per block iteration
+  static constexpr int TPC = KP <= 8 ? 1 : (KP <= 16 ? 2 : (KP <= 24 ? 4 : 8));   // threads per column group
+  static constexpr int RB = (KP + TPC - 1) / TPC;       // rows of the Gram per thread (last block may be partial)
+  static constexpr int VEC = KP <= 12 ? 4 : 2;          // consecutive columns per load (register budget)
+  static constexpr int COLS_PER_ITER = (256 / TPC) * VEC;
 };
 
 template <int VEC> struct VecLoad;
@@ -289,24 +309,18 @@ template <> struct VecLoad<2> {
 };
 
 template <int KP>
-__global__ void __launch_bounds__(256)
-gram_partial_kernel(FactorView f, BatchMeta b, double* __restrict__ gram_partial) {
+__device__ __forceinline__ void gram_body(const FactorView& f, int K, int o, int col_begin, int col_end,
+                                          double* part /* smem 8 x 8 x 32 */, double* __restrict__ out) {
   using C = GramCfg<KP>;
-  const int slot = blockIdx.y;
-  const int r = b.rid[slot];
-  if (b.done[r]) return;
-  const int K = b.k[slot], o = b.off[slot];
   const int rb = threadIdx.x % C::TPC;                 // which row block of the Gram
   const int cl = threadIdx.x / C::TPC;                 // column-group lane inside the block
-  const int col_begin = blockIdx.x * GRAM_COLS_PER_BLOCK;
-  const int col_end = min(f.n, col_begin + GRAM_COLS_PER_BLOCK);   // padding columns (< ld) hold zeros
   float acc[C::RB][KP];
 #pragma unroll
   for (int a = 0; a < C::RB; ++a)
 #pragma unroll
     for (int i = 0; i < KP; ++i) acc[a][i] = 0.f;
   const float* __restrict__ Fp = f.F;
-  for (int col = col_begin + cl * C::VEC; col < col_end; col += C::COLS_PER_ITER) {
+  for (int col = col_begin + cl * C::VEC; col < col_end; col += C::COLS_PER_ITER) {   // padding columns hold zeros
     float fv[KP][C::VEC];
 #pragma unroll
     for (int i = 0; i < KP; ++i) {
@@ -324,7 +338,7 @@ gram_partial_kernel(FactorView f, BatchMeta b, double* __restrict__ gram_partial
         float fa = 0.f;                                 // fv[rb * RB + a][u] without dynamic register indexing
 #pragma unroll
         for (int t = 0; t < C::TPC; ++t)
-          if (t == rb) fa = fv[t * C::RB + a][u];
+          if (t == rb && t * C::RB + a < KP) fa = fv[t * C::RB + a < KP ? t * C::RB + a : 0][u];
 #pragma unroll
         for (int i = 0; i < KP; ++i) acc[a][i] = fmaf(fa, fv[i][u], acc[a][i]);
       }
@@ -333,8 +347,6 @@ gram_partial_kernel(FactorView f, BatchMeta b, double* __restrict__ gram_partial
   // reduction over the column lanes: xor-shuffles among the lanes that share a row block (lane % TPC),
   // then the 8 warps' partials are summed in fixed order through shared memory -- all in fp64
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __shared__ double part[8][C::TPC][KP];
-  double* out = gram_partial + ((long long)r * gridDim.x + blockIdx.x) * (KP * KP);
 #pragma unroll
   for (int a = 0; a < C::RB; ++a) {
     double v[KP];
@@ -347,17 +359,34 @@ gram_partial_kernel(FactorView f, BatchMeta b, double* __restrict__ gram_partial
     __syncthreads();
     if (lane < C::TPC) {
 #pragma unroll
-      for (int i = 0; i < KP; ++i) part[warp][lane][i] = v[i];
+      for (int i = 0; i < KP; ++i) part[(warp * 8 + lane) * 32 + i] = v[i];
     }
     __syncthreads();
     if (threadIdx.x < C::TPC * KP) {
       const int rbb = threadIdx.x / KP, i = threadIdx.x % KP;
-      double sum = 0.0;
+      const int row = rbb * C::RB + a;
+      if (row < KP) {
+        double sum = 0.0;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) sum += part[w][rbb][i];
-      out[(rbb * C::RB + a) * KP + i] = sum;
+        for (int w = 0; w < 8; ++w) sum += part[(w * 8 + rbb) * 32 + i];
+        out[row * KP + i] = sum;
+      }
     }
   }
+}
+
+template <int KPMAX>
+__global__ void __launch_bounds__(256)
+gram_partial_kernel(FactorView f, BatchMeta b, double* __restrict__ gram_partial) {
+  const int slot = blockIdx.y;
+  const int r = b.rid[slot];
+  if (b.done[r]) return;
+  const int K = b.k[slot], o = b.off[slot];
+  __shared__ double part[8 * 8 * 32];
+  const int col_begin = blockIdx.x * f.gcpb;
+  const int col_end = min(f.n, col_begin + f.gcpb);
+  double* out = gram_partial + ((long long)r * gridDim.x + blockIdx.x) * (KPMAX * KPMAX);
+  CNMF_KP_SWITCH(K, KPMAX, (gram_body<KP>(f, K, o, col_begin, col_end, part, out)));
 }
 
 __global__ void finalize_kernel(const double* __restrict__ gram_partial, double* __restrict__ gram,
@@ -365,11 +394,13 @@ __global__ void finalize_kernel(const double* __restrict__ gram_partial, double*
                                 BatchMeta b) {
   const int r = b.rid[blockIdx.x];
   if (b.done[r]) return;
-  const int KP = b.kp;
   if (gram_partial) {
+    const int K = b.k[blockIdx.x];
+    const int KP = ((K + 3) / 4) * 4;                   // layout written by gram_body<KP>
+    const int stride = b.kp * b.kp;
     for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
       double a = 0.0;
-      for (int ch = 0; ch < chunks; ++ch) a += gram_partial[((long long)r * chunks + ch) * (KP * KP) + e];
+      for (int ch = 0; ch < chunks; ++ch) a += gram_partial[((long long)r * chunks + ch) * stride + e];
       const int c = e / KP, i = e % KP;
       gram[(long long)r * KMAX * KMAX + c * KMAX + i] = a;
     }
@@ -472,43 +503,42 @@ int launch_matrix_sums(const float* X, int rows, int cols, int ld, double* out2,
   return 0;
 }
 
-#define CNMF_DISPATCH_KP(kp, CALL)                                   \
+#define CNMF_DISPATCH_KPMAX(kp, CALL)                               \
   switch (kp) {                                                      \
-    case 8: { constexpr int KP = 8; CALL; } break;                   \
-    case 16: { constexpr int KP = 16; CALL; } break;                 \
-    case 32: { constexpr int KP = 32; CALL; } break;                 \
-    default: set_last_error("kp must be 8, 16 or 32"); return -1;    \
+    case 16: { constexpr int KPMAX = 16; CALL; } break;              \
+    case 32: { constexpr int KPMAX = 32; CALL; } break;              \
+    default: set_last_error("kp must be 16 or 32"); return -1;       \
   }
 
 int launch_mu_update(const FactorView& f, const float* NUM, int nsplit, long long sstride, const double* gram,
                      const BatchMeta& b, float l1, float l2, double* cross_partial, cudaStream_t s) {
-  dim3 grid(col_chunks(f.n), b.R);
-  CNMF_DISPATCH_KP(b.kp, (mu_update_kernel<KP><<<grid, UPD_THREADS, 0, s>>>(f, NUM, nsplit, sstride, gram, b, l1, l2,
-                                                                             cross_partial)));
+  dim3 grid(col_chunks(f), b.R);
+  CNMF_DISPATCH_KPMAX(b.kp, (mu_update_kernel<KPMAX><<<grid, UPD_THREADS, 0, s>>>(f, NUM, nsplit, sstride, gram, b, l1,
+                                                                                    l2, cross_partial)));
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 int launch_cd_update(const FactorView& f, const float* NUM, int nsplit, long long sstride, const double* gram,
                      const BatchMeta& b, float l1, float l2, double* viol_partial, cudaStream_t s) {
-  dim3 grid(col_chunks(f.n), b.R);
-  CNMF_DISPATCH_KP(b.kp, (cd_update_kernel<KP><<<grid, UPD_THREADS, 0, s>>>(f, NUM, nsplit, sstride, gram, b, l1, l2,
-                                                                             viol_partial)));
+  dim3 grid(col_chunks(f), b.R);
+  CNMF_DISPATCH_KPMAX(b.kp, (cd_update_kernel<KPMAX><<<grid, UPD_THREADS, 0, s>>>(f, NUM, nsplit, sstride, gram, b, l1,
+                                                                                    l2, viol_partial)));
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 int launch_cross(const FactorView& f, const float* NUM, int nsplit, long long sstride, const BatchMeta& b,
                  double* cross_partial, cudaStream_t s) {
-  dim3 grid(col_chunks(f.n), b.R);
+  dim3 grid(col_chunks(f), b.R);
   cross_kernel<<<grid, UPD_THREADS, 0, s>>>(f, NUM, nsplit, sstride, b, cross_partial);
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 int launch_gram_partial(const FactorView& f, const BatchMeta& b, double* gram_partial, cudaStream_t s) {
-  dim3 grid(gram_chunks(f.n), b.R);
-  CNMF_DISPATCH_KP(b.kp, (gram_partial_kernel<KP><<<grid, 256, 0, s>>>(f, b, gram_partial)));
+  dim3 grid(gram_chunks(f), b.R);
+  CNMF_DISPATCH_KPMAX(b.kp, (gram_partial_kernel<KPMAX><<<grid, 256, 0, s>>>(f, b, gram_partial)));
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

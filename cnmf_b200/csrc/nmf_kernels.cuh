@@ -13,8 +13,6 @@
 namespace cnmf {
 
 constexpr int UPD_THREADS = 256;
-constexpr int UPD_COLS_PER_BLOCK = 2048;   // columns handled by one block of the update kernels
-constexpr int GRAM_COLS_PER_BLOCK = 8192;  // columns handled by one block of the Gram kernel
 
 struct FactorView {
   float* F;        // SK x ld, in/out
@@ -22,7 +20,17 @@ struct FactorView {
   float* F_lo;
   int n;           // valid columns
   int ld;
+  int cpb;         // columns handled by one block of the update / cross kernels (multiple of 256)
+  int gcpb;        // columns handled by one block of the Gram kernel (multiple of 1024)
 };
+
+// block granularity: large enough to amortise the per-block prologue, small enough that
+// (column chunks) x (restarts) fills the 148 SMs a few times over even for a single refit
+inline int pick_cols_per_block(int n, int n_restarts, int max_cols, int min_cols) {
+  int c = max_cols;
+  while (c > min_cols && (long long)((n + c - 1) / c) * n_restarts < 148 * 8) c /= 2;
+  return c;
+}
 
 // "slot" = position of a live restart in the packed arrays (changes when converged restarts are
 // compacted away); "rid" = its index in the caller's restart list (never changes).  Packed factor
@@ -33,11 +41,11 @@ struct BatchMeta {
   const int* rid;  // [slots] its restart id
   const int* done; // [n restarts] 1 = converged, frozen (indexed by rid)
   int R;           // live slots
-  int kp;          // 8, 16 or 32: >= max k in the batch (template dispatch)
+  int kp;          // 16 or 32: >= max k in the batch (selects the kernel's register budget)
 };
 
-inline int col_chunks(int n) { return (n + UPD_COLS_PER_BLOCK - 1) / UPD_COLS_PER_BLOCK; }
-inline int gram_chunks(int n) { return (n + GRAM_COLS_PER_BLOCK - 1) / GRAM_COLS_PER_BLOCK; }
+inline int col_chunks(const FactorView& f) { return (f.n + f.cpb - 1) / f.cpb; }
+inline int gram_chunks(const FactorView& f) { return (f.n + f.gcpb - 1) / f.gcpb; }
 
 // x -> (hi, lo) tf32 pieces, elementwise over rows x ld (padding included)
 int launch_split_tf32(const float* src, float* hi, float* lo, long long n_elems, cudaStream_t s);
