@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcnmf_b200.so")
 
 SOLVER_MU, SOLVER_CD = 0, 1
-PRECISION_FP32, PRECISION_TF32X3 = 0, 1
+PRECISION_FP32, PRECISION_TF32X3, PRECISION_TF32X3_GENERAL = 0, 1, 2
 MAX_COMPONENTS = 32
 
 
@@ -48,6 +48,7 @@ SIGNATURES = {
     "cnmf_dataset_destroy": (_i, [_vp]),
     "cnmf_dataset_shape": (_i, [_vp, _pp(_i), _pp(_i)]),
     "cnmf_dataset_ld": (_i, [_vp, _pp(_i), _pp(_i)]),
+    "cnmf_dataset_is_exact": (_i, [_vp]),
     "cnmf_dataset_sums": (_i, [_vp, _pp(_d), _pp(_d)]),
     "cnmf_dataset_col_stats": (_i, [_vp, _vp, _vp, _vp]),
     "cnmf_random_init_host": (_i, [_c.c_uint32, _d, _i, _i, _i, _vp, _ll, _vp, _ll]),

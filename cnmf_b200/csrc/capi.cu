@@ -209,6 +209,38 @@ static int dataset_finish(cnmf_dataset_s* d, cudaStream_t s) {
   cnmf_handle_s* h = d->h;
   const size_t nx = (size_t)d->n_rows * d->ld_c, nxt = (size_t)d->n_cols * d->ld_r;
   if (d->precision == CNMF_PRECISION_TF32X3) {
+    // ---- exact-count detection: is X = diag(r) C diag(s) with C integer <= 2048 ?  (column scale first,
+    //      then row scale; datasets derived by cnmf_dataset_from_columns arrive with `exact` already decided)
+    static const bool allow_exact = [] { const char* e = std::getenv("CNMF_EXACT"); return !(e && e[0] == '0'); }();
+    if (allow_exact && d->allow_exact && !d->exact && d->n_rows <= 65535 * 64) {
+      float* cmin = nullptr;
+      float* rmin = nullptr;
+      CNMF_TRY(dataset_alloc(d, &cmin, (size_t)d->ld_c));
+      CNMF_TRY(dataset_alloc(d, &rmin, (size_t)d->ld_r));
+      int* n_bad = static_cast<int*>(h->dev_buf("dataset.nbad", sizeof(int) * 2));
+      if (!n_bad) return -2;
+      CNMF_TRY(launch_min_positive(d->X, d->n_rows, d->n_cols, d->ld_c, cmin, rmin, s));
+      CNMF_TRY(launch_fix_scale(cmin, d->n_cols, d->ld_c, s));
+      CNMF_TRY(launch_fix_scale(rmin, d->n_rows, d->ld_r, s));
+      CNMF_CUDA_CHECK(cudaMemsetAsync(n_bad, 0, sizeof(int) * 2, s));
+      CNMF_TRY(launch_check_scaled_int(d->X, d->n_rows, d->n_cols, d->ld_c, nullptr, cmin, n_bad, s));
+      CNMF_TRY(launch_check_scaled_int(d->X, d->n_rows, d->n_cols, d->ld_c, rmin, nullptr, n_bad + 1, s));
+      h->launches += 5;
+      int bad[2] = {1, 1};
+      CNMF_CUDA_CHECK(cudaMemcpyAsync(bad, n_bad, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+      CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+      if (bad[0] == 0) { d->exact = true; d->col_scale = cmin; d->row_scale = nullptr; }
+      else if (bad[1] == 0) { d->exact = true; d->row_scale = rmin; d->col_scale = nullptr; }
+    }
+    if (d->exact) {
+      CNMF_TRY(dataset_alloc(d, &d->X_hi, nx));
+      CNMF_TRY(dataset_alloc(d, &d->Xt_hi, nxt));
+      CNMF_CUDA_CHECK(cudaMemsetAsync(d->X_hi, 0, nx * sizeof(float), s));
+      CNMF_CUDA_CHECK(cudaMemsetAsync(d->Xt_hi, 0, nxt * sizeof(float), s));
+      CNMF_TRY(launch_build_counts(d->X, d->n_rows, d->n_cols, d->ld_c, d->row_scale, d->col_scale, d->X_hi, s));
+      CNMF_TRY(launch_transpose(d->X_hi, d->n_rows, d->n_cols, d->ld_c, d->Xt_hi, nullptr, nullptr, d->ld_r, s));
+      h->launches += 2;
+    } else {
     CNMF_TRY(dataset_alloc(d, &d->X_hi, nx));
     CNMF_TRY(dataset_alloc(d, &d->X_lo, nx));
     CNMF_TRY(dataset_alloc(d, &d->Xt_hi, nxt));
@@ -218,6 +250,7 @@ static int dataset_finish(cnmf_dataset_s* d, cudaStream_t s) {
     CNMF_TRY(launch_split_tf32(d->X, d->X_hi, d->X_lo, (long long)nx, s));
     CNMF_TRY(launch_transpose(d->X, d->n_rows, d->n_cols, d->ld_c, nullptr, d->Xt_hi, d->Xt_lo, d->ld_r, s));
     h->launches += 2;
+    }
   } else {
     CNMF_TRY(dataset_alloc(d, &d->Xt, nxt));
     CNMF_CUDA_CHECK(cudaMemsetAsync(d->Xt, 0, nxt * sizeof(float), s));
@@ -241,7 +274,8 @@ int cnmf_dataset_create(cnmf_handle_t h, const float* X, int n_rows, int n_cols,
                         int precision, void* stream, cnmf_dataset_t* out) {
   CNMF_REQUIRE(h && X && out, "dataset_create: NULL argument");
   CNMF_REQUIRE(n_rows > 0 && n_cols > 0 && ld >= n_cols, "dataset_create: bad shape");
-  CNMF_REQUIRE(precision == CNMF_PRECISION_FP32 || precision == CNMF_PRECISION_TF32X3, "dataset_create: bad precision");
+  CNMF_REQUIRE(precision == CNMF_PRECISION_FP32 || precision == CNMF_PRECISION_TF32X3 ||
+                   precision == CNMF_PRECISION_TF32X3_GENERAL, "dataset_create: bad precision");
   cudaStream_t s = as_stream(stream);
   CNMF_CUDA_CHECK(cudaSetDevice(h->device));
   auto* d = new cnmf_dataset_s();
@@ -250,7 +284,8 @@ int cnmf_dataset_create(cnmf_handle_t h, const float* X, int n_rows, int n_cols,
   d->n_cols = n_cols;
   d->ld_c = pad_ld(n_cols);
   d->ld_r = pad_ld(n_rows);
-  d->precision = precision;
+  d->allow_exact = precision != CNMF_PRECISION_TF32X3_GENERAL;
+  d->precision = precision == CNMF_PRECISION_TF32X3_GENERAL ? CNMF_PRECISION_TF32X3 : precision;
   int rc = dataset_alloc(d, &d->X, (size_t)n_rows * d->ld_c);
   if (rc == 0) {
     cudaError_t e = cudaMemsetAsync(d->X, 0, (size_t)n_rows * d->ld_c * sizeof(float), s);
@@ -287,6 +322,8 @@ int cnmf_dataset_shape(cnmf_dataset_t d, int* n_rows, int* n_cols) {
   if (n_cols) *n_cols = d->n_cols;
   return 0;
 }
+
+int cnmf_dataset_is_exact(cnmf_dataset_t d) { return (d && d->exact) ? 1 : 0; }
 
 int cnmf_dataset_sums(cnmf_dataset_t d, double* sum, double* sum_sq) {
   CNMF_REQUIRE(d, "dataset_sums: NULL dataset");
@@ -355,12 +392,12 @@ int run_and_download(cnmf_dataset_s* d, const std::vector<int>& ks, int SK, Fact
                      double* err_host, cudaStream_t s) {
   cnmf_handle_s* h = d->h;
   const bool tf32 = p.precision == CNMF_PRECISION_TF32X3;
+  DataView v = make_view(d, false);
   if (tf32) {
-    CNMF_TRY(launch_split_tf32(fb.Fr, fb.Fr_hi, fb.Fr_lo, (long long)SK * d->ld_r, s));
-    CNMF_TRY(launch_split_tf32(fb.Fc, fb.Fc_hi, fb.Fc_lo, (long long)SK * d->ld_c, s));
+    CNMF_TRY(launch_split_scaled(fb.Fr, fb.Fr_hi, fb.Fr_lo, SK, d->ld_r, v.exact ? v.scale_r : nullptr, s));
+    CNMF_TRY(launch_split_scaled(fb.Fc, fb.Fc_hi, fb.Fc_lo, SK, d->ld_c, v.exact ? v.scale_c : nullptr, s));
     h->launches += 2;
   }
-  DataView v = make_view(d, false);
   SolveIO io;
   io.R = (int)ks.size();
   io.ks = ks;
@@ -507,12 +544,12 @@ int cnmf_factorize_dev(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, c
   CNMF_TRY(alloc_factors(h, SK, d->ld_r, d->ld_c, tf32, &fb));
   CNMF_CUDA_CHECK(cudaMemcpyAsync(fb.Fr, Wt0_dev, (size_t)SK * d->ld_r * 4, cudaMemcpyDeviceToDevice, s));
   CNMF_CUDA_CHECK(cudaMemcpyAsync(fb.Fc, H0_dev, (size_t)SK * d->ld_c * 4, cudaMemcpyDeviceToDevice, s));
+  DataView v = make_view(d, false);
   if (tf32) {
-    CNMF_TRY(launch_split_tf32(fb.Fr, fb.Fr_hi, fb.Fr_lo, (long long)SK * d->ld_r, s));
-    CNMF_TRY(launch_split_tf32(fb.Fc, fb.Fc_hi, fb.Fc_lo, (long long)SK * d->ld_c, s));
+    CNMF_TRY(launch_split_scaled(fb.Fr, fb.Fr_hi, fb.Fr_lo, SK, d->ld_r, v.exact ? v.scale_r : nullptr, s));
+    CNMF_TRY(launch_split_scaled(fb.Fc, fb.Fc_hi, fb.Fc_lo, SK, d->ld_c, v.exact ? v.scale_c : nullptr, s));
     h->launches += 2;
   }
-  DataView v = make_view(d, false);
   SolveIO io;
   io.R = n_restarts;
   io.ks = ks;

@@ -41,6 +41,13 @@ __global__ void col_stats_kernel(const float* __restrict__ X, int rows, int cols
   atomicAdd(&var[c], q);
 }
 
+__global__ void combine_scale_kernel(const float* __restrict__ scale, const float* __restrict__ src_cs,
+                                     const int* __restrict__ cols, int n, int n_pad, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_pad) return;
+  out[c] = (c < n) ? scale[c] * (src_cs ? src_cs[cols[c]] : 1.f) : 0.f;
+}
+
 __global__ void gather_cols_kernel(const float* __restrict__ src, int rows, int ld_src, const int* __restrict__ cols,
                                    const float* __restrict__ scale, int n_cols, float* __restrict__ dst, int ld_dst) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -101,6 +108,7 @@ int cnmf_dataset_from_columns(cnmf_dataset_t src, const int32_t* cols_host, cons
   d->ld_c = pad_ld(n_cols);
   d->ld_r = pad_ld(src->n_rows);
   d->precision = src->precision;
+  d->allow_exact = src->allow_exact;
   int rc = cnmf_dataset_alloc_internal(d, &d->X, (size_t)d->n_rows * d->ld_c);
   if (rc == 0) {
     cudaError_t e = cudaMemsetAsync(d->X, 0, (size_t)d->n_rows * d->ld_c * sizeof(float), s);
@@ -115,6 +123,22 @@ int cnmf_dataset_from_columns(cnmf_dataset_t src, const int32_t* cols_host, cons
       gather_cols_kernel<<<grid, 128, 0, s>>>(src->X, d->n_rows, src->ld_c, d_cols, d_scale, n_cols, d->X, d->ld_c);
       h->launches += 1;
       if (cudaGetLastError() != cudaSuccess) rc = -2;
+    }
+  }
+  if (rc == 0 && src->exact) {
+    // an exact-count source stays exact: same integer matrix (the selected columns), same row scale, and the
+    // column scale becomes scale[c] * src.col_scale[cols[c]]; finish() rebuilds C from the scaled values
+    d->exact = true;
+    rc = cnmf_dataset_alloc_internal(d, &d->col_scale, (size_t)d->ld_c);
+    if (rc == 0) {
+      combine_scale_kernel<<<(d->ld_c + 255) / 256, 256, 0, s>>>(d_scale, src->col_scale, d_cols, n_cols, d->ld_c, d->col_scale);
+      h->launches += 1;
+      if (cudaGetLastError() != cudaSuccess) rc = -2;
+    }
+    if (rc == 0 && src->row_scale) {
+      rc = cnmf_dataset_alloc_internal(d, &d->row_scale, (size_t)d->ld_r);
+      if (rc == 0 && cudaMemcpyAsync(d->row_scale, src->row_scale, sizeof(float) * d->ld_r, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+        rc = -2;
     }
   }
   if (rc == 0) rc = cnmf_dataset_finish_internal(d, stream);
@@ -162,8 +186,8 @@ int cnmf_refit(cnmf_dataset_t d, int transposed, int k, const float* fixed_host,
     h->launches += 1;
   }  // 'cd': zeros (sklearn _nmf.py:1227-1228)
   if (tf32) {
-    CNMF_TRY(launch_split_tf32(Fr, Fr_hi, Fr_lo, (long long)nr, s));
-    CNMF_TRY(launch_split_tf32(Fc, Fc_hi, Fc_lo, (long long)nc, s));
+    CNMF_TRY(launch_split_scaled(Fr, Fr_hi, Fr_lo, k, v.ld_r, v.exact ? v.scale_r : nullptr, s));
+    CNMF_TRY(launch_split_scaled(Fc, Fc_hi, Fc_lo, k, v.ld_c, v.exact ? v.scale_c : nullptr, s));
     h->launches += 2;
   }
   SolveIO io;
@@ -207,7 +231,7 @@ int cnmf_project_rows(cnmf_dataset_t d, int k, const float* Ut_host, float* out_
     A_hi = static_cast<float*>(h->dev_buf("proj.A_hi", nr * 4));
     A_lo = static_cast<float*>(h->dev_buf("proj.A_lo", nr * 4));
     if (!A_hi || !A_lo) return -2;
-    CNMF_TRY(launch_split_tf32(A, A_hi, A_lo, (long long)nr, s));
+    CNMF_TRY(launch_split_scaled(A, A_hi, A_lo, k, d->ld_r, d->exact ? d->row_scale : nullptr, s));
     h->launches += 1;
   }
   GemmArgs g{};
@@ -228,6 +252,8 @@ int cnmf_project_rows(cnmf_dataset_t d, int k, const float* Ut_host, float* out_
   g.C = C;
   if (tf32) {
     g.A_hi = A_hi; g.A_lo = A_lo; g.B_hi = d->Xt_hi; g.B_lo = d->Xt_lo;
+    g.b_exact = d->exact ? 1 : 0;
+    g.out_col_scale = d->exact ? d->col_scale : nullptr;
     CNMF_TRY(gemm_tf32x3(g, s));
   } else {
     g.A_hi = A; g.B_hi = d->Xt;

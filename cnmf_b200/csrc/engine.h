@@ -51,6 +51,13 @@ struct cnmf_dataset_s {
   int precision = 0;
   float *X = nullptr, *Xt = nullptr;
   float *X_hi = nullptr, *X_lo = nullptr, *Xt_hi = nullptr, *Xt_lo = nullptr;
+  // "exact" datasets (tf32x3 only): X = diag(row_scale) * C * diag(col_scale) with C small non-negative integers
+  // (what HVG-normalised counts and TPM are).  Then X_hi / Xt_hi hold C / C^T -- exactly representable in tf32,
+  // no lo piece -- the scales are folded into the factor pieces / applied to the GEMM output, and every big
+  // product needs 2 tensor-core passes instead of 3.  Either scale may be nullptr (= 1).
+  bool exact = false;
+  bool allow_exact = true;
+  float *row_scale = nullptr, *col_scale = nullptr;    // lengths ld_r / ld_c, zero padded
   double sum = 0.0, sum_sq = 0.0;
   std::vector<std::pair<void*, size_t>> owned;
 };
@@ -61,7 +68,7 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 struct Operand {     // a K-major matrix as the GEMM sees it
   const float* full;
-  const float* hi;
+  const float* hi;     // tf32 hi piece, or the exact integer matrix when `exact`
   const float* lo;
   int rows, cols, ld;
 };
@@ -73,6 +80,9 @@ struct DataView {
   Operand B_cols;   // n_c x n_r : B operand when updating Fc (reduction over n_r)
   int n_r, n_c, ld_r, ld_c;
   double sum, sum_sq;
+  bool exact;               // both operands hold exact integers; scales below complete X
+  const float* scale_r;     // per row-item scale (length ld_r) or nullptr
+  const float* scale_c;     // per column-item scale (length ld_c) or nullptr
 };
 
 DataView make_view(const cnmf_dataset_s* d, bool transposed);

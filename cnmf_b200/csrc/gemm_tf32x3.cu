@@ -46,11 +46,13 @@ constexpr int NUM_EPI_WARPS = 8;                         // two per TMEM lane qu
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;      // 320
 constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;   // ~2 s: a dead pipeline traps instead of hanging
 
-template <int BN, int STAGES>
+// BEXACT: the B operand is exactly representable in tf32 (e.g. integer counts), so it needs no "lo" piece:
+// 2 MMAs per k-step instead of 3, 64 KB stages (3 of them) instead of 96 KB (2).
+template <int BN, int STAGES, bool BEXACT>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 4;              // 16 KB
   static constexpr int B_BYTES = BN * BK * 4;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + (BEXACT ? 1 : 2) * B_BYTES;
   static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFFSET = TILE_BYTES;            // full[STAGES], empty[STAGES], tfull[2], tempty[2]
   static constexpr int TMEM_PTR_OFFSET = BAR_OFFSET + (2 * STAGES + 4) * 8;
@@ -143,13 +145,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ the kernel
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool BEXACT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    float* __restrict__ C, int M, int N, int ldc, long long c_split_stride,
-                   int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split, int chain_kb, int bn) {
-  using L = SmemLayout<BN, STAGES>;
+                   int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split, int chain_kb, int bn,
+                   const float* __restrict__ out_scale) {
+  using L = SmemLayout<BN, STAGES, BEXACT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024 B alignment
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -202,11 +205,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 0);
           const uint32_t st = smem_base + stage * L::STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), 2u * L::A_BYTES + 2u * static_cast<uint32_t>(bn) * BK * 4u);
+          mbar_arrive_expect_tx(full_bar(stage),
+                                2u * L::A_BYTES + (BEXACT ? 1u : 2u) * static_cast<uint32_t>(bn) * BK * 4u);
           tma_load_2d(st, &tmA_hi, full_bar(stage), kb * BK, mt * BM);
           tma_load_2d(st + L::A_BYTES, &tmA_lo, full_bar(stage), kb * BK, mt * BM);
           tma_load_2d(st + 2 * L::A_BYTES, &tmB_hi, full_bar(stage), kb * BK, nt * bn);
-          tma_load_2d(st + 2 * L::A_BYTES + L::B_BYTES, &tmB_lo, full_bar(stage), kb * BK, nt * bn);
+          if constexpr (!BEXACT) tma_load_2d(st + 2 * L::A_BYTES + L::B_BYTES, &tmB_lo, full_bar(stage), kb * BK, nt * bn);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -240,7 +244,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 4) >> 4);   // +32 B per k-step inside the swizzle row
               umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, (kb > c0 || k > 0) ? 1u : 0u);   // small terms first
-              umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1u);
+              if constexpr (!BEXACT) umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1u);
               umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, 1u);
             }
             umma_commit(empty_bar(stage));         // smem slot is free once these MMAs have read it
@@ -294,8 +298,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         const int col0 = nt * bn + half * HALF;
 #pragma unroll
         for (int i = 0; i < HALF; i += 4) {
-          if (half * HALF + i < bn && col0 + i + 3 < ldc)
-            *reinterpret_cast<float4*>(crow + col0 + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+          if (half * HALF + i < bn && col0 + i + 3 < ldc) {
+            float4 v = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+            if (out_scale) {                            // per-output-column scale (length >= ldc, zero padded)
+              const float4 sc = *reinterpret_cast<const float4*>(out_scale + col0 + i);
+              v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+            }
+            *reinterpret_cast<float4*>(crow + col0 + i) = v;
+          }
         }
       }
     }
@@ -345,9 +355,9 @@ int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int
   return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool BEXACT>
 int launch(const GemmArgs& g, cudaStream_t stream) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, BEXACT>;
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
   if ((rc = make_map(&mAh, g.A_hi, g.M, g.Kd, g.lda, BM))) return rc;
@@ -377,7 +387,7 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
     if (env_bn >= 16 && env_bn <= BN && env_bn % 16 == 0) bn = env_bn;
   }
   if ((rc = make_map(&mBh, g.B_hi, g.N, g.Kd, g.ldb, bn))) return rc;
-  if ((rc = make_map(&mBl, g.B_lo, g.N, g.Kd, g.ldb, bn))) return rc;
+  if ((rc = make_map(&mBl, BEXACT ? g.B_hi : g.B_lo, g.N, g.Kd, g.ldb, bn))) return rc;
 
   const int n_tiles = (g.N + bn - 1) / bn;
   const int total_kb = (g.Kd + BK - 1) / BK;
@@ -387,7 +397,7 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   splits = (total_kb + kb_per_split - 1) / kb_per_split;      // no empty slices
   if (splits != g.splits_effective) { set_last_error("gemm: splits_effective mismatch (use gemm_effective_splits)"); return -1; }
 
-  auto kern = gemm_tf32x3_kernel<BN, STAGES>;
+  auto kern = gemm_tf32x3_kernel<BN, STAGES, BEXACT>;
   static bool attr_set = false;
   if (!attr_set) {
     CNMF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
@@ -406,7 +416,7 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   }
   kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(mAh, mAl, mBh, mBl, g.C, g.M, g.N, g.ldc, g.c_split_stride,
                                                     m_tiles, n_tiles, splits, total_kb, kb_per_split,
-                                                    chain_kb, bn);
+                                                    chain_kb, bn, g.out_col_scale);
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -426,8 +436,10 @@ int gemm_tf32x3(const GemmArgs& g, cudaStream_t stream) {
   CNMF_REQUIRE(g.lda % 4 == 0 && g.ldb % 4 == 0 && g.ldc % 4 == 0, "gemm: leading dimensions must be multiples of 4 floats");
   CNMF_REQUIRE((reinterpret_cast<uintptr_t>(g.A_hi) | reinterpret_cast<uintptr_t>(g.A_lo) |
                 reinterpret_cast<uintptr_t>(g.B_hi) | reinterpret_cast<uintptr_t>(g.B_lo) |
-                reinterpret_cast<uintptr_t>(g.C)) % 16 == 0, "gemm: pointers must be 16-byte aligned");
-  return launch<256, 2>(g, stream);
+                reinterpret_cast<uintptr_t>(g.C) | reinterpret_cast<uintptr_t>(g.out_col_scale)) % 16 == 0,
+               "gemm: pointers must be 16-byte aligned");
+  if (g.b_exact) return launch<256, 3, true>(g, stream);
+  return launch<256, 2, false>(g, stream);
 }
 
 }  // namespace cnmf

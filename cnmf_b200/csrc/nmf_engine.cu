@@ -32,6 +32,9 @@ DataView make_view(const cnmf_dataset_s* d, bool transposed) {
   }
   v.sum = d->sum;
   v.sum_sq = d->sum_sq;
+  v.exact = d->exact;
+  v.scale_r = transposed ? d->col_scale : d->row_scale;
+  v.scale_c = transposed ? d->row_scale : d->col_scale;
   return v;
 }
 
@@ -54,7 +57,8 @@ struct GemmPlan {
 
 // C[z] (SK x N) = A (SK x Kd) * B (N x Kd)^T
 int run_gemm(cnmf_handle_s* h, int precision, const float* A, const float* A_hi, const float* A_lo, int SK, int lda,
-             const Operand& B, float* C, int ldc, const GemmPlan& plan, cudaStream_t s) {
+             const Operand& B, float* C, int ldc, const GemmPlan& plan, bool exact, const float* out_scale,
+             cudaStream_t s) {
   GemmArgs g{};
   g.M = SK; g.N = B.rows; g.Kd = B.cols;
   g.lda = lda; g.ldb = B.ld; g.ldc = ldc;
@@ -67,6 +71,8 @@ int run_gemm(cnmf_handle_s* h, int precision, const float* A, const float* A_hi,
   int rc;
   if (precision == CNMF_PRECISION_TF32X3) {
     g.A_hi = A_hi; g.A_lo = A_lo; g.B_hi = B.hi; g.B_lo = B.lo;
+    g.b_exact = exact ? 1 : 0;
+    g.out_col_scale = exact ? out_scale : nullptr;
     rc = gemm_tf32x3(g, s);
   } else {
     g.A_hi = A; g.A_lo = nullptr; g.B_hi = B.full; g.B_lo = nullptr;
@@ -177,9 +183,11 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   bool compacted = false;
 
   auto bm = [&]() { return BatchMeta{d_off, d_k, d_rid, d_done, R, kp}; };
-  auto fr = [&]() { return FactorView{wFr, tf32 ? wFr_hi : nullptr, tf32 ? wFr_lo : nullptr, v.n_r, v.ld_r, cpb_r, gcpb_r}; };
+  auto fr = [&]() {
+    return FactorView{wFr, tf32 ? wFr_hi : nullptr, tf32 ? wFr_lo : nullptr, v.n_r, v.ld_r, v.exact ? v.scale_r : nullptr, cpb_r, gcpb_r};
+  };
   auto fc = [&]() {
-    FactorView f{wFc, tf32 ? wFc_hi : nullptr, tf32 ? wFc_lo : nullptr, v.n_c, v.ld_c, cpb_c, gcpb_c};
+    FactorView f{wFc, tf32 ? wFc_hi : nullptr, tf32 ? wFc_lo : nullptr, v.n_c, v.ld_c, v.exact ? v.scale_c : nullptr, cpb_c, gcpb_c};
     if (!io.update_cols) { f.F_hi = nullptr; f.F_lo = nullptr; }   // never rewritten
     return f;
   };
@@ -193,10 +201,10 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     return launch_finalize(nullptr, nullptr, part, out, chunks, bm(), s);
   };
   auto gemm_rows = [&]() -> int {   // NUM_r = Fc * B_rows^T
-    return run_gemm(h, p.precision, wFc, wFc_hi, wFc_lo, SK, v.ld_c, v.B_rows, NUMr, v.ld_r, plan_r, s);
+    return run_gemm(h, p.precision, wFc, wFc_hi, wFc_lo, SK, v.ld_c, v.B_rows, NUMr, v.ld_r, plan_r, v.exact, v.scale_r, s);
   };
   auto gemm_cols = [&]() -> int {   // NUM_c = Fr * B_cols^T
-    return run_gemm(h, p.precision, wFr, wFr_hi, wFr_lo, SK, v.ld_r, v.B_cols, NUMc, v.ld_c, plan_c, s);
+    return run_gemm(h, p.precision, wFr, wFr_hi, wFr_lo, SK, v.ld_r, v.B_cols, NUMc, v.ld_c, plan_c, v.exact, v.scale_c, s);
   };
 
   // gathers `cnt` restarts' rows: dst[dst_off[i] ..] <- src[src_off[i] ..].  Index triples go through a pinned

@@ -38,6 +38,80 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, float* __restri
   }
 }
 
+__global__ void split_scaled_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
+                                    int rows, int ld, const float* __restrict__ col_scale) {
+  const int ld4 = ld / 4;
+  const long long n4 = (long long)rows * ld4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % ld4);
+    float4 v = reinterpret_cast<const float4*>(src)[i];
+    if (col_scale) {
+      const float4 sc = reinterpret_cast<const float4*>(col_scale)[c4];
+      v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+    }
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x);
+    split_tf32(v.y, h.y, l.y);
+    split_tf32(v.z, h.z, l.z);
+    split_tf32(v.w, h.w, l.w);
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
+  }
+}
+
+// positive floats order like their bit patterns: atomicMin on the int view
+__global__ void min_positive_kernel(const float* __restrict__ X, int rows, int cols, int ld, int* __restrict__ col_min,
+                                    int* __restrict__ row_min) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r0 = blockIdx.y * 64;
+  int cm = 0x7f800000;
+  for (int r = r0; r < min(rows, r0 + 64); ++r) {
+    const float v = (c < cols) ? X[(long long)r * ld + c] : 0.f;
+    int b = (v > 0.f) ? __float_as_int(v) : 0x7f800000;
+    cm = min(cm, b);
+    // row minimum: warp reduce then one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) b = min(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if ((threadIdx.x & 31) == 0 && b != 0x7f800000) atomicMin(&row_min[r], b);
+  }
+  if (c < cols && cm != 0x7f800000) atomicMin(&col_min[c], cm);
+}
+
+__global__ void check_scaled_int_kernel(const float* __restrict__ X, int rows, int cols, int ld,
+                                        const float* __restrict__ rs, const float* __restrict__ cs, int* __restrict__ n_bad) {
+  int bad = 0;
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const float v = X[(long long)r * ld + c];
+    if (v == 0.f) continue;
+    const float sc = (rs ? rs[r] : 1.f) * (cs ? cs[c] : 1.f);
+    const float q = v / sc;
+    const float n = rintf(q);
+    if (!(v > 0.f) || !(n >= 1.f) || n > 2048.f || fabsf(q - n) > 1e-4f * n) ++bad;
+  }
+  bad = warp_sum(bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(n_bad, bad);
+}
+
+__global__ void build_counts_kernel(const float* __restrict__ X, int rows, int cols, int ld, const float* __restrict__ rs,
+                                    const float* __restrict__ cs, float* __restrict__ C) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const float v = X[(long long)r * ld + c];
+    const float sc = (rs ? rs[r] : 1.f) * (cs ? cs[c] : 1.f);
+    C[(long long)r * ld + c] = (v == 0.f) ? 0.f : rintf(v / sc);
+  }
+}
+
+__global__ void fix_scale_kernel(float* __restrict__ v, int n, int n_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  if (i >= n) { v[i] = 0.f; return; }
+  const float x = v[i];
+  v[i] = (isfinite(x) && x > 0.f && x < 1e30f) ? x : 1.f;   // rows / columns without a positive entry: any scale works
+}
+
 __global__ void transpose_kernel(const float* __restrict__ src, int rows, int cols, int ld_src, float* __restrict__ dst,
                                  float* __restrict__ dst_hi, float* __restrict__ dst_lo, int ld_dst) {
   __shared__ float tile[32][33];
@@ -128,11 +202,11 @@ __device__ __forceinline__ void load_column(const FactorView& f, const float* __
   }
 }
 
-__device__ __forceinline__ void store_elem(const FactorView& f, long long e, float v) {
+__device__ __forceinline__ void store_elem(const FactorView& f, long long e, float v, float pscale) {
   f.F[e] = v;
   if (f.F_hi) {
     float h, l;
-    split_tf32(v, h, l);
+    split_tf32(v * pscale, h, l);
     f.F_hi[e] = h;
     f.F_lo[e] = l;
   }
@@ -146,6 +220,7 @@ __device__ __forceinline__ double mu_body(const FactorView& f, const float* __re
   for (int col = col_begin + threadIdx.x; col < col_end; col += UPD_THREADS) {
     float fv[KP], nv[KP];
     load_column<KP>(f, NUM, nsplit, sstride, K, o, col, fv, nv);
+    const float pscale = f.piece_scale ? f.piece_scale[col] : 1.f;
 #pragma unroll
     for (int c = 0; c < KP; ++c) {
       if (c < K) {
@@ -162,7 +237,7 @@ __device__ __forceinline__ double mu_body(const FactorView& f, const float* __re
         if (l2 > 0.f) den += l2 * fv[c];
         if (den == 0.f) den = EPSILON_F32;
         const float fn = fv[c] * (nv[c] / den);
-        store_elem(f, (long long)(o + c) * f.ld + col, fn);
+        store_elem(f, (long long)(o + c) * f.ld + col, fn, pscale);
         cross += (double)nv[c] * (double)fn;
       }
     }
@@ -179,6 +254,7 @@ __device__ __forceinline__ double cd_body(const FactorView& f, const float* __re
   for (int col = col_begin + threadIdx.x; col < col_end; col += UPD_THREADS) {
     float fv[KP], nv[KP];
     load_column<KP>(f, NUM, nsplit, sstride, K, o, col, fv, nv);
+    const float pscale = f.piece_scale ? f.piece_scale[col] : 1.f;
 #pragma unroll
     for (int t = 0; t < KP; ++t) {
       if (t < K) {
@@ -195,7 +271,7 @@ __device__ __forceinline__ double cd_body(const FactorView& f, const float* __re
         viol += (double)fabsf(pg);
         const float h = Gs[t * KP + t];
         if (h != 0.f) fv[t] = fmaxf(fv[t] - g / h, 0.f);
-        store_elem(f, (long long)(o + t) * f.ld + col, fv[t]);
+        store_elem(f, (long long)(o + t) * f.ld + col, fv[t], pscale);
       }
     }
   }
@@ -479,6 +555,46 @@ int launch_split_tf32(const float* src, float* hi, float* lo, long long n_elems,
   if (n4 == 0) return 0;
   const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
   split_tf32_kernel<<<blocks, 256, 0, s>>>(src, hi, lo, n4);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_split_scaled(const float* src, float* hi, float* lo, int rows, int ld, const float* col_scale, cudaStream_t s) {
+  CNMF_REQUIRE(ld % 4 == 0, "split_scaled: ld must be a multiple of 4");
+  const long long n4 = (long long)rows * (ld / 4);
+  if (n4 == 0) return 0;
+  const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  split_scaled_kernel<<<blocks, 256, 0, s>>>(src, hi, lo, rows, ld, col_scale);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_min_positive(const float* X, int rows, int cols, int ld, float* col_min, float* row_min, cudaStream_t s) {
+  CNMF_CUDA_CHECK(cudaMemsetAsync(col_min, 0x7f, sizeof(float) * cols, s));   // 0x7f7f7f7f: a huge finite float
+  CNMF_CUDA_CHECK(cudaMemsetAsync(row_min, 0x7f, sizeof(float) * rows, s));
+  dim3 grid((cols + 255) / 256, (rows + 63) / 64);
+  CNMF_REQUIRE(grid.y <= 65535, "min_positive: too many rows for one launch");
+  min_positive_kernel<<<grid, 256, 0, s>>>(X, rows, cols, ld, reinterpret_cast<int*>(col_min), reinterpret_cast<int*>(row_min));
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_check_scaled_int(const float* X, int rows, int cols, int ld, const float* row_scale, const float* col_scale,
+                            int* n_bad, cudaStream_t s) {
+  check_scaled_int_kernel<<<148 * 8, 256, 0, s>>>(X, rows, cols, ld, row_scale, col_scale, n_bad);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_build_counts(const float* X, int rows, int cols, int ld, const float* row_scale, const float* col_scale,
+                        float* C, cudaStream_t s) {
+  build_counts_kernel<<<148 * 8, 256, 0, s>>>(X, rows, cols, ld, row_scale, col_scale, C);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_fix_scale(float* v, int n, int n_pad, cudaStream_t s) {
+  fix_scale_kernel<<<(n_pad + 255) / 256, 256, 0, s>>>(v, n, n_pad);
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

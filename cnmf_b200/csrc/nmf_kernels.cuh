@@ -20,6 +20,8 @@ struct FactorView {
   float* F_lo;
   int n;           // valid columns
   int ld;
+  const float* piece_scale;   // optional per-column scale folded into the tf32 pieces: hi + lo = F * piece_scale
+                              // (exact-count datasets: the per-gene / per-cell scale of X lives in the A operand)
   int cpb;         // columns handled by one block of the update / cross kernels (multiple of 256)
   int gcpb;        // columns handled by one block of the Gram kernel (multiple of 1024)
 };
@@ -49,6 +51,21 @@ inline int gram_chunks(const FactorView& f) { return (f.n + f.gcpb - 1) / f.gcpb
 
 // x -> (hi, lo) tf32 pieces, elementwise over rows x ld (padding included)
 int launch_split_tf32(const float* src, float* hi, float* lo, long long n_elems, cudaStream_t s);
+// (hi, lo) = split(src[r, c] * col_scale[c]) over rows x ld; col_scale may be nullptr (plain split)
+int launch_split_scaled(const float* src, float* hi, float* lo, int rows, int ld, const float* col_scale, cudaStream_t s);
+
+// ---- exact-count detection (dataset preparation) ----
+// col_min[c] / row_min[r] = smallest strictly positive entry of the column / row (+inf if none)
+int launch_min_positive(const float* X, int rows, int cols, int ld, float* col_min, float* row_min, cudaStream_t s);
+// counts entries that are not (positive-integer <= 2048) * row_scale[r] * col_scale[c] within 1e-4 relative
+// (either scale may be nullptr = 1); *n_bad is accumulated atomically (zero it first)
+int launch_check_scaled_int(const float* X, int rows, int cols, int ld, const float* row_scale, const float* col_scale,
+                            int* n_bad, cudaStream_t s);
+// C[r, c] = rint(X[r, c] / (row_scale[r] * col_scale[c])) as fp32 (exact in tf32 for values <= 2048)
+int launch_build_counts(const float* X, int rows, int cols, int ld, const float* row_scale, const float* col_scale,
+                        float* C, cudaStream_t s);
+// v[i] = isfinite(v[i]) && v[i] > 0 ? v[i] : 1 for i < n, 0 for n <= i < n_pad
+int launch_fix_scale(float* v, int n, int n_pad, cudaStream_t s);
 
 // dst (cols x ld_dst) = src (rows x ld_src)^T ; optionally also emits tf32 pieces of dst
 int launch_transpose(const float* src, int rows, int cols, int ld_src, float* dst, float* dst_hi, float* dst_lo,

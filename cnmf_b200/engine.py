@@ -8,15 +8,21 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import NmfParams, PRECISION_FP32, PRECISION_TF32X3, SOLVER_CD, SOLVER_MU, check, f32c, ptr
+from ._lib import (NmfParams, PRECISION_FP32, PRECISION_TF32X3, PRECISION_TF32X3_GENERAL, SOLVER_CD, SOLVER_MU,
+                   check, f32c, ptr)
 
 _DEFAULT_PRECISION = PRECISION_TF32X3
 
 
 def precision_code(p):
-    if p in (PRECISION_FP32, PRECISION_TF32X3):
+    """'fp32' | 'tf32x3' (default; 2-pass products when X is scaled integer counts) | 'tf32x3-general' (always 3-pass)."""
+    if p in (PRECISION_FP32, PRECISION_TF32X3, PRECISION_TF32X3_GENERAL):
         return p
-    return {"fp32": PRECISION_FP32, "tf32x3": PRECISION_TF32X3}[p]
+    return {"fp32": PRECISION_FP32, "tf32x3": PRECISION_TF32X3, "tf32x3-general": PRECISION_TF32X3_GENERAL}[p]
+
+
+def _params_precision(p):
+    return PRECISION_TF32X3 if p == PRECISION_TF32X3_GENERAL else p
 
 
 def make_params(nmf_kwargs, n_samples, n_features, precision):
@@ -38,7 +44,7 @@ def make_params(nmf_kwargs, n_samples, n_features, precision):
     l1_ratio = float(nmf_kwargs.get("l1_ratio", 0.0))
     p = NmfParams()
     p.solver = SOLVER_MU if solver == "mu" else SOLVER_CD
-    p.precision = precision_code(precision)
+    p.precision = _params_precision(precision_code(precision))
     p.max_iter = int(nmf_kwargs.get("max_iter", 1000))
     p.tol = float(nmf_kwargs.get("tol", 1e-4))
     p.l1_reg_W = n_features * alpha_W * l1_ratio
@@ -99,7 +105,7 @@ class Engine:
         assert B.shape[1] == Kd
         C = np.empty((M, N), np.float32)
         ms = ctypes.c_float(0)
-        check(self.lib.cnmf_gemm_abt_host(self._h, precision_code(precision), ptr(A), ptr(B), M, N, Kd, splits,
+        check(self.lib.cnmf_gemm_abt_host(self._h, _params_precision(precision_code(precision)), ptr(A), ptr(B), M, N, Kd, splits,
                                           ptr(C), reps, ctypes.byref(ms), None))
         return C, float(ms.value)
 
@@ -153,6 +159,11 @@ class Dataset:
         check(self.lib.cnmf_factorize_dev(self._d, R, ptr(ks), ctypes.c_void_p(Wt0_ptr), ctypes.c_void_p(H0_ptr),
                                           ctypes.byref(p), ctypes.c_void_p(out_ptr), ptr(n_iter), ptr(err), None))
         return n_iter, err
+
+    @property
+    def exact(self):
+        """True when X was recognised as scaled integer counts (2-pass tensor-core products)."""
+        return bool(self.lib.cnmf_dataset_is_exact(self._d))
 
     def sums(self):
         s, q = ctypes.c_double(), ctypes.c_double()

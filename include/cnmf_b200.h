@@ -35,7 +35,9 @@ typedef struct cnmf_handle_s* cnmf_handle_t;
 typedef struct cnmf_dataset_s* cnmf_dataset_t;
 
 enum { CNMF_SOLVER_MU = 0, CNMF_SOLVER_CD = 1 };            /* yaml 'solver': cnmf.py:618-631 */
-enum { CNMF_PRECISION_FP32 = 0, CNMF_PRECISION_TF32X3 = 1 }; /* FFMA  |  tcgen05 3xTF32 (default) */
+/* FFMA | tcgen05 3xTF32 with exact-count detection (default: 2 passes when X is scaled integers, else 3) |
+ * tcgen05 3xTF32 always in the general 3-pass form.  Params for a dataset created with 2 use precision 1. */
+enum { CNMF_PRECISION_FP32 = 0, CNMF_PRECISION_TF32X3 = 1, CNMF_PRECISION_TF32X3_GENERAL = 2 };
 
 /* Mirrors the nmf_kwargs dict of cnmf.py:618-627 after sklearn's own scaling of the
  * regularisation (sklearn/decomposition/_nmf.py:1249-1260): l1_reg_W = n_features*alpha_W*l1_ratio ... */
@@ -80,6 +82,11 @@ int cnmf_dataset_shape(cnmf_dataset_t d, int* n_rows, int* n_cols);
 /* padded row strides of the packed factor layout: W^T rows (ld_rows >= n_rows), H rows (ld_cols >= n_cols) */
 int cnmf_dataset_ld(cnmf_dataset_t d, int* ld_rows, int* ld_cols);
 int cnmf_dataset_sums(cnmf_dataset_t d, double* sum, double* sum_sq);
+/* 1 when the dataset was recognised as (row scale) x (integer counts <= 2048) x (column scale) -- what
+ * HVG-normalised counts (cnmf.py:542) and TPM (cnmf.py:245-251) are -- and therefore runs the 2-pass
+ * tensor-core products (the integer operand needs no tf32 "lo" piece); 0 = general 3-pass 3xTF32.
+ * CNMF_EXACT=0 in the environment disables the detection. */
+int cnmf_dataset_is_exact(cnmf_dataset_t d);
 /* per-column mean and population variance (StandardScaler(with_mean=False), cnmf.py:131-134) */
 int cnmf_dataset_col_stats(cnmf_dataset_t d, double* mean_host, double* var_host, void* stream);
 

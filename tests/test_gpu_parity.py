@@ -65,7 +65,22 @@ def test_gemm_properties_full_size(eng):
 
 
 # ------------------------------------------------------------------------------------ factorize
-@pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
+def test_exact_count_detection(eng):
+    """HVG-normalised counts (counts / std) and TPM (counts * 1e6 / total) are recognised as scaled integers and
+    take the 2-pass products; arbitrary real data and 'tf32x3-general' stay on the general 3-pass path."""
+    g = load_golden("sim_mu")
+    assert eng.dataset(g["X"]).exact
+    assert eng.dataset(g["tpm"]).exact
+    assert not eng.dataset(g["X"], precision="tf32x3-general").exact
+    assert not eng.dataset(g["X"], precision="fp32").exact
+    rng = np.random.RandomState(0)
+    assert not eng.dataset(np.abs(rng.randn(300, 120))).exact
+    big = g["X"].copy()
+    big[0, 0] = big[big[:, 0] > 0, 0].min() * 5000        # a count above 2048 is not tf32-exact
+    assert not eng.dataset(big).exact
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32x3-general", "fp32"])
 @pytest.mark.parametrize("tag", ["sim_mu", "sim_cd"])
 def test_factorize_matches_reference_fixture(eng, precision, tag):
     """Every restart of the reference's own factorize() run (fixture): same n_iter, spectra within tolerance."""
@@ -135,14 +150,15 @@ def test_factorize_with_regularisation(eng):
 
 
 # ------------------------------------------------------------------------------------ refits
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32x3-general"])
 @pytest.mark.parametrize("tag", ["sim_mu", "sim_cd"])
-def test_refits_match_oracle(eng, tag):
+def test_refits_match_oracle(eng, tag, precision):
     from oracle import nmf_ref
     g = load_golden(tag)
     k = int(g["ks"][1])
     X, tpm = g["X"], g["tpm"]
     kw = dict(solver=g["solver"], tol=1e-4, max_iter=1000)
-    ds = eng.dataset(X)
+    ds = eng.dataset(X, precision=precision)
     H = g["cspectra_k%d" % k]
     W, it, err = ds.refit(H, kw)
     Wr, itr = nmf_ref.refit(X, H, g["solver"])
@@ -150,10 +166,23 @@ def test_refits_match_oracle(eng, tag):
     assert abs(err - nmf_ref.frobenius_error(X, Wr, H)) / err < 1e-5
     # refit_spectra: transposed problem on the TPM matrix (cnmf.py:805-820, 952)
     U = Wr / Wr.sum(axis=1, keepdims=True)
-    tds = eng.dataset(tpm)
+    tds = eng.dataset(tpm, precision=precision)
     Ht, it2, _ = tds.refit(np.ascontiguousarray(U.T), kw, transposed=True)
     Hr, itr2 = nmf_ref.refit(tpm.T, U.T, g["solver"])
     assert it2 == itr2 and rel(Ht, Hr) < TOL_SPECTRA
+    # column-subset dataset (cnmf.py:965-969: tpm[:, hvgs] / std) keeps its exactness and its values
+    hv = g["hvg_idx"]
+    std1 = tpm[:, hv].std(axis=0, ddof=1)
+    sub = tds.from_columns(hv, 1.0 / std1)
+    assert sub.exact == tds.exact
+    Xs = tpm[:, hv] / std1
+    Hs = np.abs(np.random.RandomState(1).randn(k, len(hv))) + 0.1
+    Ws, its, _ = sub.refit(Hs, kw)
+    Wsr, itsr = nmf_ref.refit(Xs, Hs, g["solver"])
+    assert its == itsr and rel(Ws, Wsr) < TOL_SPECTRA
+    # OLS projection accumulator (cnmf.py:119): Ut @ X with signed (centred) Ut
+    Ut = np.random.RandomState(2).randn(k, tpm.shape[0])
+    assert rel(tds.project_rows(Ut), Ut @ tpm) < 1e-5
 
 
 # ------------------------------------------------------------------------------------ consensus kernels
