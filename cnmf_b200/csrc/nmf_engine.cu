@@ -111,8 +111,10 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   int R = R0, SK = SK0;     // live slots / live packed rows
   const int kp = kmax <= 16 ? 16 : 32;
   // block granularity of the streaming kernels, fixed for the whole solve (partial buffers are sized by it)
-  const int cpb_r = pick_cols_per_block(v.n_r, R0, 2048, 256), cpb_c = pick_cols_per_block(v.n_c, R0, 2048, 256);
-  const int gcpb_r = pick_cols_per_block(v.n_r, R0, 8192, 1024), gcpb_c = pick_cols_per_block(v.n_c, R0, 8192, 1024);
+  // update kernels: 3 blocks/SM resident -> aim for >= 8 blocks per SM; Gram kernel: 1 block/SM resident and a
+  // fixed-cost block reduction -> long blocks, about two waves
+  const int cpb_r = pick_cols_per_block(v.n_r, R0, 2048, 256, 148 * 8), cpb_c = pick_cols_per_block(v.n_c, R0, 2048, 256, 148 * 8);
+  const int gcpb_r = pick_cols_per_block(v.n_r, R0, 8192, 1024, 148 * 2), gcpb_c = pick_cols_per_block(v.n_c, R0, 8192, 1024, 148 * 2);
   const int chunks_r = (v.n_r + cpb_r - 1) / cpb_r, chunks_c = (v.n_c + cpb_c - 1) / cpb_c;
   const int chunks_max = std::max(chunks_r, chunks_c);
   const int gchunks_max = std::max((v.n_r + gcpb_r - 1) / gcpb_r, (v.n_c + gcpb_c - 1) / gcpb_c);

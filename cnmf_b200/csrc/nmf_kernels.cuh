@@ -28,9 +28,9 @@ struct FactorView {
 
 // block granularity: large enough to amortise the per-block prologue, small enough that
 // (column chunks) x (restarts) fills the 148 SMs a few times over even for a single refit
-inline int pick_cols_per_block(int n, int n_restarts, int max_cols, int min_cols) {
+inline int pick_cols_per_block(int n, int n_restarts, int max_cols, int min_cols, int min_blocks) {
   int c = max_cols;
-  while (c > min_cols && (long long)((n + c - 1) / c) * n_restarts < 148 * 8) c /= 2;
+  while (c > min_cols && (long long)((n + c - 1) / c) * n_restarts < min_blocks) c /= 2;
   return c;
 }
 
