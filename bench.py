@@ -114,6 +114,11 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import reference_path
+    try:      # torchrun exports OMP_NUM_THREADS=1 to its children: give the reference all the host threads back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     X = make_data().astype(np.float64)
     ks, seeds = restart_jobs(1, 0)
     jobs = list(zip(ks, seeds))
@@ -284,6 +289,11 @@ def run_ours(args, rank, world, local):
     }
     if world == 1 and not args.no_cpu_baseline:
         from oracle import reference_path
+        try:
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(limits=os.cpu_count())
+        except Exception:
+            pass
         _, its, sec = reference_path.factorize(X.astype(np.float64), [(ks[0], seeds[0])], "mu")
         try:
             from threadpoolctl import threadpool_info

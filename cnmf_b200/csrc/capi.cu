@@ -154,6 +154,13 @@ int cnmf_create(cnmf_handle_t* out, int device) {
   auto* h = new cnmf_handle_s();
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);      // lo = lowest priority (numerically largest)
+    if (cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, lo) != cudaSuccess) h->aux = nullptr;
+    if (cudaEventCreateWithFlags(&h->ev_upd, cudaEventDisableTiming) != cudaSuccess) h->ev_upd = nullptr;
+    if (cudaEventCreateWithFlags(&h->ev_gram, cudaEventDisableTiming) != cudaSuccess) h->ev_gram = nullptr;
+  }
   *out = h;
   return 0;
 }
@@ -161,6 +168,9 @@ int cnmf_create(cnmf_handle_t* out, int device) {
 int cnmf_destroy(cnmf_handle_t h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
+  if (h->aux) cudaStreamDestroy(h->aux);
+  if (h->ev_upd) cudaEventDestroy(h->ev_upd);
+  if (h->ev_gram) cudaEventDestroy(h->ev_gram);
   h->release_all();
   delete h;
   return 0;

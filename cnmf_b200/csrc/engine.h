@@ -15,6 +15,10 @@ struct cnmf_handle_s {
   long long launches = 0;                       // kernels launched by this library (bench: gpu_launches)
   // optional per-launch timing of the dominant kernel (the batched GEMM) with CUDA events on the
   // launching stream; read back by bench.py for the roofline line
+  // auxiliary low-priority stream: the K x K Gram kernels of the MU iteration run here, under the GEMM that
+  // does not depend on them (one-warp blocks that fit beside the resident GEMM CTA)
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_upd = nullptr, ev_gram = nullptr;
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<std::pair<int, double>> ev_pending;   // (index of start event in ev_pool, flops)

@@ -11,6 +11,7 @@
 // (their blocks exit) and the host only polls the flags.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.h"
@@ -198,6 +199,32 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     CNMF_TRY(launch_gram_partial(f, bm(), d_gram_part, s));
     return launch_finalize(d_gram_part, gram_out, nullptr, nullptr, gram_chunks(f), bm(), s);
   };
+  // Overlapped form (MU iteration): the Gram of a freshly updated factor is not needed by the GEMM that follows
+  // the update, only by the update after it.  Run it on the auxiliary stream in one-warp blocks (they fit beside
+  // the resident GEMM CTA: 8 K registers, 2 KB smem) and join before the consumer.  CNMF_OVERLAP=0 disables.
+  static const bool overlap_env = [] { const char* e = std::getenv("CNMF_OVERLAP"); return !(e && e[0] == '0'); }();
+  const bool overlap = overlap_env && mu && io.update_cols && h->aux && h->ev_upd && h->ev_gram;
+  const int gcpb_small = 1024;
+  const int gchunks_small = std::max((v.n_r + gcpb_small - 1) / gcpb_small, (v.n_c + gcpb_small - 1) / gcpb_small);
+  double* d_gram_part2 = nullptr;
+  if (overlap) {
+    d_gram_part2 = static_cast<double*>(h->dev_buf("solve.gram_part_aux", sizeof(double) * (size_t)R0 * gchunks_small * kp * kp));
+    if (!d_gram_part2) return -2;
+  }
+  auto gram_async = [&](FactorView f, double* gram_out) -> int {     // enqueue on aux after everything on s so far
+    f.gcpb = gcpb_small;
+    CNMF_CUDA_CHECK(cudaEventRecord(h->ev_upd, s));
+    CNMF_CUDA_CHECK(cudaStreamWaitEvent(h->aux, h->ev_upd, 0));
+    h->launches += 2;
+    CNMF_TRY(launch_gram_partial(f, bm(), d_gram_part2, h->aux, true));
+    CNMF_TRY(launch_finalize(d_gram_part2, gram_out, nullptr, nullptr, gram_chunks(f), bm(), h->aux));
+    CNMF_CUDA_CHECK(cudaEventRecord(h->ev_gram, h->aux));
+    return 0;
+  };
+  auto gram_join = [&]() -> int {                                    // s waits for the last gram_async
+    CNMF_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_gram, 0));
+    return 0;
+  };
   auto finalize_scal = [&](const double* part, double* out, int chunks) -> int {
     h->launches += 1;
     return launch_finalize(nullptr, nullptr, part, out, chunks, bm(), s);
@@ -351,19 +378,28 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     CNMF_TRY(launch_mu_check(st, d_crossB, d_gramR, d_gramC, normX2, bm(), 0, p.tol, p.max_iter, s));
 
     for (it = 1; it <= p.max_iter; ++it) {
-      if (io.update_cols) CNMF_TRY(gemm_rows());
+      if (io.update_cols) CNMF_TRY(gemm_rows());                    // overlaps gram(Fc) of the previous iteration
+      if (overlap && it > 1) CNMF_TRY(gram_join());                 // update of Fr needs Gram(Fc)
       h->launches += 1;
       CNMF_TRY(launch_mu_update(fr(), NUMr, plan_r.splits, plan_r.split_stride, d_gramC, bm(), l1W, l2W,
                                 io.update_cols ? nullptr : d_scalA, s));
       if (io.update_cols) {
-        CNMF_TRY(gram_of(fr(), d_gramR, chunks_r));
-        CNMF_TRY(gemm_cols());
+        if (overlap) {
+          CNMF_TRY(gram_async(fr(), d_gramR));                      // runs under gemm_cols
+          CNMF_TRY(gemm_cols());
+          CNMF_TRY(gram_join());                                    // update of Fc needs Gram(Fr)
+        } else {
+          CNMF_TRY(gram_of(fr(), d_gramR, chunks_r));
+          CNMF_TRY(gemm_cols());
+        }
         h->launches += 1;
         CNMF_TRY(launch_mu_update(fc(), NUMc, plan_c.splits, plan_c.split_stride, d_gramR, bm(), l1H, l2H, d_scalB, s));
-        CNMF_TRY(gram_of(fc(), d_gramC, chunks_c));
+        if (overlap) CNMF_TRY(gram_async(fc(), d_gramC));           // runs under the next gemm_rows
+        else CNMF_TRY(gram_of(fc(), d_gramC, chunks_c));
       }
       const bool check = (p.tol > 0 && it % 10 == 0) || it == p.max_iter;
       if (check) {
+        if (overlap) CNMF_TRY(gram_join());                         // the error needs both Grams
         if (io.update_cols) {
           CNMF_TRY(finalize_scal(d_scalB, d_crossB, chunks_c));
         } else {
@@ -379,6 +415,7 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
         if (all) break;
       }
     }
+    if (overlap) CNMF_CUDA_CHECK(cudaStreamSynchronize(h->aux));
   } else {
     // ---------------- coordinate descent (sklearn _nmf.py:399-518, shuffle=False) ----------------
     const int poll_every = 4;

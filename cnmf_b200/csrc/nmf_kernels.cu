@@ -362,12 +362,13 @@ cross_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long 
 // one 4-byte column per step was latency-bound at ~0.6 TB/s).  TPC threads cooperate on one column group;
 // partial sums are fp32 over the thread's columns, then fp64 through shuffles + a fixed-order
 // shared-memory reduction (deterministic).  Same per-restart KP dispatch as the update kernels.
-template <int KP>
+template <int KP, int BT>
 struct GramCfg {
   static constexpr int TPC = KP <= 8 ? 1 : (KP <= 16 ? 2 : (KP <= 24 ? 4 : 8));   // threads per column group
   static constexpr int RB = (KP + TPC - 1) / TPC;       // rows of the Gram per thread (last block may be partial)
   static constexpr int VEC = KP <= 12 ? 4 : 2;          // consecutive columns per load (register budget)
-  static constexpr int COLS_PER_ITER = (256 / TPC) * VEC;
+  static constexpr int COLS_PER_ITER = (BT / TPC) * VEC;
+  static constexpr int WARPS = BT / 32;
 };
 
 template <int VEC> struct VecLoad;
@@ -384,10 +385,10 @@ template <> struct VecLoad<2> {
   }
 };
 
-template <int KP>
+template <int KP, int BT>
 __device__ __forceinline__ void gram_body(const FactorView& f, int K, int o, int col_begin, int col_end,
-                                          double* part /* smem 8 x 8 x 32 */, double* __restrict__ out) {
-  using C = GramCfg<KP>;
+                                          double* part /* smem WARPS x 8 x 32 */, double* __restrict__ out) {
+  using C = GramCfg<KP, BT>;
   const int rb = threadIdx.x % C::TPC;                 // which row block of the Gram
   const int cl = threadIdx.x / C::TPC;                 // column-group lane inside the block
   float acc[C::RB][KP];
@@ -438,31 +439,33 @@ __device__ __forceinline__ void gram_body(const FactorView& f, int K, int o, int
       for (int i = 0; i < KP; ++i) part[(warp * 8 + lane) * 32 + i] = v[i];
     }
     __syncthreads();
-    if (threadIdx.x < C::TPC * KP) {
-      const int rbb = threadIdx.x / KP, i = threadIdx.x % KP;
+    for (int t = threadIdx.x; t < C::TPC * KP; t += BT) {
+      const int rbb = t / KP, i = t % KP;
       const int row = rbb * C::RB + a;
       if (row < KP) {
         double sum = 0.0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) sum += part[(w * 8 + rbb) * 32 + i];
+        for (int w = 0; w < C::WARPS; ++w) sum += part[(w * 8 + rbb) * 32 + i];
         out[row * KP + i] = sum;
       }
     }
   }
 }
 
-template <int KPMAX>
-__global__ void __launch_bounds__(256)
+// BT = 256: stand-alone launches (one block per SM by registers).  BT = 32: one-warp blocks that fit beside a
+// resident GEMM CTA (8 K registers, 2 KB smem), used when the Gram runs on the auxiliary stream under a GEMM.
+template <int KPMAX, int BT>
+__global__ void __launch_bounds__(BT)
 gram_partial_kernel(FactorView f, BatchMeta b, double* __restrict__ gram_partial) {
   const int slot = blockIdx.y;
   const int r = b.rid[slot];
   if (b.done[r]) return;
   const int K = b.k[slot], o = b.off[slot];
-  __shared__ double part[8 * 8 * 32];
+  __shared__ double part[(BT / 32) * 8 * 32];
   const int col_begin = blockIdx.x * f.gcpb;
   const int col_end = min(f.n, col_begin + f.gcpb);
   double* out = gram_partial + ((long long)r * gridDim.x + blockIdx.x) * (KPMAX * KPMAX);
-  CNMF_KP_SWITCH(K, KPMAX, (gram_body<KP>(f, K, o, col_begin, col_end, part, out)));
+  CNMF_KP_SWITCH(K, KPMAX, (gram_body<KP, BT>(f, K, o, col_begin, col_end, part, out)));
 }
 
 __global__ void finalize_kernel(const double* __restrict__ gram_partial, double* __restrict__ gram,
@@ -652,9 +655,13 @@ int launch_cross(const FactorView& f, const float* NUM, int nsplit, long long ss
   return 0;
 }
 
-int launch_gram_partial(const FactorView& f, const BatchMeta& b, double* gram_partial, cudaStream_t s) {
+int launch_gram_partial(const FactorView& f, const BatchMeta& b, double* gram_partial, cudaStream_t s, bool one_warp_blocks) {
   dim3 grid(gram_chunks(f), b.R);
-  CNMF_DISPATCH_KPMAX(b.kp, (gram_partial_kernel<KPMAX><<<grid, 256, 0, s>>>(f, b, gram_partial)));
+  if (one_warp_blocks) {
+    CNMF_DISPATCH_KPMAX(b.kp, (gram_partial_kernel<KPMAX, 32><<<grid, 32, 0, s>>>(f, b, gram_partial)));
+  } else {
+    CNMF_DISPATCH_KPMAX(b.kp, (gram_partial_kernel<KPMAX, 256><<<grid, 256, 0, s>>>(f, b, gram_partial)));
+  }
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

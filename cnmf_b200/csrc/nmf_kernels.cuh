@@ -94,7 +94,8 @@ int launch_cross(const FactorView& f, const float* NUM, int nsplit, long long nu
                  double* cross_partial, cudaStream_t s);
 
 // gram_partial[(rid*gram_chunks+chunk)*kp*kp + c*kp + i] = sum_j F[c,j] F[i,j] over the chunk's columns
-int launch_gram_partial(const FactorView& f, const BatchMeta& b, double* gram_partial, cudaStream_t s);
+int launch_gram_partial(const FactorView& f, const BatchMeta& b, double* gram_partial, cudaStream_t s,
+                        bool one_warp_blocks = false);
 
 // gram[r][c*KMAX+i] = sum over chunks (fixed order -> deterministic); scal[r] = sum over chunks of scal_partial
 int launch_finalize(const double* gram_partial, double* gram, const double* scal_partial, double* scal, int chunks,

@@ -33,7 +33,10 @@ def init_process_group(backend=None):
             torch.cuda.set_device(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29512")
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        kwargs = {}
+        if backend == "nccl":
+            kwargs["device_id"] = torch.device("cuda:%d" % local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
     return dist
 
 

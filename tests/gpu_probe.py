@@ -113,6 +113,80 @@ def stage_c3():
                 r, rows[r][0], it, n_iter[r], rel(sp[r], H), time.time() - t3), flush=True)
 
 
+def stage_consensus_c4():
+    """BASELINE configs[3] consensus sizes: R = 4000 stacked spectra (K=20 x 200 restarts) x 2000 genes,
+    density_threshold 0.01-style tight clusters + outliers; refits on 68k x 2k.  GPU vs the reference's sklearn path."""
+    from cnmf_b200 import consensus as cs
+    from cnmf_b200.synth import make_counts, normalise
+    from oracle import reference_path, nmf_ref
+    eng = Engine()
+    rng = np.random.RandomState(11)
+    K, R, G = 20, 4000, 2000
+    cen = np.abs(rng.gamma(0.3, 1.0, size=(K, G)))
+    pts = np.vstack([c * (1 + 0.02 * rng.randn(190, G)) for c in cen] + [np.abs(rng.gamma(0.3, 1.0, size=(200, G)))])
+    pts = np.abs(pts)[rng.permutation(R)]
+    t0 = time.time()
+    dens_r, keep_r, labels_r, med_r = reference_path.consensus_cluster(pts, K, density_threshold=0.1)
+    t_ref = time.time() - t0
+    for rep in range(2):
+        t0 = time.time()
+        S = cs.SpectraMatrix(eng, pts).l2_normalize()
+        dens, _ = S.local_density(int(0.3 * R / K))
+        t1 = time.time()
+        keep = dens < 0.1
+        S2 = S.take_rows(np.where(keep)[0])
+        labels, labels_t, inertia, _ = cs.kmeans(S2, K)
+        t2 = time.time()
+        med = cs.cluster_medians(S2, labels_t, K)
+        t3 = time.time()
+        sil = cs.silhouette(S2, labels, labels_t, K)
+        t4 = time.time()
+    from sklearn.metrics import silhouette_score
+    l2 = (pts.T / np.sqrt((pts ** 2).sum(1))).T
+    sil_r = silhouette_score(l2[keep_r], labels_r)
+    print("consensus_c4: reference (sklearn, %d cores) %.2fs | gpu: l2+density %.3fs kmeans %.3fs median %.3fs silhouette %.3fs" % (
+        os.cpu_count(), t_ref, t1 - t0, t2 - t1, t3 - t2, t4 - t3), flush=True)
+    print("   density rel %.2e keep equal %s labels equal %s medians rel %.2e silhouette %.6f vs %.6f" % (
+        rel(dens, dens_r), np.array_equal(keep, keep_r), np.array_equal(labels, labels_r), rel(med, med_r), sil, sil_r), flush=True)
+    # refit on the c4 data matrix
+    X, _ = normalise(make_counts(68000, 2000, k_true=20))
+    ds = eng.dataset(X)
+    H = np.abs(rng.gamma(0.3, 1.0, size=(K, X.shape[1])))
+    H /= H.sum(1, keepdims=True)
+    for solver in ("cd", "mu"):
+        kw = dict(solver=solver, tol=1e-4, max_iter=1000)
+        ds.refit(H, kw)
+        t0 = time.time()
+        W, it, err = ds.refit(H, kw)
+        t1 = time.time()
+        Wr, itr = nmf_ref.refit(X.astype(np.float64), H, solver)
+        t2 = time.time()
+        print("   refit %s 68k x 2k K=20: gpu %.3fs (%d its) oracle %.1fs (%d its) rel %.2e exact=%s" % (
+            solver, t1 - t0, it, t2 - t1, itr, rel(W, Wr), ds.exact), flush=True)
+
+
+def stage_cd():
+    """The reference's DEFAULT solver (cd) on the c2 workload."""
+    from cnmf_b200.synth import make_counts, normalise, restart_table
+    from oracle import reference_path
+    eng = Engine()
+    X, _ = normalise(make_counts(20000, 2000, k_true=12))
+    rows = restart_table([10], 100)
+    ds = eng.dataset(X)
+    kw = dict(solver="cd", tol=1e-4, max_iter=1000)
+    for rep in range(2):
+        eng.profile(True)
+        t0 = time.time()
+        sp, _, n_iter, err = ds.factorize([r[0] for r in rows], [r[2] for r in rows], kw)
+        dt = time.time() - t0
+        ms, nl, fl = eng.profile_get()
+        print("cd c2 rep %d: %.2fs -> %.1f restarts/s; n_iter mean %.1f max %d; gemm %.0f ms (%.1f algo TF/s)" % (
+            rep, dt, len(rows) / dt, n_iter.mean(), n_iter.max(), ms, fl / ms / 1e9 if ms else 0), flush=True)
+    spr, its, sec = reference_path.factorize(X, [(rows[0][0], rows[0][2]), (rows[1][0], rows[1][2])], "cd")
+    print("   reference cd: %.2fs per restart (%d cores); n_iter %s vs gpu %s; rel-L2 %.2e %.2e" % (
+        sec / 2, os.cpu_count(), its, n_iter[:2].tolist(), rel(sp[0], spr[0]), rel(sp[1], spr[1])), flush=True)
+
+
 def stage_perf():
     eng = Engine()
     rng = np.random.RandomState(0)
@@ -223,3 +297,7 @@ if __name__ == "__main__":
         stage_gemmperf()
     elif st == "c3":
         stage_c3()
+    elif st == "consensus_c4":
+        stage_consensus_c4()
+    elif st == "cd":
+        stage_cd()
