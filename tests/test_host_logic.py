@@ -141,3 +141,68 @@ def test_allgather_spectra_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     for r, o in enumerate(outs):
         assert "RANK%d_OK=True" % r in o, o
+
+
+def _fake_run(tmp_path, ks=(3,), n_iter=4, genes=6):
+    """A cNMF directory with a params table and hand-written per-restart spectra files (no GPU needed)."""
+    obj = cNMF(output_dir=str(tmp_path), name="fake")
+    rp, kw = obj.get_nmf_iter_params(ks=list(ks), n_iter=n_iter, random_state_seed=3, beta_loss="frobenius")
+    obj.save_nmf_iter_params(rp, kw)
+    cols = ["g%d" % i for i in range(genes)]
+    for _, p in rp.iterrows():
+        k, it = int(p["n_components"]), int(p["iter"])
+        df = pd.DataFrame(np.full((k, genes), float(it)), index=np.arange(1, k + 1), columns=cols)
+        save_df_to_npz(df, obj.paths["iter_spectra"] % (k, it))
+    return obj, rp
+
+
+def test_combine_layout_and_missing_files(tmp_path):
+    """combine_nmf (cnmf.py:748-773): row labels iter%d_topic%d, iter-major order, missing-file semantics."""
+    obj, rp = _fake_run(tmp_path)
+    merged = obj.combine_nmf(3)
+    assert list(merged.index[:4]) == ["iter0_topic1", "iter0_topic2", "iter0_topic3", "iter1_topic1"]
+    assert merged.shape == (12, 6) and (merged.iloc[3:6].values == 1.0).all()
+    assert load_df_from_npz(obj.paths["merged_spectra"] % 3).equals(merged)
+    os.remove(obj.paths["iter_spectra"] % (3, 2))
+    with pytest.raises(FileNotFoundError):
+        obj.combine_nmf(3)
+    m2 = obj.combine_nmf(3, skip_missing_files=True)
+    assert m2.shape == (9, 6) and "iter2_topic1" not in m2.index
+    obj.combine(components=3, skip_missing_files=True)      # int / list / None forms of `components` (cnmf.py:474-480)
+    obj.combine(components=[3], skip_missing_files=True)
+
+
+def test_completed_ledger_and_skip(tmp_path):
+    """update_nmf_iter_params / skip_completed_runs bookkeeping (cnmf.py:605-616, 636-651, 729-733)."""
+    obj, rp = _fake_run(tmp_path, n_iter=3)
+    assert not rp["completed"].any()                      # table was built before the files existed
+    obj.update_nmf_iter_params()
+    rp2 = load_df_from_npz(obj.paths["nmf_replicate_parameters"])
+    assert rp2["completed"].all()
+    os.remove(obj.paths["iter_spectra"] % (3, 1))
+    obj.update_nmf_iter_params()
+    rp3 = load_df_from_npz(obj.paths["nmf_replicate_parameters"])
+    assert list(rp3["completed"]) == [True, False, True]
+    todo = list(worker_filter(rp3.index[rp3["completed"] == False], 0, 1))   # noqa: E712
+    assert todo == [1]
+    import warnings
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        obj.get_nmf_iter_params(ks=[3], n_iter=3, random_state_seed=3)
+        assert any("already appear completed" in str(x.message) for x in w)
+
+
+def test_solver_selection_rule():
+    """cnmf.py:629-631: beta_loss='frobenius' -> 'cd' (the default); anything else keeps 'mu'."""
+    import tempfile
+    obj = cNMF(output_dir=tempfile.mkdtemp(), name="x")
+    assert obj.get_nmf_iter_params([3], 1, 1, beta_loss="frobenius")[1]["solver"] == "cd"
+    assert obj.get_nmf_iter_params([3], 1, 1, beta_loss=2.0)[1]["solver"] == "mu"
+    from cnmf_b200.engine import make_params
+    with pytest.raises(NotImplementedError):
+        make_params(dict(solver="mu", beta_loss="kullback-leibler"), 10, 10, "tf32x3")
+    with pytest.raises(NotImplementedError):
+        make_params(dict(solver="cd", init="nndsvd"), 10, 10, "tf32x3")
+    p = make_params(dict(solver="cd", alpha_W=0.5, alpha_H="same", l1_ratio=0.25, tol=1e-3, max_iter=7), 100, 40, "fp32")
+    assert (p.solver, p.max_iter, p.tol) == (1, 7, 1e-3)
+    assert p.l1_reg_W == 40 * 0.5 * 0.25 and p.l2_reg_H == 100 * 0.5 * 0.75      # sklearn _nmf.py:1249-1260
