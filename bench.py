@@ -261,6 +261,34 @@ def run_ours(args, rank, world, local):
 
     if rank != 0:
         return
+
+    # ---------------- informational: the consensus stage (cnmf.py:871-919) on this step's spectra ----------------
+    consensus = None
+    try:
+        from cnmf_b200 import consensus as cs
+        d3 = eng.dataset(Xnp, precision=args.precision)
+        sp, _, _, _ = d3.factorize(ks, seeds, NMF_KW)
+        merged = np.vstack(sp)
+        torch.cuda.synchronize(dev)
+        tc = [time.perf_counter()]
+        S = cs.SpectraMatrix(eng, merged).l2_normalize()
+        dens, _ = S.local_density(int(0.3 * merged.shape[0] / K))
+        tc.append(time.perf_counter())
+        keep = np.where(dens < 0.5)[0]
+        S2 = S.take_rows(keep) if len(keep) < S.R else S
+        labels, labels_t, _, _ = cs.kmeans(S2, K)
+        tc.append(time.perf_counter())
+        med = cs.cluster_medians(S2, labels_t, K)
+        tc.append(time.perf_counter())
+        W, it_refit, _ = d3.refit(med, NMF_KW)
+        tc.append(time.perf_counter())
+        d3.close()
+        consensus = {"R": int(merged.shape[0]), "kept": int(len(keep)), "ms": {
+            "upload_l2_density": 1e3 * (tc[1] - tc[0]), "kmeans_n_init10": 1e3 * (tc[2] - tc[1]),
+            "cluster_median": 1e3 * (tc[3] - tc[2]), "refit_usage": 1e3 * (tc[4] - tc[3])},
+            "refit_n_iter": int(it_refit), "note": "wall clock, outside the timed factorize regions"}
+    except Exception as ex:          # never let the informational block break the bench line
+        consensus = {"error": repr(ex)}
     peak, peak_src = measured_peaks()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     traffic = None
@@ -286,6 +314,7 @@ def run_ours(args, rank, world, local):
                                  "recognised as scaled integer counts -> exact B operand, 2 passes" if passes == 2
                                  else "general real matrix -> 3 passes")},
         "n_iter": {"mean": float(np.mean(n_iter)), "max": int(np.max(n_iter))},
+        "consensus": consensus,
     }
     if world == 1 and not args.no_cpu_baseline:
         from oracle import reference_path

@@ -16,6 +16,10 @@
 
 namespace cnmf {
 
+int launch_rng_init(const uint32_t* seeds_host, const int* ks_host, const int* offs_host, const double* avgs_host, int R,
+                    int n_samples, int n_features, float* Wt, long long ldW, float* H, long long ldH, cnmf_handle_s* h,
+                    cudaStream_t s);
+
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
@@ -461,6 +465,20 @@ int cnmf_factorize(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, const
   using clk = std::chrono::steady_clock;
   auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
   h->t_rng_ms = h->t_h2d_ms = h->t_solve_ms = h->t_d2h_ms = 0;
+  if ((p->reserved & 1) == 0) {
+    // ---- device RNG (default): the same legacy MT19937 / polar-gauss stream, generated in place on the GPU
+    auto t_rng = clk::now();
+    const double mean_d = d->sum / ((double)d->n_rows * (double)d->n_cols);
+    std::vector<double> avgs(n_restarts);
+    for (int r = 0; r < n_restarts; ++r) avgs[r] = std::sqrt(mean_d / ks[r]);
+    CNMF_CUDA_CHECK(cudaMemsetAsync(fb.Fr, 0, (size_t)SK * d->ld_r * 4, s));
+    CNMF_CUDA_CHECK(cudaMemsetAsync(fb.Fc, 0, (size_t)SK * d->ld_c * 4, s));
+    CNMF_TRY(launch_rng_init(seeds, ks.data(), off.data(), avgs.data(), n_restarts, d->n_rows, d->n_cols, fb.Fr, d->ld_r,
+                             fb.Fc, d->ld_c, h, s));
+    CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+    h->t_rng_ms = ms_since(t_rng);
+    return run_and_download(d, ks, SK, fb, *p, spectra_host, usages_host, n_iter_host, err_host, s);
+  }
   // host RNG (bit-exact numpy legacy stream) in groups through a pinned staging buffer
   const double mean = d->sum / ((double)d->n_rows * (double)d->n_cols);
   const size_t group_budget = (size_t)256 << 20;   // bytes of W^T staged per group
@@ -573,6 +591,30 @@ int cnmf_factorize_dev(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, c
     if (n_iter_host) n_iter_host[r] = io.n_iter[r];
     if (err_host) err_host[r] = io.err[r];
   }
+  return 0;
+}
+
+int cnmf_random_init_dev(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, const uint32_t* seeds, float* Wt_dev,
+                         float* H_dev, void* stream) {
+  CNMF_REQUIRE(d && n_restarts > 0 && ks_in && seeds && Wt_dev && H_dev, "random_init_dev: bad arguments");
+  cnmf_handle_s* h = d->h;
+  cudaStream_t s = as_stream(stream);
+  CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  std::vector<int> ks(ks_in, ks_in + n_restarts), off(n_restarts);
+  std::vector<double> avgs(n_restarts);
+  const double mean_d = d->sum / ((double)d->n_rows * (double)d->n_cols);
+  int SK = 0;
+  for (int r = 0; r < n_restarts; ++r) {
+    CNMF_REQUIRE(ks[r] >= 1 && ks[r] <= KMAX, "random_init_dev: n_components must be in [1, 32]");
+    off[r] = SK;
+    SK += ks[r];
+    avgs[r] = std::sqrt(mean_d / ks[r]);
+  }
+  CNMF_CUDA_CHECK(cudaMemsetAsync(Wt_dev, 0, (size_t)SK * d->ld_r * 4, s));
+  CNMF_CUDA_CHECK(cudaMemsetAsync(H_dev, 0, (size_t)SK * d->ld_c * 4, s));
+  CNMF_TRY(launch_rng_init(seeds, ks.data(), off.data(), avgs.data(), n_restarts, d->n_rows, d->n_cols, Wt_dev, d->ld_r,
+                           H_dev, d->ld_c, h, s));
+  CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
   return 0;
 }
 

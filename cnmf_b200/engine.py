@@ -45,6 +45,10 @@ def make_params(nmf_kwargs, n_samples, n_features, precision):
     p = NmfParams()
     p.solver = SOLVER_MU if solver == "mu" else SOLVER_CD
     p.precision = _params_precision(precision_code(precision))
+    rng = nmf_kwargs.get("rng", "device")
+    if rng not in ("device", "host"):
+        raise ValueError("rng must be 'device' or 'host'")
+    p.reserved = 1 if rng == "host" else 0          # bit 0: draw the random init on the host
     p.max_iter = int(nmf_kwargs.get("max_iter", 1000))
     p.tol = float(nmf_kwargs.get("tol", 1e-4))
     p.l1_reg_W = n_features * alpha_W * l1_ratio
@@ -147,6 +151,13 @@ class Dataset:
         a, b = ctypes.c_int(), ctypes.c_int()
         check(self.lib.cnmf_dataset_ld(self._d, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
+
+    def random_init_dev(self, ks, seeds, Wt_ptr, H_ptr):
+        """sklearn's random init for every (k, seed), generated on the GPU into packed padded device buffers."""
+        ks = np.ascontiguousarray(ks, dtype=np.int32)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        check(self.lib.cnmf_random_init_dev(self._d, len(ks), ptr(ks), ptr(seeds), ctypes.c_void_p(Wt_ptr),
+                                            ctypes.c_void_p(H_ptr), None))
 
     def factorize_dev(self, ks, Wt0_ptr, H0_ptr, out_ptr, nmf_kwargs):
         """Device-resident factorize: raw device pointers (e.g. torch.Tensor.data_ptr()) of the packed,

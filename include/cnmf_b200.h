@@ -45,7 +45,7 @@ typedef struct cnmf_nmf_params {
   int32_t solver;        /* CNMF_SOLVER_* */
   int32_t precision;     /* CNMF_PRECISION_* */
   int32_t max_iter;      /* 'max_iter' (cnmf.py:625) */
-  int32_t reserved;
+  int32_t reserved;      /* flags: bit 0 = draw the random init on the host (bit-exact numpy stream) instead of the GPU */
   double tol;            /* 'tol' (cnmf.py:624) */
   double l1_reg_W, l2_reg_W, l1_reg_H, l2_reg_H;
 } cnmf_nmf_params;
@@ -95,6 +95,13 @@ int cnmf_dataset_col_stats(cnmf_dataset_t d, double* mean_host, double* var_host
  * Wt (k x n_samples, row stride ldW).  Pure host code (no CUDA). */
 int cnmf_random_init_host(uint32_t seed, double avg, int n_samples, int n_features, int k,
                           float* Wt, long long ldW, float* H, long long ldH);
+
+/* Same stream generated ON THE DEVICE (one thread block per restart; see csrc/rng_device.cu for the one
+ * caveat: log() may differ from glibc in the last fp64 bit, visible in ~1 fp32 value per 10^8) into packed,
+ * padded device buffers: Wt_dev (sum ks) x ld_rows, H_dev (sum ks) x ld_cols (cnmf_dataset_ld), avg =
+ * sqrt(mean(X) / k) as sklearn.  This is what cnmf_factorize uses unless params.reserved bit 0 is set. */
+int cnmf_random_init_dev(cnmf_dataset_t d, int n_restarts, const int32_t* ks, const uint32_t* seeds, float* Wt_dev,
+                         float* H_dev, void* stream);
 
 /* ---- batched factorize: replaces the restart loop of cNMF.factorize ---------------- */
 /* For r in [0, n_restarts): one NMF of the dataset with n_components = ks[r] and

@@ -64,6 +64,43 @@ def test_gemm_properties_full_size(eng):
     assert rel(C1[:3], ref_row) < TOL_GEMM
 
 
+# ------------------------------------------------------------------------------------ random init
+def test_device_rng_reproduces_numpy_legacy_stream(eng):
+    """The on-device generator (MT19937 + polar gauss, one block per restart) against the host generator, which
+    is bit-exact with numpy (tests/test_host_logic.py).  Only log() may differ from glibc in its last fp64 bit:
+    at most a handful of fp32 values per million may differ, and then by one ulp."""
+    import torch
+    from cnmf_b200 import _lib
+    g = load_golden("sim_mu")
+    X = g["X"]
+    ds = eng.dataset(X)
+    n, G = ds.shape
+    ks = np.array([3, 7, 32, 1, 10], np.int32)
+    seeds = np.array([1, 2 ** 31 - 2, 123456789, 42, 59886188], np.uint32)
+    ld_r, ld_c = ds.ld()
+    SK = int(ks.sum())
+    Wt = torch.full((SK, ld_r), 7.0, dtype=torch.float32, device="cuda:0")
+    H = torch.full((SK, ld_c), 7.0, dtype=torch.float32, device="cuda:0")
+    ds.random_init_dev(ks, seeds, Wt.data_ptr(), H.data_ptr())
+    Wd, Hd = Wt.cpu().numpy(), H.cpu().numpy()
+    s, _ = ds.sums()
+    mean = s / (n * float(G))
+    lib = _lib.load()
+    Wh = np.zeros((SK, ld_r), np.float32)
+    Hh = np.zeros((SK, ld_c), np.float32)
+    o = 0
+    for k, seed in zip(ks, seeds):
+        _lib.check(lib.cnmf_random_init_host(int(seed), float(np.sqrt(mean / k)), n, G, int(k),
+                                             _lib.ptr(Wh[o:o + k]), ld_r, _lib.ptr(Hh[o:o + k]), ld_c))
+        o += k
+    for dev, host in ((Wd, Wh), (Hd, Hh)):
+        assert not dev[:, -1].any() or dev.shape[1] in (n, G)          # padding columns are zero
+        diff = dev != host
+        assert diff.sum() <= max(2, int(2e-6 * dev.size)), int(diff.sum())
+        if diff.any():
+            assert (np.abs(dev[diff] - host[diff]) <= np.abs(host[diff]) * 2.0 ** -22).all()
+
+
 # ------------------------------------------------------------------------------------ factorize
 def test_exact_count_detection(eng):
     """HVG-normalised counts (counts / std) and TPM (counts * 1e6 / total) are recognised as scaled integers and
@@ -80,15 +117,17 @@ def test_exact_count_detection(eng):
     assert not eng.dataset(big).exact
 
 
-@pytest.mark.parametrize("precision", ["tf32x3", "tf32x3-general", "fp32"])
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32x3-hostrng", "tf32x3-general", "fp32"])
 @pytest.mark.parametrize("tag", ["sim_mu", "sim_cd"])
 def test_factorize_matches_reference_fixture(eng, precision, tag):
     """Every restart of the reference's own factorize() run (fixture): same n_iter, spectra within tolerance."""
     from oracle import nmf_ref
     g = load_golden(tag)
+    rng = "host" if precision.endswith("-hostrng") else "device"
+    precision = precision.replace("-hostrng", "")
     ds = eng.dataset(g["X"], precision=precision)
     kw = dict(solver=g["solver"], tol=1e-4, max_iter=1000, alpha_W=0.0, alpha_H=0.0, l1_ratio=0.0,
-              beta_loss=2.0 if g["solver"] == "mu" else "frobenius", init="random")
+              beta_loss=2.0 if g["solver"] == "mu" else "frobenius", init="random", rng=rng)
     table = g["table"]
     sp, us, n_iter, err = ds.factorize(table[:, 0], table[:, 2], kw, return_usages=True)
     errs = []
