@@ -21,7 +21,8 @@
 // Accumulation accuracy.  The tensor core adds each MMA result into the TMEM accumulator with
 // truncation: measured on B200, a chain of n MMAs on non-negative data is biased low by about
 // n * 3e-8 relative (2.3e-5 at K = 2048), which is far outside the 1e-4 parity budget of an NMF
-// run.  So TMEM only ever holds SHORT chains (`chain_kb` k-blocks = 12 * chain_kb MMAs, default 1):
+// run.  So TMEM only ever holds SHORT chains (`chain_kb` k-blocks, at most 16 MMAs: 1 k-block of 12 MMAs
+// in the general 3-pass form, 2 k-blocks of 8 MMAs in the exact-B 2-pass form):
 // the MMA warp ping-pongs between two TMEM buffers, and the eight accumulate warps drain each
 // finished chain into round-to-nearest fp32 register accumulators (128 per thread) while the next
 // chain is being issued.  Result: ~4e-7 relative, the same class as an FFMA fp32 GEMM.
@@ -405,14 +406,16 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   }
   const int items = m_tiles * n_tiles * splits;
   const int grid = items < sms ? items : sms;
+  // k-blocks per TMEM accumulation chain: at most 16 MMAs between drains (general: 1 k-block = 12 MMAs,
+  // exact-B: 2 k-blocks = 16 MMAs; with 8 MMAs per chain the drain, not the tensor pipe, paced the kernel)
   int chain_kb = g.chain_kb;
   if (chain_kb <= 0) {
     static const int env_chain = [] {
-      const char* e = std::getenv("CNMF_CHAIN_KB");      // tuning knob; default 1 (12 MMAs per TMEM chain)
-      const int v = e ? std::atoi(e) : 1;
-      return v >= 1 ? v : 1;
+      const char* e = std::getenv("CNMF_CHAIN_KB");      // tuning knob
+      const int v = e ? std::atoi(e) : 0;
+      return v >= 1 ? v : 0;
     }();
-    chain_kb = env_chain;
+    chain_kb = env_chain > 0 ? env_chain : (BEXACT ? 2 : 1);
   }
   kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(mAh, mAl, mBh, mBl, g.C, g.M, g.N, g.ldc, g.c_split_stride,
                                                     m_tiles, n_tiles, splits, total_kb, kb_per_split,
