@@ -214,7 +214,8 @@ __device__ __forceinline__ void store_elem(const FactorView& f, long long e, flo
 
 template <int KP>
 __device__ __forceinline__ double mu_body(const FactorView& f, const float* __restrict__ NUM, int nsplit, long long sstride,
-                                          const float* G, int K, int o, float l1, float l2, int col_begin, int col_end) {
+                                          const float* G, int K, int o, float l1, float l2, int col_begin, int col_end,
+                                          bool want_cross) {
   const volatile float4* Gv = reinterpret_cast<const volatile float4*>(G);
   double cross = 0.0;
   for (int col = col_begin + threadIdx.x; col < col_end; col += UPD_THREADS) {
@@ -238,7 +239,7 @@ __device__ __forceinline__ double mu_body(const FactorView& f, const float* __re
         if (den == 0.f) den = EPSILON_F32;
         const float fn = fv[c] * (nv[c] / den);
         store_elem(f, (long long)(o + c) * f.ld + col, fn, pscale);
-        cross += (double)nv[c] * (double)fn;
+        if (want_cross) cross += (double)nv[c] * (double)fn;
       }
     }
   }
@@ -304,7 +305,7 @@ mu_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long l
   const int col_end = min(f.n, col_begin + f.cpb);
   double cross = 0.0;
   CNMF_KP_SWITCH(K, KPMAX, (load_gram_smem(G, gram, r, K, KP, 0.f),
-                            cross = mu_body<KP>(f, NUM, nsplit, sstride, G, K, o, l1, l2, col_begin, col_end)));
+                            cross = mu_body<KP>(f, NUM, nsplit, sstride, G, K, o, l1, l2, col_begin, col_end, cross_partial != nullptr)));
   if (cross_partial) {
     cross = block_sum(cross, red);
     if (threadIdx.x == 0) cross_partial[(long long)r * gridDim.x + blockIdx.x] = cross;

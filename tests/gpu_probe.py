@@ -165,6 +165,34 @@ def stage_consensus_c4():
             solver, t1 - t0, it, t2 - t1, itr, rel(W, Wr), ds.exact), flush=True)
 
 
+def stage_big():
+    """BASELINE configs[3] and [4] factorize sizes on ONE GPU (capacity / sanity: no oracle at this size):
+    c4 68k x 2k, K=20 x 200 restarts; c5 200k x 5k, K=30 x 200 restarts."""
+    from cnmf_b200.synth import make_counts, normalise, restart_table
+    eng = Engine()
+    for name, (n, g, k, nrest) in {"c4": (68000, 2000, 20, 200), "c5": (200000, 5000, 30, 200)}.items():
+        t0 = time.time()
+        X, _ = normalise(make_counts(n, g, k_true=max(12, k // 2)))
+        rows = restart_table([k], nrest)
+        t1 = time.time()
+        ds = eng.dataset(X)
+        eng.profile(True)
+        t2 = time.time()
+        sp, _, n_iter, err = ds.factorize([r[0] for r in rows], [r[2] for r in rows], dict(solver="mu", tol=1e-4, max_iter=1000))
+        t3 = time.time()
+        ms, nl, fl = eng.profile_get()
+        import torch
+        free, tot = torch.cuda.mem_get_info()
+        normX = np.sqrt(float((X.astype(np.float64) ** 2).sum()))
+        ok = bool(np.isfinite(err).all() and (err < normX).all() and all(np.isfinite(s).all() and (s >= 0).all() for s in sp))
+        print("%s %s exact=%s: data %.0fs upload %.1fs factorize %.1fs -> %.1f restarts/s; n_iter mean %.0f max %d; gemm %.0f ms %.0f algo TF/s; "
+              "err/||X|| in [%.4f, %.4f]; sane=%s; HBM used %.1f GB" % (
+                  name, X.shape, ds.exact, t1 - t0, t2 - t1, t3 - t2, nrest / (t3 - t2), n_iter.mean(), n_iter.max(), ms,
+                  fl / ms / 1e9 if ms else 0, err.min() / normX, err.max() / normX, ok, (tot - free) / 2 ** 30), flush=True)
+        ds.close()
+        del X
+
+
 def stage_cd():
     """The reference's DEFAULT solver (cd) on the c2 workload."""
     from cnmf_b200.synth import make_counts, normalise, restart_table
@@ -301,3 +329,5 @@ if __name__ == "__main__":
         stage_consensus_c4()
     elif st == "cd":
         stage_cd()
+    elif st == "big":
+        stage_big()
