@@ -16,12 +16,18 @@ struct GemmArgs {
   int splits;                 // requested split-K factor
   int splits_effective;       // gemm_effective_splits(Kd, splits): what the kernel will actually write
   int chain_kb;               // tf32x3: k-blocks (of 32) accumulated in TMEM before draining to registers (0 -> 1)
+  int bn;                     // tf32x3: tile width (UMMA N); 0 = choose from (M, N, Kd, splits)
   int b_exact;                // tf32x3: B_hi holds B exactly (tf32-representable values); B_lo unused -> 2 passes
   const float* out_col_scale; // optional: C[:, n] *= out_col_scale[n] (length >= ldc, 16-byte aligned, zero padded)
 };
 
 // number of non-empty split-K slices for a reduction length Kd (k-blocks of 32)
 int gemm_effective_splits(int Kd, int splits);
+
+// Joint choice of the split-K factor and the tile width for the tcgen05 kernel: minimises
+// (waves of the persistent grid) x (tile cost) x (k-blocks per item + pipeline fill), with a mild penalty per
+// extra split-K slice (its partial output is written and re-read by the update kernel).
+void gemm_plan(int M, int N, int Kd, int sm_count, int* splits, int* bn);
 
 // tcgen05 / TMEM / TMA path (gemm_tf32x3.cu)
 int gemm_tf32x3(const GemmArgs& g, cudaStream_t stream);

@@ -30,6 +30,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 
@@ -367,23 +368,23 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   CNMF_CUDA_CHECK(cudaGetDevice(&dev));
   CNMF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int m_tiles = (g.M + BM - 1) / BM;
-  // Tile width: the UMMA N is a runtime value (multiple of 16, <= BN).  With more than one tile column,
-  // pick among {256..192} the width that minimises (waves of the persistent grid) x (tile cost), where the
-  // tile cost bn + 64 charges the per-tile A-operand traffic and pipeline fill that do not shrink with bn
-  // (a pure waves x bn model picked 16-column tiles: 7x slower).  A single tile column uses just N rounded up.
-  int bn = BN;
-  {
+  // Tile width: the UMMA N is a runtime value (multiple of 16, <= BN), normally supplied by gemm_plan().
+  int bn = g.bn;
+  if (bn <= 0 || bn > BN || bn % 16 != 0) {
     const int sp = gemm_effective_splits(g.Kd, g.splits);
     if (g.N <= BN) {
       bn = ((g.N + 15) / 16) * 16;
     } else {
       long long best = -1;
+      bn = BN;
       for (int cand = BN; cand >= 192; cand -= 16) {
         const long long tiles = (long long)m_tiles * ((g.N + cand - 1) / cand) * sp;
         const long long cost = ((tiles + sms - 1) / sms) * (cand + 64);
         if (best < 0 || cost < best) { best = cost; bn = cand; }
       }
     }
+  }
+  {
     static const int env_bn = [] { const char* e = std::getenv("CNMF_GEMM_BN"); return e ? std::atoi(e) : 0; }();
     if (env_bn >= 16 && env_bn <= BN && env_bn % 16 == 0) bn = env_bn;
   }
@@ -425,6 +426,31 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
 }
 
 }  // namespace
+
+void gemm_plan(int M, int N, int Kd, int sm_count, int* splits_out, int* bn_out) {
+  const int m_tiles = (M + BM - 1) / BM;
+  const int total_kb = (Kd + BK - 1) / BK;
+  const int max_splits = std::max(1, std::min(32, total_kb / 8));
+  double best = -1.0;
+  int best_s = 1, best_bn = 256;
+  const int bn_lo = N <= 256 ? ((N + 15) / 16) * 16 : 192;
+  const int bn_hi = N <= 256 ? bn_lo : 256;
+  for (int s = 1; s <= max_splits; ++s) {
+    const int se = gemm_effective_splits(Kd, s);
+    if (se != s) continue;                                   // skip factors that collapse to a smaller one
+    const int kbps = (total_kb + s - 1) / s;
+    for (int bn = bn_hi; bn >= bn_lo; bn -= 16) {
+      const long long items = (long long)m_tiles * ((N + bn - 1) / bn) * s;
+      const long long waves = (items + sm_count - 1) / sm_count;
+      // tile cost bn + 64: per-tile A traffic / fill that does not shrink with bn; + 6 k-blocks of pipeline
+      // fill and epilogue per item; 2 % per extra slice for the partial-output traffic
+      const double cost = (double)waves * (bn + 64) * (kbps + 6) * (1.0 + 0.02 * (s - 1));
+      if (best < 0 || cost < best) { best = cost; best_s = s; best_bn = bn; }
+    }
+  }
+  *splits_out = best_s;
+  *bn_out = best_bn;
+}
 
 int gemm_effective_splits(int Kd, int splits) {
   const int total_kb = (Kd + BK - 1) / BK;

@@ -53,6 +53,7 @@ int pick_splits(int sm_count, int M, int N, int Kd) {
 
 struct GemmPlan {
   int splits;
+  int bn;                   // tile width for the tcgen05 kernel (0 = let the launcher choose)
   long long split_stride;   // elements
 };
 
@@ -67,6 +68,7 @@ int run_gemm(cnmf_handle_s* h, int precision, const float* A, const float* A_hi,
   g.c_split_stride = plan.split_stride;
   g.splits = plan.splits;
   g.splits_effective = plan.splits;
+  g.bn = plan.bn;
   h->launches += 1;
   const int slot = h->prof_begin(s, 2.0 * (double)g.M * (double)g.N * (double)g.Kd);
   int rc;
@@ -124,17 +126,27 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   int* d_meta = static_cast<int*>(h->dev_buf("solve.meta", sizeof(int) * 8 * R0));
   double* d_state = static_cast<double*>(h->dev_buf("solve.state", sizeof(double) * 8 * R0));
   double* d_gram = static_cast<double*>(h->dev_buf("solve.gram", sizeof(double) * 2 * R0 * KMAX * KMAX));
-  double* d_gram_part =
-      static_cast<double*>(h->dev_buf("solve.gram_part", sizeof(double) * (size_t)R0 * gchunks_max * kp * kp));
+  // per-chunk Gram partials of each factor (consumed directly by the update kernels; finalised K x K
+  // matrices are only formed when a convergence check needs them)
+  const size_t gpart_elems = (size_t)R0 * std::max(gchunks_max, std::max((v.n_r + 1023) / 1024, (v.n_c + 1023) / 1024)) * kp * kp;
+  double* d_gram_part = static_cast<double*>(h->dev_buf("solve.gram_part", sizeof(double) * 2 * gpart_elems));
   double* d_scal_part = static_cast<double*>(h->dev_buf("solve.scal_part", sizeof(double) * 2 * (size_t)R0 * chunks_max));
   if (!d_meta || !d_state || !d_gram || !d_gram_part || !d_scal_part) return -2;
 
   GemmPlan plan_r, plan_c;   // plan_r: NUM_r = Fc * B_rows^T (reduce over n_c); plan_c: NUM_c = Fr * B_cols^T
   float *NUMr = nullptr, *NUMc = nullptr;
+  auto plan_one = [&](int sk, int n, int kd, GemmPlan* pl) {
+    if (tf32) {
+      gemm_plan(sk, n, kd, h->sm_count, &pl->splits, &pl->bn);
+    } else {
+      pl->splits = pick_splits(h->sm_count, sk, n, kd);
+      pl->bn = 0;
+    }
+  };
   auto plan_gemms = [&]() -> int {
-    plan_r.splits = pick_splits(h->sm_count, SK, v.n_r, v.n_c);
+    plan_one(SK, v.n_r, v.n_c, &plan_r);
     plan_r.split_stride = (long long)SK * v.ld_r;
-    plan_c.splits = pick_splits(h->sm_count, SK, v.n_c, v.n_r);
+    plan_one(SK, v.n_c, v.n_r, &plan_c);
     plan_c.split_stride = (long long)SK * v.ld_c;
     return 0;
   };
@@ -142,10 +154,12 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   // size the product buffers for the worst case over all compaction states (splits <= 32 but bounded by SK0 rows)
   {
     size_t need_r = 0, need_c = 0;
-    for (int sk = SK0; sk >= 1; sk = (sk > 128 ? sk - 128 : 0)) {
-      need_r = std::max(need_r, (size_t)pick_splits(h->sm_count, sk, v.n_r, v.n_c) * (size_t)sk * v.ld_r);
-      need_c = std::max(need_c, (size_t)pick_splits(h->sm_count, sk, v.n_c, v.n_r) * (size_t)sk * v.ld_c);
-      if (sk <= 128) break;
+    for (int sk = SK0; sk >= 1; sk -= (io.update_cols ? 1 : SK0)) {   // every SK a compaction can produce
+      GemmPlan a, b2;
+      plan_one(sk, v.n_r, v.n_c, &a);
+      plan_one(sk, v.n_c, v.n_r, &b2);
+      need_r = std::max(need_r, (size_t)a.splits * (size_t)sk * v.ld_r);
+      need_c = std::max(need_c, (size_t)b2.splits * (size_t)sk * v.ld_c);
     }
     need_r = std::max(need_r, (size_t)plan_r.splits * (size_t)plan_r.split_stride);
     need_c = std::max(need_c, (size_t)plan_c.splits * (size_t)plan_c.split_stride);
@@ -178,6 +192,9 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   double* d_gramC = d_gram + (size_t)R0 * KMAX * KMAX; // Gram of Fc (e.g. H H^T), by rid
   double* d_scalA = d_scal_part;
   double* d_scalB = d_scal_part + (size_t)R0 * chunks_max;
+  double* d_gpartR = d_gram_part;                      // partials of Gram(Fr)
+  double* d_gpartC = d_gram_part + gpart_elems;        // partials of Gram(Fc)
+  int gchR = 1, gchC = 1;                              // chunk counts of the partials currently stored
 
   // working factor arrays (start in the caller's buffers; compaction ping-pongs to "solve.alt.*")
   float *wFr = io.Fr, *wFr_hi = io.Fr_hi, *wFr_lo = io.Fr_lo, *wFc = io.Fc, *wFc_hi = io.Fc_hi, *wFc_lo = io.Fc_lo;
@@ -194,10 +211,19 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     if (!io.update_cols) { f.F_hi = nullptr; f.F_lo = nullptr; }   // never rewritten
     return f;
   };
-  auto gram_of = [&](const FactorView& f, double* gram_out, int /*scalar chunks, unused*/) -> int {
+  // side: 0 = row factor Fr, 1 = column factor Fc.  Writes the per-chunk partials only.
+  auto gram_of = [&](const FactorView& f, double* /*unused*/, int side_is_c) -> int {
+    h->launches += 1;
+    double* part = side_is_c ? d_gpartC : d_gpartR;
+    (side_is_c ? gchC : gchR) = gram_chunks(f);
+    return launch_gram_partial(f, bm(), part, s);
+  };
+  auto gref_R = [&]() { return GramRef{d_gpartR, gchR, kp * kp}; };
+  auto gref_C = [&]() { return GramRef{d_gpartC, gchC, kp * kp}; };
+  auto finalize_grams = [&](const BatchMeta& m) -> int {   // K x K matrices for the error / check kernels
     h->launches += 2;
-    CNMF_TRY(launch_gram_partial(f, bm(), d_gram_part, s));
-    return launch_finalize(d_gram_part, gram_out, nullptr, nullptr, gram_chunks(f), bm(), s);
+    CNMF_TRY(launch_finalize(d_gpartR, d_gramR, nullptr, nullptr, gchR, m, s));
+    return launch_finalize(d_gpartC, d_gramC, nullptr, nullptr, gchC, m, s);
   };
   // Overlapped form (MU iteration): the Gram of a freshly updated factor is not needed by the GEMM that follows
   // the update, only by the update after it.  Run it on the auxiliary stream in one-warp blocks (they fit beside
@@ -207,19 +233,13 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   static const bool overlap_env = [] { const char* e = std::getenv("CNMF_OVERLAP"); return e && e[0] == '1'; }();
   const bool overlap = overlap_env && mu && io.update_cols && h->aux && h->ev_upd && h->ev_gram;
   const int gcpb_small = 1024;
-  const int gchunks_small = std::max((v.n_r + gcpb_small - 1) / gcpb_small, (v.n_c + gcpb_small - 1) / gcpb_small);
-  double* d_gram_part2 = nullptr;
-  if (overlap) {
-    d_gram_part2 = static_cast<double*>(h->dev_buf("solve.gram_part_aux", sizeof(double) * (size_t)R0 * gchunks_small * kp * kp));
-    if (!d_gram_part2) return -2;
-  }
-  auto gram_async = [&](FactorView f, double* gram_out) -> int {     // enqueue on aux after everything on s so far
+  auto gram_async = [&](FactorView f, double* /*unused*/, int side_is_c) -> int {   // enqueue on aux after everything on s so far
     f.gcpb = gcpb_small;
     CNMF_CUDA_CHECK(cudaEventRecord(h->ev_upd, s));
     CNMF_CUDA_CHECK(cudaStreamWaitEvent(h->aux, h->ev_upd, 0));
-    h->launches += 2;
-    CNMF_TRY(launch_gram_partial(f, bm(), d_gram_part2, h->aux, true));
-    CNMF_TRY(launch_finalize(d_gram_part2, gram_out, nullptr, nullptr, gram_chunks(f), bm(), h->aux));
+    h->launches += 1;
+    (side_is_c ? gchC : gchR) = gram_chunks(f);
+    CNMF_TRY(launch_gram_partial(f, bm(), side_is_c ? d_gpartC : d_gpartR, h->aux, true));
     CNMF_CUDA_CHECK(cudaEventRecord(h->ev_gram, h->aux));
     return 0;
   };
@@ -273,10 +293,11 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     CNMF_CUDA_CHECK(cudaMemsetAsync(d_zero, 0, sizeof(int) * 2 * R0, s));
     BatchMeta bm0{d_off, d_k, d_rid, d_zero, R, kp};
     h->launches += 7;
-    CNMF_TRY(launch_gram_partial(fr(), bm0, d_gram_part, s));
-    CNMF_TRY(launch_finalize(d_gram_part, d_gramR, nullptr, nullptr, gram_chunks(fr()), bm0, s));
-    CNMF_TRY(launch_gram_partial(fc(), bm0, d_gram_part, s));
-    CNMF_TRY(launch_finalize(d_gram_part, d_gramC, nullptr, nullptr, gram_chunks(fc()), bm0, s));
+    gchR = gram_chunks(fr());
+    gchC = gram_chunks(fc());
+    CNMF_TRY(launch_gram_partial(fr(), bm0, d_gpartR, s));
+    CNMF_TRY(launch_gram_partial(fc(), bm0, d_gpartC, s));
+    CNMF_TRY(finalize_grams(bm0));
     if (io.update_cols) {
       CNMF_TRY(launch_cross(fc(), NUMc, plan_c.splits, plan_c.split_stride, bm0, d_scalB, s));
       CNMF_TRY(launch_finalize(nullptr, nullptr, d_scalB, d_crossB, chunks_c, bm0, s));
@@ -363,8 +384,9 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
 
   if (mu) {
     // ---------------- multiplicative update (sklearn _nmf.py:726-888) ----------------
-    CNMF_TRY(gram_of(fc(), d_gramC, chunks_c));
-    CNMF_TRY(gram_of(fr(), d_gramR, chunks_r));
+    CNMF_TRY(gram_of(fc(), d_gramC, 1));
+    CNMF_TRY(gram_of(fr(), d_gramR, 0));
+    CNMF_TRY(finalize_grams(bm()));
     if (io.update_cols) {
       CNMF_TRY(gemm_cols());
       h->launches += 1;
@@ -383,21 +405,21 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
       if (io.update_cols) CNMF_TRY(gemm_rows());                    // overlaps gram(Fc) of the previous iteration
       if (overlap && it > 1) CNMF_TRY(gram_join());                 // update of Fr needs Gram(Fc)
       h->launches += 1;
-      CNMF_TRY(launch_mu_update(fr(), NUMr, plan_r.splits, plan_r.split_stride, d_gramC, bm(), l1W, l2W,
+      CNMF_TRY(launch_mu_update(fr(), NUMr, plan_r.splits, plan_r.split_stride, gref_C(), bm(), l1W, l2W,
                                 io.update_cols ? nullptr : d_scalA, s));
       if (io.update_cols) {
         if (overlap) {
-          CNMF_TRY(gram_async(fr(), d_gramR));                      // runs under gemm_cols
+          CNMF_TRY(gram_async(fr(), d_gramR, 0));                   // runs under gemm_cols
           CNMF_TRY(gemm_cols());
           CNMF_TRY(gram_join());                                    // update of Fc needs Gram(Fr)
         } else {
-          CNMF_TRY(gram_of(fr(), d_gramR, chunks_r));
+          CNMF_TRY(gram_of(fr(), d_gramR, 0));
           CNMF_TRY(gemm_cols());
         }
         h->launches += 1;
-        CNMF_TRY(launch_mu_update(fc(), NUMc, plan_c.splits, plan_c.split_stride, d_gramR, bm(), l1H, l2H, d_scalB, s));
-        if (overlap) CNMF_TRY(gram_async(fc(), d_gramC));           // runs under the next gemm_rows
-        else CNMF_TRY(gram_of(fc(), d_gramC, chunks_c));
+        CNMF_TRY(launch_mu_update(fc(), NUMc, plan_c.splits, plan_c.split_stride, gref_R(), bm(), l1H, l2H, d_scalB, s));
+        if (overlap) CNMF_TRY(gram_async(fc(), d_gramC, 1));        // runs under the next gemm_rows
+        else CNMF_TRY(gram_of(fc(), d_gramC, 1));
       }
       const bool check = (p.tol > 0 && it % 10 == 0) || it == p.max_iter;
       if (check) {
@@ -405,9 +427,10 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
         if (io.update_cols) {
           CNMF_TRY(finalize_scal(d_scalB, d_crossB, chunks_c));
         } else {
-          CNMF_TRY(gram_of(fr(), d_gramR, chunks_r));
+          CNMF_TRY(gram_of(fr(), d_gramR, 0));
           CNMF_TRY(finalize_scal(d_scalA, d_crossB, chunks_r));
         }
+        CNMF_TRY(finalize_grams(bm()));
         h->launches += 1;
         // at it == max_iter with it % 10 != 0 sklearn does not test; tol = -1 makes the test never fire
         const double tol_eff = (p.tol > 0 && it % 10 == 0) ? p.tol : -1.0;
@@ -423,17 +446,17 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     const int poll_every = 4;
     for (it = 1; it <= p.max_iter; ++it) {
       if (io.update_cols || it == 1) {
-        CNMF_TRY(gram_of(fc(), d_gramC, chunks_c));
+        CNMF_TRY(gram_of(fc(), d_gramC, 1));
         CNMF_TRY(gemm_rows());
       }
       h->launches += 1;
-      CNMF_TRY(launch_cd_update(fr(), NUMr, plan_r.splits, plan_r.split_stride, d_gramC, bm(), l1W, l2W, d_scalA, s));
+      CNMF_TRY(launch_cd_update(fr(), NUMr, plan_r.splits, plan_r.split_stride, gref_C(), bm(), l1W, l2W, d_scalA, s));
       CNMF_TRY(finalize_scal(d_scalA, d_crossA, chunks_r));
       if (io.update_cols) {
-        CNMF_TRY(gram_of(fr(), d_gramR, chunks_r));
+        CNMF_TRY(gram_of(fr(), d_gramR, 0));
         CNMF_TRY(gemm_cols());
         h->launches += 1;
-        CNMF_TRY(launch_cd_update(fc(), NUMc, plan_c.splits, plan_c.split_stride, d_gramR, bm(), l1H, l2H, d_scalB, s));
+        CNMF_TRY(launch_cd_update(fc(), NUMc, plan_c.splits, plan_c.split_stride, gref_R(), bm(), l1H, l2H, d_scalB, s));
         CNMF_TRY(finalize_scal(d_scalB, d_crossB, chunks_c));
       }
       h->launches += 1;

@@ -177,11 +177,15 @@ __global__ void sums_final_kernel(const double* __restrict__ part, int nblocks, 
 // kernel's register budget: 80 registers / 3 blocks per SM for KPMAX = 16.  The K x K Gram is re-read
 // from shared memory for every column through a volatile pointer (broadcast LDS.128) instead of being
 // hoisted into ~256 registers (that version ran at ~1 TB/s).
-__device__ __forceinline__ void load_gram_smem(float* G, const double* __restrict__ gram, int r, int K, int KP,
-                                               float diag_add) {
+__device__ __forceinline__ void load_gram_smem(float* G, const GramRef& gram, int r, int K, int KP, float diag_add) {
   for (int idx = threadIdx.x; idx < KP * KP; idx += blockDim.x) {
     const int c = idx / KP, i = idx % KP;
-    float g = (c < K && i < K) ? (float)gram[(long long)r * KMAX * KMAX + c * KMAX + i] : 0.f;
+    double a = 0.0;
+    if (c < K && i < K) {
+      const double* p = gram.part + (long long)r * gram.chunks * gram.stride + idx;
+      for (int ch = 0; ch < gram.chunks; ++ch) a += p[(long long)ch * gram.stride];    // fixed order: deterministic
+    }
+    float g = (float)a;
     if (c == i && c < K) g += diag_add;
     G[idx] = g;
   }
@@ -294,7 +298,7 @@ __device__ __forceinline__ double cd_body(const FactorView& f, const float* __re
 template <int KPMAX>
 __global__ void __launch_bounds__(UPD_THREADS, KPMAX == 32 ? 2 : 3)
 mu_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
-                 const double* __restrict__ gram, BatchMeta b, float l1, float l2, double* __restrict__ cross_partial) {
+                 GramRef gram, BatchMeta b, float l1, float l2, double* __restrict__ cross_partial) {
   const int slot = blockIdx.y;
   const int r = b.rid[slot];
   if (b.done[r]) return;
@@ -315,7 +319,7 @@ mu_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long l
 template <int KPMAX>
 __global__ void __launch_bounds__(UPD_THREADS, KPMAX == 32 ? 2 : 3)
 cd_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
-                 const double* __restrict__ gram, BatchMeta b, float l1, float l2, double* __restrict__ viol_partial) {
+                 GramRef gram, BatchMeta b, float l1, float l2, double* __restrict__ viol_partial) {
   const int slot = blockIdx.y;
   const int r = b.rid[slot];
   if (b.done[r]) return;
@@ -630,7 +634,7 @@ int launch_matrix_sums(const float* X, int rows, int cols, int ld, double* out2,
     default: set_last_error("kp must be 16 or 32"); return -1;       \
   }
 
-int launch_mu_update(const FactorView& f, const float* NUM, int nsplit, long long sstride, const double* gram,
+int launch_mu_update(const FactorView& f, const float* NUM, int nsplit, long long sstride, const GramRef& gram,
                      const BatchMeta& b, float l1, float l2, double* cross_partial, cudaStream_t s) {
   dim3 grid(col_chunks(f), b.R);
   CNMF_DISPATCH_KPMAX(b.kp, (mu_update_kernel<KPMAX><<<grid, UPD_THREADS, 0, s>>>(f, NUM, nsplit, sstride, gram, b, l1,
@@ -639,7 +643,7 @@ int launch_mu_update(const FactorView& f, const float* NUM, int nsplit, long lon
   return 0;
 }
 
-int launch_cd_update(const FactorView& f, const float* NUM, int nsplit, long long sstride, const double* gram,
+int launch_cd_update(const FactorView& f, const float* NUM, int nsplit, long long sstride, const GramRef& gram,
                      const BatchMeta& b, float l1, float l2, double* viol_partial, cudaStream_t s) {
   dim3 grid(col_chunks(f), b.R);
   CNMF_DISPATCH_KPMAX(b.kp, (cd_update_kernel<KPMAX><<<grid, UPD_THREADS, 0, s>>>(f, NUM, nsplit, sstride, gram, b, l1,

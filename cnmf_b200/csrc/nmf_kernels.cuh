@@ -75,18 +75,27 @@ int launch_transpose(const float* src, int rows, int cols, int ld_src, float* ds
 int launch_matrix_sums(const float* X, int rows, int cols, int ld, double* out2, double* scratch, int scratch_len,
                        cudaStream_t s);
 
+// K x K Gram of the OTHER factor as the update kernels consume it: the per-chunk fp64 partials written by
+// launch_gram_partial, summed in fixed chunk order while the block loads its Gram into shared memory (so no
+// separate finalize launch sits on the critical path of an iteration).
+struct GramRef {
+  const double* part;   // [(rid * chunks + chunk) * stride + c * KP + i], KP = K rounded up to 4
+  int chunks;
+  int stride;           // kp * kp of the batch
+};
+
 // Multiplicative update (sklearn _nmf.py:535-549,610-624 / :633-635,696-721):
 //   F[c, j] <- F[c, j] * NUM[c, j] / max-style-guard( sum_i gram[c, i] F[i, j] + l1 + l2 F[c, j] )
 // NUM = sum over `nsplit` split-K slices (stride num_split_stride elements).
 // cross_partial[r * chunks + chunk] = sum NUM * F_new (fp64), used by the trace-form error.
 int launch_mu_update(const FactorView& f, const float* NUM, int nsplit, long long num_split_stride,
-                     const double* gram, const BatchMeta& b, float l1, float l2, double* cross_partial,
+                     const GramRef& gram, const BatchMeta& b, float l1, float l2, double* cross_partial,
                      cudaStream_t s);
 
 // One coordinate-descent sweep over the K coordinates of every column (sklearn _cdnmf_fast.pyx:8-37):
 //   viol_partial[r * chunks + chunk] = sum |projected gradient|
 int launch_cd_update(const FactorView& f, const float* NUM, int nsplit, long long num_split_stride,
-                     const double* gram, const BatchMeta& b, float l1, float l2, double* viol_partial,
+                     const GramRef& gram, const BatchMeta& b, float l1, float l2, double* viol_partial,
                      cudaStream_t s);
 
 // cross_partial[r*chunks+chunk] = sum_{c,j} NUM[c,j] * F[c,j]   (no update; used for the error at init)
