@@ -312,3 +312,88 @@ def test_pipeline_matches_reference_outputs(tmp_path, tag):
                 e = rel(got, ref)
                 assert e < 2e-4, (tag, k, key, e)
                 assert os.path.exists(obj.paths[key + "__txt"] % (k, dts))
+
+
+# ------------------------------------------------------------------------------------ facade behaviour on the GPU
+def _prepared(tmp_path, g, name="run", n_iter=None):
+    import pandas as pd
+    from cnmf_b200 import cNMF, save_df_to_npz
+    counts = g["counts"].astype(np.float64)
+    df = pd.DataFrame(counts, index=["c%d" % i for i in range(counts.shape[0])],
+                      columns=["g%d" % i for i in range(counts.shape[1])])
+    fn = str(tmp_path / "counts.df.npz")
+    save_df_to_npz(df, fn)
+    obj = cNMF(output_dir=str(tmp_path), name=name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        obj.prepare(fn, components=list(g["ks"]), n_iter=int(g["n_iter"]) if n_iter is None else n_iter,
+                    seed=int(g["seed"]), densify=True, beta_loss=2.0 if g["solver"] == "mu" else "frobenius",
+                    num_highvar_genes=len(g["hvg_idx"]))
+    return obj
+
+
+def test_worker_split_and_resume_give_identical_files(tmp_path):
+    """factorize(worker_i, total_workers) over two workers, and a resumed run with skip_completed_runs, write
+    exactly the files a single worker writes (cnmf.py:692-745, 729-733).  (Bit-exact here because batches of this
+    size share one GEMM plan; in general the split-K partition follows the number of live rows, so a restart's
+    result can move in its last bits with the batch composition -- never with the run: a given batch is deterministic.)"""
+    from cnmf_b200 import load_df_from_npz
+    g = load_golden("sim_mu")
+    a = _prepared(tmp_path / "a", g, n_iter=4)
+    b = _prepared(tmp_path / "b", g, n_iter=4)
+    c = _prepared(tmp_path / "c", g, n_iter=4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a.factorize()
+        b.factorize(worker_i=0, total_workers=2)
+        b.factorize(worker_i=1, total_workers=2)
+        c.factorize(worker_i=1, total_workers=3)            # a partial run ...
+        c.update_nmf_iter_params()
+        c.factorize(skip_completed_runs=True)               # ... resumed
+    for k in g["ks"]:
+        for it in range(4):
+            ref = load_df_from_npz(a.paths["iter_spectra"] % (k, it))
+            for other in (b, c):
+                got = load_df_from_npz(other.paths["iter_spectra"] % (k, it))
+                assert np.array_equal(ref.values, got.values), (k, it)
+                assert list(got.index) == list(range(1, k + 1))
+
+
+def test_consensus_errors_and_density_cache(tmp_path):
+    """Zero surviving spectra raises the reference's RuntimeError (cnmf.py:905-906); the local-density cache is
+    written once and reused, keyed by k only (cnmf.py:887-899)."""
+    import os as _os
+    from cnmf_b200 import load_df_from_npz
+    g = load_golden("sim_mu")
+    obj = _prepared(tmp_path, g)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        obj.factorize()
+        obj.combine()
+        k = int(g["ks"][0])
+        with pytest.raises(RuntimeError, match="Zero components remain"):
+            obj.consensus(k, density_threshold=1e-9, show_clustering=False)
+        cache = obj.paths["local_density_cache"] % k
+        assert _os.path.exists(cache)
+        before = load_df_from_npz(cache)
+        mtime = _os.path.getmtime(cache)
+        obj.consensus(k, density_threshold=0.5, local_neighborhood_size=0.9, show_clustering=False)   # cache wins
+        assert _os.path.getmtime(cache) == mtime and load_df_from_npz(cache).equals(before)
+        usage, scores, tpm, top = obj.load_results(k, 0.5, n_top_genes=5)
+        assert np.allclose(usage.sum(axis=1), 1.0) and top.shape == (5, k)
+
+
+def test_k_selection_statistics(tmp_path):
+    """k_selection_plot statistics (cnmf.py:1119-1135) against the reference's own stats branch output."""
+    g = load_golden("sim_mu")
+    obj = _prepared(tmp_path, g)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        obj.factorize()
+        obj.combine()
+        stats = obj.k_selection_plot(close_fig=True)
+    for row, k in enumerate(sorted(int(x) for x in g["ks"])):
+        ref = g["stats_k%d" % k]
+        assert int(stats.loc[row, "k"]) == k
+        assert abs(stats.loc[row, "silhouette"] - ref[2]) < 1e-4
+        assert abs(stats.loc[row, "prediction_error"] - ref[3]) / ref[3] < 1e-5
