@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libcnmf_b200.so")
 
 SOLVER_MU, SOLVER_CD = 0, 1
 PRECISION_FP32, PRECISION_TF32X3, PRECISION_TF32X3_GENERAL = 0, 1, 2
+LOSS_FROBENIUS, LOSS_KULLBACK_LEIBLER, LOSS_ITAKURA_SAITO = 0, 1, 2
 MAX_COMPONENTS = 32
 
 
@@ -26,7 +27,8 @@ class NmfParams(ctypes.Structure):
     _fields_ = [("solver", ctypes.c_int32), ("precision", ctypes.c_int32), ("max_iter", ctypes.c_int32),
                 ("reserved", ctypes.c_int32), ("tol", ctypes.c_double),
                 ("l1_reg_W", ctypes.c_double), ("l2_reg_W", ctypes.c_double),
-                ("l1_reg_H", ctypes.c_double), ("l2_reg_H", ctypes.c_double)]
+                ("l1_reg_H", ctypes.c_double), ("l2_reg_H", ctypes.c_double),
+                ("beta_loss", ctypes.c_int32), ("reserved2", ctypes.c_int32)]
 
 
 _c = ctypes
@@ -50,6 +52,7 @@ SIGNATURES = {
     "cnmf_dataset_ld": (_i, [_vp, _pp(_i), _pp(_i)]),
     "cnmf_dataset_is_exact": (_i, [_vp]),
     "cnmf_dataset_sums": (_i, [_vp, _pp(_d), _pp(_d)]),
+    "cnmf_dataset_min": (_i, [_vp, _pp(_c.c_float), _vp]),
     "cnmf_dataset_col_stats": (_i, [_vp, _vp, _vp, _vp]),
     "cnmf_random_init_host": (_i, [_c.c_uint32, _d, _i, _i, _i, _vp, _ll, _vp, _ll]),
     "cnmf_random_init_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
@@ -86,7 +89,7 @@ def load():
         fn = getattr(lib, name)        # AttributeError here = ABI mismatch: let it propagate
         fn.restype = res
         fn.argtypes = args
-    if lib.cnmf_abi_version() != 1:
+    if lib.cnmf_abi_version() != 2:
         raise CnmfError("libcnmf_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -323,6 +323,12 @@ int cnmf_dataset_create(cnmf_handle_t h, const float* X, int n_rows, int n_cols,
 
 int cnmf_dataset_finish_internal(cnmf_dataset_t d, void* stream) { return dataset_finish(d, as_stream(stream)); }
 
+int cnmf_dataset_min(cnmf_dataset_t d, float* min_host, void* stream) {
+  CNMF_REQUIRE(d && min_host, "dataset_min: NULL argument");
+  CNMF_CUDA_CHECK(cudaSetDevice(d->h->device));
+  return cnmf::matrix_min(d->h, d->X, d->n_rows, d->n_cols, d->ld_c, min_host, as_stream(stream));
+}
+
 int cnmf_dataset_destroy(cnmf_dataset_t d) {
   if (!d) return 0;
   for (auto& pr : d->owned) d->h->pool_give(pr.first, pr.second);
@@ -439,6 +445,8 @@ int run_and_download(cnmf_dataset_s* d, const std::vector<int>& ks, int SK, Fact
 int check_params(cnmf_dataset_s* d, const cnmf_nmf_params* p) {
   CNMF_REQUIRE(d && p, "NULL dataset or params");
   CNMF_REQUIRE(p->precision == d->precision, "params.precision must match the precision the dataset was created with");
+  CNMF_REQUIRE(p->reserved2 == 0, "params.reserved2 must be 0");
+  if (p->beta_loss != CNMF_LOSS_FROBENIUS) CNMF_TRY(cnmf::dataset_ensure_full_transpose(d, nullptr));
   return 0;
 }
 
@@ -626,3 +634,19 @@ int cnmf_dataset_ld(cnmf_dataset_t d, int* ld_rows, int* ld_cols) {
 }
 
 }  // extern "C"
+
+namespace cnmf {
+
+int dataset_ensure_full_transpose(cnmf_dataset_s* d, cudaStream_t s) {
+  if (d->Xt) return 0;
+  CNMF_CUDA_CHECK(cudaSetDevice(d->h->device));
+  const size_t nxt = (size_t)d->n_cols * d->ld_r;
+  CNMF_TRY(cnmf_dataset_alloc_internal(d, &d->Xt, nxt));
+  CNMF_CUDA_CHECK(cudaMemsetAsync(d->Xt, 0, nxt * sizeof(float), s));
+  CNMF_TRY(launch_transpose(d->X, d->n_rows, d->n_cols, d->ld_c, d->Xt, nullptr, nullptr, d->ld_r, s));
+  d->h->launches += 1;
+  CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+}  // namespace cnmf

@@ -160,6 +160,7 @@ int cnmf_refit(cnmf_dataset_t d, int transposed, int k, const float* fixed_host,
   cudaStream_t s = as_stream(stream);
   CNMF_CUDA_CHECK(cudaSetDevice(h->device));
   const bool tf32 = p->precision == CNMF_PRECISION_TF32X3;
+  if (p->beta_loss != CNMF_LOSS_FROBENIUS) CNMF_TRY(dataset_ensure_full_transpose(d, s));
   DataView v = make_view(d, transposed != 0);
 
   const size_t nr = (size_t)k * v.ld_r, nc = (size_t)k * v.ld_c;

@@ -105,5 +105,11 @@ struct SolveIO {
 
 // Runs the batched solver in place on io.Fr / io.Fc.
 int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_nmf_params& p, cudaStream_t s);
+// beta_loss = kullback-leibler / itakura-saito (nmf_beta.cu); reached through solve_batched
+int solve_batched_beta(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_nmf_params& p, cudaStream_t s);
+int matrix_min(cnmf_handle_s* h, const float* X, int rows, int cols, int ld, float* out_host, cudaStream_t s);
+// the streaming beta-divergence kernels read X in both orientations in full fp32: builds d->Xt if the dataset
+// (tf32x3 mode) only holds the pieces
+int dataset_ensure_full_transpose(cnmf_dataset_s* d, cudaStream_t s);
 
 }  // namespace cnmf

@@ -95,6 +95,7 @@ int run_gemm(cnmf_handle_s* h, int precision, const float* A, const float* A_hi,
 
 int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_nmf_params& p, cudaStream_t s) {
   const int R0 = io.R;
+  if (p.beta_loss != CNMF_LOSS_FROBENIUS) return solve_batched_beta(h, v, io, p, s);
   CNMF_REQUIRE(R0 > 0 && (int)io.ks.size() == R0, "solve: bad restart list");
   CNMF_REQUIRE(p.solver == CNMF_SOLVER_MU || p.solver == CNMF_SOLVER_CD, "solve: unknown solver");
   CNMF_REQUIRE(p.max_iter >= 1, "solve: max_iter must be >= 1");

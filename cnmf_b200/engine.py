@@ -8,8 +8,8 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import (NmfParams, PRECISION_FP32, PRECISION_TF32X3, PRECISION_TF32X3_GENERAL, SOLVER_CD, SOLVER_MU,
-                   check, f32c, ptr)
+from ._lib import (LOSS_FROBENIUS, LOSS_ITAKURA_SAITO, LOSS_KULLBACK_LEIBLER, NmfParams, PRECISION_FP32,
+                   PRECISION_TF32X3, PRECISION_TF32X3_GENERAL, SOLVER_CD, SOLVER_MU, check, f32c, ptr)
 
 _DEFAULT_PRECISION = PRECISION_TF32X3
 
@@ -32,8 +32,9 @@ def make_params(nmf_kwargs, n_samples, n_features, precision):
     path implements is accepted; anything else raises (no silent fallback)."""
     solver = nmf_kwargs.get("solver", "mu")
     beta = nmf_kwargs.get("beta_loss", "frobenius")
-    if beta not in ("frobenius", 2, 2.0):
-        raise NotImplementedError("cnmf_b200: only the Frobenius loss is implemented on the CUDA path (got %r)" % (beta,))
+    loss = loss_code(beta)
+    if loss != LOSS_FROBENIUS and solver != "mu":      # sklearn _nmf.py:1195-1199
+        raise ValueError("Invalid beta_loss parameter: solver %r does not handle beta_loss = %r" % (solver, beta))
     if nmf_kwargs.get("init", "random") != "random":
         raise NotImplementedError("cnmf_b200: only init='random' is implemented on the CUDA path")
     if solver not in ("mu", "cd"):
@@ -55,7 +56,20 @@ def make_params(nmf_kwargs, n_samples, n_features, precision):
     p.l1_reg_H = n_samples * alpha_H * l1_ratio
     p.l2_reg_W = n_features * alpha_W * (1.0 - l1_ratio)
     p.l2_reg_H = n_samples * alpha_H * (1.0 - l1_ratio)
+    p.beta_loss = loss
     return p
+
+
+def loss_code(beta):
+    """'frobenius' | 2 -> tensor-core path; 'kullback-leibler' | 1 and 'itakura-saito' | 0 -> streaming MU kernels
+    (sklearn _nmf.py:52-58 `_beta_loss_to_float`).  Other beta values are not implemented on the CUDA path."""
+    table = {"frobenius": LOSS_FROBENIUS, 2: LOSS_FROBENIUS, "kullback-leibler": LOSS_KULLBACK_LEIBLER,
+             1: LOSS_KULLBACK_LEIBLER, "itakura-saito": LOSS_ITAKURA_SAITO, 0: LOSS_ITAKURA_SAITO}
+    try:
+        return table[beta]
+    except (KeyError, TypeError):
+        raise NotImplementedError("cnmf_b200: beta_loss must be 'frobenius' (2), 'kullback-leibler' (1) or "
+                                  "'itakura-saito' (0) on the CUDA path (got %r)" % (beta,))
 
 
 class Engine:
@@ -165,6 +179,7 @@ class Dataset:
         ks = np.ascontiguousarray(ks, dtype=np.int32)
         R = len(ks)
         p = self.params(nmf_kwargs)
+        self._check_loss(p)
         n_iter = np.zeros(R, np.int32)
         err = np.zeros(R, np.float64)
         check(self.lib.cnmf_factorize_dev(self._d, R, ptr(ks), ctypes.c_void_p(Wt0_ptr), ctypes.c_void_p(H0_ptr),
@@ -175,6 +190,17 @@ class Dataset:
     def exact(self):
         """True when X was recognised as scaled integer counts (2-pass tensor-core products)."""
         return bool(self.lib.cnmf_dataset_is_exact(self._d))
+
+    def min(self):
+        m = ctypes.c_float()
+        check(self.lib.cnmf_dataset_min(self._d, ctypes.byref(m), None))
+        return float(m.value)
+
+    def _check_loss(self, p):
+        # sklearn _nmf.py:1675-1680
+        if p.beta_loss == LOSS_ITAKURA_SAITO and self.min() == 0:
+            raise ValueError("When beta_loss <= 0 and X contains zeros, the solver may diverge. Please add small values "
+                             "to X, or use a positive beta_loss.")
 
     def sums(self):
         s, q = ctypes.c_double(), ctypes.c_double()
@@ -204,6 +230,7 @@ class Dataset:
         SK = int(ks.sum())
         n, g = self.shape
         p = self.params(nmf_kwargs)
+        self._check_loss(p)
         spectra = np.empty((SK, g), np.float32)
         usages = np.empty((SK, n), np.float32) if return_usages else None
         n_iter = np.zeros(R, np.int32)
@@ -231,6 +258,7 @@ class Dataset:
         n_r, n_c = (g, n) if transposed else (n, g)
         assert fixed.shape[1] == n_c
         p = make_params(nmf_kwargs, n_r, n_c, self.precision)
+        self._check_loss(p)
         out = np.empty((n_r, k), np.float32)
         it = ctypes.c_int32(0)
         err = ctypes.c_double(0)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CNMF_B200_ABI_VERSION 1
+#define CNMF_B200_ABI_VERSION 2
 #define CNMF_MAX_COMPONENTS 32          /* largest n_components per restart on the CUDA path */
 
 typedef struct cnmf_handle_s* cnmf_handle_t;
@@ -39,6 +39,11 @@ enum { CNMF_SOLVER_MU = 0, CNMF_SOLVER_CD = 1 };            /* yaml 'solver': cn
  * tcgen05 3xTF32 always in the general 3-pass form.  Params for a dataset created with 2 use precision 1. */
 enum { CNMF_PRECISION_FP32 = 0, CNMF_PRECISION_TF32X3 = 1, CNMF_PRECISION_TF32X3_GENERAL = 2 };
 
+/* yaml 'beta_loss' (cnmf.py:622, CLI --beta-loss cnmf.py:1251).  'frobenius' (or 2) runs the tensor-core path with
+ * either solver; 'kullback-leibler' (1) and 'itakura-saito' (0) run the multiplicative updates of sklearn
+ * _nmf.py:551-608, 637-694 as fused streaming kernels (solver must be CNMF_SOLVER_MU, as in sklearn). */
+enum { CNMF_LOSS_FROBENIUS = 0, CNMF_LOSS_KULLBACK_LEIBLER = 1, CNMF_LOSS_ITAKURA_SAITO = 2 };
+
 /* Mirrors the nmf_kwargs dict of cnmf.py:618-627 after sklearn's own scaling of the
  * regularisation (sklearn/decomposition/_nmf.py:1249-1260): l1_reg_W = n_features*alpha_W*l1_ratio ... */
 typedef struct cnmf_nmf_params {
@@ -48,6 +53,8 @@ typedef struct cnmf_nmf_params {
   int32_t reserved;      /* flags: bit 0 = draw the random init on the host (bit-exact numpy stream) instead of the GPU */
   double tol;            /* 'tol' (cnmf.py:624) */
   double l1_reg_W, l2_reg_W, l1_reg_H, l2_reg_H;
+  int32_t beta_loss;     /* CNMF_LOSS_* ('beta_loss', cnmf.py:622); 0 = frobenius */
+  int32_t reserved2;     /* must be 0 */
 } cnmf_nmf_params;
 
 /* ---- library / handle -------------------------------------------------------------- */
@@ -82,6 +89,8 @@ int cnmf_dataset_shape(cnmf_dataset_t d, int* n_rows, int* n_cols);
 /* padded row strides of the packed factor layout: W^T rows (ld_rows >= n_rows), H rows (ld_cols >= n_cols) */
 int cnmf_dataset_ld(cnmf_dataset_t d, int* ld_rows, int* ld_cols);
 int cnmf_dataset_sums(cnmf_dataset_t d, double* sum, double* sum_sq);
+/* smallest entry of X (sklearn refuses beta_loss <= 0 when X.min() == 0, _nmf.py:1675-1680; the caller raises) */
+int cnmf_dataset_min(cnmf_dataset_t d, float* min_host, void* stream);
 /* 1 when the dataset was recognised as (row scale) x (integer counts <= 2048) x (column scale) -- what
  * HVG-normalised counts (cnmf.py:542) and TPM (cnmf.py:245-251) are -- and therefore runs the 2-pass
  * tensor-core products (the integer operand needs no tf32 "lo" piece); 0 = general 3-pass 3xTF32.

@@ -201,7 +201,7 @@ def silhouette(l2, labels):
 
 def consensus(merged, X, tpm, tpm_std, hvg_idx, k, density_threshold=0.5,
               local_neighborhood_size=0.30, solver="mu", tol=1e-4, max_iter=1000,
-              refit_usage=True):
+              refit_usage=True, beta=2):
     """Numeric part of cNMF.consensus (cnmf.py:871-975) on plain arrays.
 
     merged   R x G stacked spectra (f64)       X    N x G normalised counts
@@ -220,20 +220,20 @@ def consensus(merged, X, tpm, tpm_std, hvg_idx, k, density_threshold=0.5,
         raise RuntimeError("Zero components remain after density filtering. Consider increasing density threshold")
     labels, inertia, _ = kmeans(l2f, k)
     med = cluster_medians(l2f, labels, k)
-    rf, _ = nmf_ref.refit(X, med, solver, tol, max_iter)
+    rf, _ = nmf_ref.refit(X, med, solver, tol, max_iter, beta=beta)
     norm_usages = rf / rf.sum(axis=1, keepdims=True)
     order = np.argsort(-norm_usages.sum(axis=0), kind="stable")
     rf = rf[:, order]
     norm_usages = norm_usages[:, order]
     med = med[order]
-    spectra_tpm_T, _ = nmf_ref.refit(tpm.T, norm_usages.T, solver, tol, max_iter)
+    spectra_tpm_T, _ = nmf_ref.refit(tpm.T, norm_usages.T, solver, tol, max_iter, beta=beta)
     spectra_tpm = spectra_tpm_T.T
     score = ols_zscore(rf, tpm)
     usages = rf
     if refit_usage:
         norm_tpm = tpm[:, hvg_idx] / tpm[:, hvg_idx].std(axis=0, ddof=1)
         sp_rf = spectra_tpm[:, hvg_idx] / tpm_std[hvg_idx]
-        usages, _ = nmf_ref.refit(norm_tpm, sp_rf, solver, tol, max_iter)
+        usages, _ = nmf_ref.refit(norm_tpm, sp_rf, solver, tol, max_iter, beta=beta)
     return dict(l2=l2, local_density=dens, keep=keep, labels=labels, inertia=inertia,
                 consensus_spectra=med, consensus_usages=usages,
                 gene_spectra_tpm=spectra_tpm, gene_spectra_score=score, order=order)

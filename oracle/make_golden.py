@@ -9,10 +9,10 @@ network downloads (download_pytest_data.py:38-52) and are not available offline,
 fixtures -- outputs of the reference itself on deterministic synthetic inputs -- are what
 pins the oracle and, through it, the CUDA path.
 
-Fixture ``<tag>.npz`` (one per solver, tags ``sim_mu`` / ``sim_cd``) holds
+Fixture ``<tag>.npz`` (one per solver / loss, tags ``sim_mu`` / ``sim_cd`` / ``sim_kl``) holds
   counts          int16 cells x genes_all  (input given to reference prepare())
   hvg_idx         positions of the HVGs chosen by the reference inside genes_all
-  ks, n_iter, seed, solver
+  ks, n_iter, seed, solver   (+ beta_loss in fixtures generated for a non-Frobenius loss)
   table           (n_components, iter, nmf_seed) rows written by reference prepare()
   merged_k<K>     reference combine() output (R x G, f64) after reference factorize()
   density_k<K>    reference local_density_cache
@@ -44,6 +44,7 @@ CASES = {
     # tag: (n_cells, n_genes_all, k_true, nhvg, ks, n_iter, seed, beta_loss, consensus dt)
     "sim_mu": (400, 260, 5, 200, [4, 5], 8, 14, 2.0, 0.5),      # float beta_loss -> solver 'mu' 
     "sim_cd": (400, 260, 5, 200, [4, 5], 8, 14, "frobenius", 0.5),  # reference default -> 'cd'
+    "sim_kl": (400, 260, 5, 200, [4, 5], 6, 14, "kullback-leibler", 0.5),  # --beta-loss kullback-leibler -> 'mu', beta=1
 }
 
 
@@ -72,7 +73,7 @@ def run_case(tag, spec):
         import yaml
         run_params = yaml.load(open(obj.paths["nmf_run_parameters"]), Loader=yaml.FullLoader)
         out.update(counts=counts.astype(np.int16), hvg_idx=hvg_idx, ks=np.array(ks), n_iter=n_iter,
-                   seed=seed, solver=run_params["solver"],
+                   seed=seed, solver=run_params["solver"], beta_loss=str(run_params["beta_loss"]),
                    table=table[["n_components", "iter", "nmf_seed"]].values.astype(np.int64))
         for k in ks:
             merged = ref.load_df_from_npz(obj.paths["merged_spectra"] % k)
@@ -111,4 +112,5 @@ def run_case(tag, spec):
 
 if __name__ == "__main__":
     for tag, spec in CASES.items():
-        run_case(tag, spec)
+        if len(sys.argv) == 1 or tag in sys.argv[1:]:      # `python -m oracle.make_golden sim_kl` regenerates one
+            run_case(tag, spec)

@@ -80,6 +80,103 @@ def mu_frobenius(X, W, H, tol=1e-4, max_iter=1000, l1_reg_W=0.0, l2_reg_W=0.0,
     return W, H, n_iter
 
 
+def beta_divergence(X, W, H, beta):
+    """SK/decomposition/_nmf.py:77-175 (dense branch), square_root=True, for beta in {1: generalized
+    Kullback-Leibler, 0: Itakura-Saito}.  Entries with X <= EPSILON are dropped (:140-142), WH is
+    floored at EPSILON (:145); the result is sqrt(2 * max(res, 0)) (:170-175)."""
+    WH = (W @ H).ravel()
+    Xd = X.ravel()
+    keep = Xd > EPSILON
+    WH = WH[keep]
+    Xd = Xd[keep]
+    WH[WH < EPSILON] = EPSILON
+    if beta == 1:
+        sum_WH = np.dot(W.sum(axis=0), H.sum(axis=1))
+        div = Xd / WH
+        res = np.dot(Xd, np.log(div)) + sum_WH - Xd.sum()
+    elif beta == 0:
+        div = Xd / WH
+        res = div.sum() - np.prod(X.shape) - np.log(div).sum()
+    else:
+        raise ValueError("oracle restates beta in {0, 1} (and 2 via mu_frobenius)")
+    return np.sqrt(2.0 * max(res, 0.0))
+
+
+def mu_beta(X, W, H, beta, tol=1e-4, max_iter=1000, l1_reg_W=0.0, l2_reg_W=0.0,
+            l1_reg_H=0.0, l2_reg_H=0.0, update_H=True):
+    """Multiplicative-update NMF for beta_loss 'kullback-leibler' (1) / 'itakura-saito' (0), dense X.
+    SK/decomposition/_nmf.py:726-888 (loop; gamma :813-818; clipping :845-846, :863-865),
+    :551-608 (W numerator / denominator), :637-694 (H), :610-624 / :696-721 (regularisation, guard).
+    Asymmetries kept: the H half replaces a zero W_sum by 1 (:669), the W half does not; with beta=1
+    only H is clipped below float64 eps (:864), with beta<1 both are (:845)."""
+    W = W.copy()
+    H = H.copy()
+    gamma = 1.0 / (2.0 - beta) if beta < 1 else 1.0
+    eps64 = np.finfo(np.float64).eps
+    err0 = prev = beta_divergence(X, W, H, beta)
+    H_sum = None
+    n_iter = 0
+    for n_iter in range(1, max_iter + 1):
+        WH = W @ H
+        WHs = WH.copy()
+        if beta < 1:
+            WH[WH < EPSILON] = EPSILON
+        WHs[WHs < EPSILON] = EPSILON
+        if beta == 1:
+            Q = X / WHs
+            num = Q @ H.T
+            if H_sum is None:
+                H_sum = H.sum(axis=1)
+            den = np.repeat(H_sum[None, :], W.shape[0], axis=0)
+        else:
+            Q = X * (1.0 / WHs) ** 2
+            num = Q @ H.T
+            den = (WH ** (beta - 1.0)) @ H.T
+        if l1_reg_W > 0:
+            den = den + l1_reg_W
+        if l2_reg_W > 0:
+            den = den + l2_reg_W * W
+        den[den == 0] = EPSILON
+        delta = num / den
+        if gamma != 1:
+            delta **= gamma
+        W *= delta
+        if beta < 1:
+            W[W < eps64] = 0.0
+        if update_H:
+            WH = W @ H
+            WHs = WH.copy()
+            if beta < 1:
+                WH[WH < EPSILON] = EPSILON
+            WHs[WHs < EPSILON] = EPSILON
+            if beta == 1:
+                num = W.T @ (X / WHs)
+                W_sum = W.sum(axis=0)
+                W_sum[W_sum == 0] = 1.0
+                den = np.repeat(W_sum[:, None], H.shape[1], axis=1)
+            else:
+                num = W.T @ (X * (1.0 / WHs) ** 2)
+                den = W.T @ (WH ** (beta - 1.0))
+            if l1_reg_H > 0:
+                den = den + l1_reg_H
+            if l2_reg_H > 0:
+                den = den + l2_reg_H * H
+            den[den == 0] = EPSILON
+            delta = num / den
+            if gamma != 1:
+                delta **= gamma
+            H *= delta
+            H_sum = None
+            if beta <= 1:
+                H[H < eps64] = 0.0
+        if tol > 0 and n_iter % 10 == 0:
+            err = beta_divergence(X, W, H, beta)
+            if (prev - err) / err0 < tol:
+                break
+            prev = err
+    return W, H, n_iter
+
+
 def _cd_sweep(A, Gram, B):
     """SK/decomposition/_cdnmf_fast.pyx:8-37 restated row-outer (rows are independent,
     verified identical to the t-outer Cython order).
@@ -132,12 +229,14 @@ def cd_frobenius(X, W, H, tol=1e-4, max_iter=1000, l1_reg_W=0.0, l2_reg_W=0.0,
 
 
 def nmf(X, k, seed, solver="mu", tol=1e-4, max_iter=1000, dtype=np.float64,
-        alpha_W=0.0, alpha_H=0.0, l1_ratio=0.0):
+        alpha_W=0.0, alpha_H=0.0, l1_ratio=0.0, beta=2):
     """One restart as cNMF.factorize issues it (cnmf.py:738-741): random init + solver."""
     X = np.asarray(X, dtype=dtype)
     n, g = X.shape
     W, H = init_random(X.mean(), n, g, k, seed, dtype=dtype)
     l1W, l2W, l1H, l2H = reg_terms(n, g, alpha_W, alpha_H, l1_ratio)
+    if solver == "mu" and beta != 2:
+        return mu_beta(X, W, H, beta, tol, max_iter, l1W, l2W, l1H, l2H)
     if solver == "mu":
         return mu_frobenius(X, W, H, tol, max_iter, l1W, l2W, l1H, l2H)
     return cd_frobenius(X, W, H, tol, max_iter, l1W, l2W, l1H, l2H)
@@ -153,7 +252,7 @@ def reg_terms(n_samples, n_features, alpha_W, alpha_H, l1_ratio):
     return l1W, l2W, l1H, l2H
 
 
-def refit(X, H, solver="mu", tol=1e-4, max_iter=1000, dtype=np.float64):
+def refit(X, H, solver="mu", tol=1e-4, max_iter=1000, dtype=np.float64, beta=2):
     """cNMF.refit_usage (cnmf.py:776-802): NMF with H fixed (update_H=False).
     W0: SK/decomposition/_nmf.py:1223-1228 -- 'mu': constant sqrt(X.mean()/k); 'cd': zeros."""
     X = np.asarray(X, dtype=dtype)
@@ -162,7 +261,10 @@ def refit(X, H, solver="mu", tol=1e-4, max_iter=1000, dtype=np.float64):
     k = H.shape[0]
     if solver == "mu":
         W0 = np.full((n, k), np.sqrt(X.mean() / k), dtype=dtype)
-        W, _, it = mu_frobenius(X, W0, H, tol, max_iter, update_H=False)
+        if beta != 2:
+            W, _, it = mu_beta(X, W0, H, beta, tol, max_iter, update_H=False)
+        else:
+            W, _, it = mu_frobenius(X, W0, H, tol, max_iter, update_H=False)
     else:
         W0 = np.zeros((n, k), dtype=dtype)
         W, _, it = cd_frobenius(X, W0, H, tol, max_iter, update_H=False)

@@ -15,22 +15,24 @@ import warnings
 import numpy as np
 
 
-def nmf_kwargs(solver="mu", tol=1e-4, max_iter=1000):
+def nmf_kwargs(solver="mu", tol=1e-4, max_iter=1000, beta_loss=None):
     """cnmf.py:618-631: beta_loss='frobenius' -> solver 'cd' (the reference default); a float
-    beta_loss=2.0 keeps solver 'mu' (SURVEY.md fact 3)."""
+    beta_loss=2.0 keeps solver 'mu' (SURVEY.md fact 3); 'kullback-leibler' / 'itakura-saito' keep 'mu'."""
     kw = dict(alpha_W=0.0, alpha_H=0.0, l1_ratio=0.0, beta_loss="frobenius", solver="mu", tol=tol,
               max_iter=max_iter, init="random")
-    if solver == "cd":
+    if beta_loss not in (None, "frobenius", 2, 2.0):
+        kw["beta_loss"] = beta_loss
+    elif solver == "cd":
         kw["solver"] = "cd"
     else:
         kw["beta_loss"] = 2.0
     return kw
 
 
-def factorize(X, jobs, solver="mu", tol=1e-4, max_iter=1000):
+def factorize(X, jobs, solver="mu", tol=1e-4, max_iter=1000, beta_loss=None):
     """jobs: list of (k, seed).  Returns (list of spectra, list of n_iter, seconds)."""
     from sklearn.decomposition import non_negative_factorization
-    kw = nmf_kwargs(solver, tol, max_iter)
+    kw = nmf_kwargs(solver, tol, max_iter, beta_loss)
     X = np.asarray(X, dtype=np.float64)              # cnmf.py:534
     out, its = [], []
     t0 = time.perf_counter()

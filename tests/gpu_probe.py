@@ -215,6 +215,29 @@ def stage_cd():
         sec / 2, os.cpu_count(), its, n_iter[:2].tolist(), rel(sp[0], spr[0]), rel(sp[1], spr[1])), flush=True)
 
 
+def stage_kl():
+    """--beta-loss kullback-leibler on the c2 workload (streaming kernels, no GEMM)."""
+    from cnmf_b200.synth import make_counts, normalise, restart_table
+    from oracle import reference_path
+    eng = Engine()
+    X, _ = normalise(make_counts(20000, 2000, k_true=12))
+    rows = restart_table([10], 100)
+    ds = eng.dataset(X)
+    for max_iter in (20, 1000):
+        kw = dict(solver="mu", beta_loss="kullback-leibler", tol=1e-4, max_iter=max_iter)
+        n0 = eng.launch_count
+        t0 = time.time()
+        sp, _, n_iter, err = ds.factorize([r[0] for r in rows], [r[2] for r in rows], kw)
+        dt = time.time() - t0
+        print("kl c2 max_iter %d: %.2fs -> %.1f restarts/s; n_iter mean %.1f max %d; %.2f ms per batched iteration; %d launches" % (
+            max_iter, dt, len(rows) / dt, n_iter.mean(), n_iter.max(), 1e3 * dt / n_iter.max(), eng.launch_count - n0), flush=True)
+    spr, its, sec = reference_path.factorize(X, [(rows[0][0], rows[0][2])], "mu", max_iter=50, beta_loss="kullback-leibler")
+    kw = dict(solver="mu", beta_loss="kullback-leibler", tol=1e-4, max_iter=50)
+    sp50, _, it50, _ = ds.factorize([rows[0][0]], [rows[0][2]], kw)
+    print("   reference kl (50 iterations): %.2fs (%d cores) = %.3f s/iteration; n_iter %s vs gpu %s; rel-L2 %.2e" % (
+        sec, os.cpu_count(), sec / its[0], its, it50.tolist(), rel(sp50[0], spr[0])), flush=True)
+
+
 def stage_perf():
     eng = Engine()
     rng = np.random.RandomState(0)
@@ -327,6 +350,8 @@ if __name__ == "__main__":
         stage_c3()
     elif st == "consensus_c4":
         stage_consensus_c4()
+    elif st == "kl":
+        stage_kl()
     elif st == "cd":
         stage_cd()
     elif st == "big":

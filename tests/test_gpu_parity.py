@@ -188,6 +188,92 @@ def test_factorize_with_regularisation(eng):
         assert rel(sp[0], H) < TOL_SPECTRA
 
 
+# ------------------------------------------------------------------------------------ beta-divergence losses
+@pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
+def test_factorize_kl_matches_reference_fixture(eng, precision):
+    """--beta-loss kullback-leibler (cnmf.py:629-631 -> solver 'mu', beta = 1): every restart of the reference's own
+    run, same n_iter, spectra within the north-star tolerance; reported errors = sqrt(2 KL) is not returned, the
+    Frobenius residual of the final factors is."""
+    from oracle import nmf_ref
+    g = load_golden("sim_kl")
+    assert g["beta"] == 1 and g["solver"] == "mu"
+    ds = eng.dataset(g["X"], precision=precision)
+    kw = dict(solver="mu", beta_loss="kullback-leibler", tol=1e-4, max_iter=1000)
+    table = g["table"]
+    sp, us, n_iter, err = ds.factorize(table[:, 0], table[:, 2], kw, return_usages=True)
+    errs = []
+    for r, (k, it, seed) in enumerate(table):
+        ref = g["merged_k%d" % k][it * k:(it + 1) * k]
+        e = rel(sp[r], ref)
+        errs.append(e)
+        limit = max(TOL_SPECTRA, 3.0 * float(g["fp32dev_k%d" % k][it]))
+        assert e < limit, (precision, k, it, e, limit)
+        Wo, Ho, n_o = nmf_ref.nmf(g["X"], int(k), int(seed), solver="mu", beta=1)
+        assert n_o == int(n_iter[r]), (precision, k, it, n_o, int(n_iter[r]))
+        e_true = nmf_ref.frobenius_error(g["X"], us[r].astype(np.float64), sp[r].astype(np.float64))
+        assert abs(err[r] - e_true) / e_true < 1e-5
+    assert np.median(errs) < 2e-5, errs
+
+
+def test_kl_refit_regularisation_and_edge_shapes(eng):
+    from oracle import nmf_ref
+    from cnmf_b200.synth import make_counts, normalise
+    g = load_golden("sim_kl")
+    X, tpm = g["X"], g["tpm"]
+    k = int(g["ks"][1])
+    kw = dict(solver="mu", beta_loss="kullback-leibler", tol=1e-4, max_iter=1000)
+    ds = eng.dataset(X)
+    # refit_usage / refit_spectra with the loss of the run (cnmf.py:792 re-reads the yaml)
+    H = g["cspectra_k%d" % k]
+    W, it, err = ds.refit(H, kw)
+    Wr, itr = nmf_ref.refit(X, H, "mu", beta=1)
+    assert it == itr and rel(W, Wr) < TOL_SPECTRA
+    assert abs(err - nmf_ref.frobenius_error(X, Wr, H)) / err < 1e-5
+    U = Wr / Wr.sum(axis=1, keepdims=True)
+    tds = eng.dataset(tpm)
+    Ht, it2, _ = tds.refit(np.ascontiguousarray(U.T), kw, transposed=True)
+    Hr, itr2 = nmf_ref.refit(tpm.T, U.T, "mu", beta=1)
+    assert it2 == itr2 and rel(Ht, Hr) < TOL_SPECTRA
+    # regularised
+    kwr = dict(kw, max_iter=150, alpha_W=0.002, alpha_H=0.001, l1_ratio=0.3)
+    sp, _, n_iter, _ = ds.factorize([5], [99], kwr)
+    _, Hreg, itreg = nmf_ref.nmf(X, 5, 99, solver="mu", beta=1, max_iter=150, alpha_W=0.002, alpha_H=0.001, l1_ratio=0.3)
+    assert itreg == int(n_iter[0]) and rel(sp[0], Hreg) < TOL_SPECTRA
+    # ragged sizes, K = 1 / 17 / 32 in ONE batch (three register classes of the kernel)
+    X64, _ = normalise(make_counts(333, 97, k_true=3, seed=3, libsize=500.0), np.float64)
+    ds2 = eng.dataset(X64)
+    ks, seeds = [1, 17, 32, 3], [11, 12, 13, 14]
+    sp, _, n_iter, _ = ds2.factorize(ks, seeds, dict(kw, max_iter=40))
+    for r, (kk, seed) in enumerate(zip(ks, seeds)):
+        _, Ho, ito = nmf_ref.nmf(X64, kk, seed, solver="mu", beta=1, max_iter=40)
+        assert ito == int(n_iter[r])
+        assert rel(sp[r], Ho) < 5e-4, (kk, rel(sp[r], Ho))
+    with pytest.raises(ValueError):          # sklearn: 'cd' does not handle beta_loss != frobenius
+        ds.factorize([3], [1], dict(kw, solver="cd"))
+
+
+def test_itakura_saito(eng):
+    """beta = 0: sklearn refuses X with zeros (_nmf.py:1675-1680) -- count data always has them; on strictly
+    positive X the updates (gamma = 1/2, both factors clipped) match the oracle."""
+    from oracle import nmf_ref
+    g = load_golden("sim_kl")
+    kw = dict(solver="mu", beta_loss="itakura-saito", tol=1e-4, max_iter=300)
+    with pytest.raises(ValueError, match="contains zeros"):
+        eng.dataset(g["X"]).factorize([4], [1], kw)
+    Xp = g["X"] + 0.1
+    ds = eng.dataset(Xp)
+    assert abs(ds.min() - Xp.min()) < 1e-6
+    sp, us, n_iter, err = ds.factorize([4, 9], [5, 6], kw, return_usages=True)
+    for r, (k, seed) in enumerate(((4, 5), (9, 6))):
+        Wo, Ho, ito = nmf_ref.nmf(Xp, k, seed, solver="mu", beta=0, max_iter=300)
+        assert ito == int(n_iter[r]), (k, ito, int(n_iter[r]))
+        assert rel(sp[r], Ho) < 5e-4, (k, rel(sp[r], Ho))
+    Wr, itr = nmf_ref.refit(Xp, Ho, "mu", beta=0, max_iter=300)
+    W, it, _ = ds.refit(Ho, kw)
+    assert it == itr and rel(W, Wr) < 5e-4
+
+
+
 # ------------------------------------------------------------------------------------ refits
 @pytest.mark.parametrize("precision", ["tf32x3", "tf32x3-general"])
 @pytest.mark.parametrize("tag", ["sim_mu", "sim_cd"])
@@ -272,7 +358,7 @@ def test_consensus_kernels_larger_random(eng):
 
 
 # ------------------------------------------------------------------------------------ end to end through the facade
-@pytest.mark.parametrize("tag", ["sim_mu", "sim_cd"])
+@pytest.mark.parametrize("tag", ["sim_mu", "sim_cd", "sim_kl"])
 def test_pipeline_matches_reference_outputs(tmp_path, tag):
     """prepare -> factorize -> combine -> consensus through cnmf_b200.cNMF on the fixture's counts; every
     file the reference wrote is reproduced within tolerance (the reference test's own criterion is a sum of
@@ -289,7 +375,7 @@ def test_pipeline_matches_reference_outputs(tmp_path, tag):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         obj.prepare(fn, components=list(g["ks"]), n_iter=int(g["n_iter"]), seed=int(g["seed"]), densify=True,
-                    beta_loss=2.0 if g["solver"] == "mu" else "frobenius", num_highvar_genes=len(g["hvg_idx"]))
+                    beta_loss=g["beta_loss_arg"], num_highvar_genes=len(g["hvg_idx"]))
         obj.factorize()
         obj.combine()
         dt = float(g["dt"])
@@ -328,7 +414,7 @@ def _prepared(tmp_path, g, name="run", n_iter=None):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         obj.prepare(fn, components=list(g["ks"]), n_iter=int(g["n_iter"]) if n_iter is None else n_iter,
-                    seed=int(g["seed"]), densify=True, beta_loss=2.0 if g["solver"] == "mu" else "frobenius",
+                    seed=int(g["seed"]), densify=True, beta_loss=g["beta_loss_arg"],
                     num_highvar_genes=len(g["hvg_idx"]))
     return obj
 

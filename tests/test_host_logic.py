@@ -90,7 +90,7 @@ def test_prepare_matches_reference_outputs(tmp_path, golden):
     fn = str(tmp_path / "counts.df.npz")
     save_df_to_npz(df, fn)
     obj = cNMF(output_dir=str(tmp_path), name="p")
-    beta = 2.0 if golden["solver"] == "mu" else "frobenius"
+    beta = golden["beta_loss_arg"]
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
@@ -199,8 +199,13 @@ def test_solver_selection_rule():
     assert obj.get_nmf_iter_params([3], 1, 1, beta_loss="frobenius")[1]["solver"] == "cd"
     assert obj.get_nmf_iter_params([3], 1, 1, beta_loss=2.0)[1]["solver"] == "mu"
     from cnmf_b200.engine import make_params
+    assert make_params(dict(solver="mu", beta_loss="kullback-leibler"), 10, 10, "tf32x3").beta_loss == 1
+    assert make_params(dict(solver="mu", beta_loss="itakura-saito"), 10, 10, "tf32x3").beta_loss == 2
+    assert make_params(dict(solver="cd", beta_loss="frobenius"), 10, 10, "tf32x3").beta_loss == 0
+    with pytest.raises(ValueError):             # sklearn _nmf.py:1195-1199: 'cd' only handles frobenius
+        make_params(dict(solver="cd", beta_loss="kullback-leibler"), 10, 10, "tf32x3")
     with pytest.raises(NotImplementedError):
-        make_params(dict(solver="mu", beta_loss="kullback-leibler"), 10, 10, "tf32x3")
+        make_params(dict(solver="mu", beta_loss=0.5), 10, 10, "tf32x3")
     with pytest.raises(NotImplementedError):
         make_params(dict(solver="cd", init="nndsvd"), 10, 10, "tf32x3")
     p = make_params(dict(solver="cd", alpha_W=0.5, alpha_H="same", l1_ratio=0.25, tol=1e-3, max_iter=7), 100, 40, "fp32")

@@ -28,7 +28,7 @@ def test_factorize_restatement_matches_reference(golden):
         merged = golden["merged_k%d" % k]
         rows = [r for r in golden["table"] if r[0] == k]
         for (kk, it, seed) in rows:
-            W, H, n_it = nmf_ref.nmf(X, int(kk), int(seed), solver=solver)
+            W, H, n_it = nmf_ref.nmf(X, int(kk), int(seed), solver=solver, beta=golden["beta"])
             ref = merged[it * k:(it + 1) * k]
             assert rel_l2(H, ref) < 1e-10, (solver, k, it)
 
@@ -50,7 +50,7 @@ def test_consensus_restatement_matches_reference(golden):
     for k in golden["ks"]:
         out = consensus_ref.consensus(golden["merged_k%d" % k], golden["X"], golden["tpm"],
                                       golden["tpm_std"], golden["hvg_idx"], int(k),
-                                      density_threshold=float(golden["dt"]), solver=solver)
+                                      density_threshold=float(golden["dt"]), solver=solver, beta=golden["beta"])
         # ||x||^2+||y||^2-2x.y cancels catastrophically for near-identical unit rows (d ~ 1e-4 here):
         # fp64 summation-order noise of 1e-16 in d^2 is 1e-8 relative -- hence rtol 1e-6, not 1e-12
         assert np.allclose(out["local_density"], golden["density_k%d" % k], rtol=1e-6, atol=1e-12)
@@ -106,7 +106,7 @@ def test_stats_branch_matches_reference(golden):
         l2 = consensus_ref.l2_normalize_rows(merged)
         labels, _, _ = consensus_ref.kmeans(l2, int(k))
         med = consensus_ref.cluster_medians(l2, labels, int(k))
-        rf, _ = nmf_ref.refit(golden["X"], med, solver)
+        rf, _ = nmf_ref.refit(golden["X"], med, solver, beta=golden["beta"])
         err = ((golden["X"] - rf @ med) ** 2).sum()
         stats = golden["stats_k%d" % k]
         assert abs(consensus_ref.silhouette(l2, labels) - stats[2]) < 1e-9
