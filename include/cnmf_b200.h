@@ -120,7 +120,7 @@ int cnmf_random_init_dev(cnmf_dataset_t d, int n_restarts, const int32_t* ks, co
  *   usages_host  : optional (may be NULL; the reference discards W) packed (sum ks) x n_rows,
  *                  i.e. W^T per restart
  *   n_iter_host  : optional [n_restarts] iterations run;  err_host: optional [n_restarts]
- *                  final ||X - WH||_F (mu) or last projected-gradient violation (cd) */
+ *                  ||X - WH||_F of the returned factors (every solver and loss) */
 int cnmf_factorize(cnmf_dataset_t d, int n_restarts, const int32_t* ks, const uint32_t* seeds,
                    const cnmf_nmf_params* params, float* spectra_host, float* usages_host,
                    int32_t* n_iter_host, double* err_host, void* stream);
