@@ -75,6 +75,9 @@ SIGNATURES = {
 _lib = None
 
 
+ABI_VERSION = 2      # include/cnmf_b200.h CNMF_B200_ABI_VERSION
+
+
 def load():
     """Load the shared library (once) and attach the signatures. Fails loudly if it is missing."""
     global _lib
@@ -89,7 +92,7 @@ def load():
         fn = getattr(lib, name)        # AttributeError here = ABI mismatch: let it propagate
         fn.restype = res
         fn.argtypes = args
-    if lib.cnmf_abi_version() != 2:
+    if lib.cnmf_abi_version() != ABI_VERSION:
         raise CnmfError("libcnmf_b200.so ABI version mismatch")
     _lib = lib
     return lib
