@@ -110,6 +110,13 @@ def measured_peaks():
     return 1400.0 / 2.0, "fallback 1.4 PFLOP/s sustained bf16 / 2, of fallback"
 
 
+def measured_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy bandwidth), of measured"
+    return 6500.0, "fallback 6.5 TB/s copy bandwidth, of fallback"
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -215,7 +222,8 @@ def run_ours(args, rank, world, local):
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
-    gemm_ms, gemm_launches, gemm_flops = eng.profile_get()
+    gemm_ms, gemm_launches, gemm_flops = eng.profile_get(0)
+    upd_ms, upd_launches, upd_bytes = eng.profile_get(1)
     eng.profile(False)
     launches = eng.launch_count - launches0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -290,6 +298,8 @@ def run_ours(args, rank, world, local):
     except Exception as ex:          # never let the informational block break the bench line
         consensus = {"error": repr(ex)}
     peak, peak_src = measured_peaks()
+    hbm_peak, hbm_src = measured_hbm()
+    upd_gbs = upd_bytes / (upd_ms * 1e-3) / 1e9 if upd_ms > 0 else 0.0
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
@@ -313,6 +323,13 @@ def run_ours(args, rank, world, local):
                                  passes, gemm_launches, gemm_ms, ms, peak_src,
                                  "recognised as scaled integer counts -> exact B operand, 2 passes" if passes == 2
                                  else "general real matrix -> 3 passes")},
+        "roofline_update": {"bound": "hbm", "kernel": "update_kernel<16,mu> (multiplicative update fused with the Gram "
+                            "of the factor it writes)", "achieved": upd_gbs, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": upd_gbs / hbm_peak, "traffic": None,
+                            "note": "second kernel of the step: achieved = algorithmic bytes per launch (factor read + "
+                                    "product slices read + factor and 2 tf32 pieces written, x live rows x items x 4 B) / "
+                                    "CUDA-event launch time; %d launches, %.1f ms of %.1f ms timed; peak = %s" % (
+                                        upd_launches, upd_ms, ms, hbm_src)},
         "n_iter": {"mean": float(np.mean(n_iter)), "max": int(np.max(n_iter))},
         "consensus": consensus,
     }

@@ -44,6 +44,7 @@ SIGNATURES = {
     "cnmf_launch_count": (_ll, [_vp]),
     "cnmf_profile_enable": (_i, [_vp, _i]),
     "cnmf_profile_get": (_i, [_vp, _pp(_d), _pp(_ll), _pp(_d)]),
+    "cnmf_profile_get_class": (_i, [_vp, _i, _pp(_d), _pp(_ll), _pp(_d)]),
     "cnmf_last_timing": (_i, [_vp, _pp(_d), _pp(_d), _pp(_d), _pp(_d)]),
     "cnmf_dataset_create": (_i, [_vp, _vp, _i, _i, _ll, _i, _i, _vp, _pp(_vp)]),
     "cnmf_dataset_from_columns": (_i, [_vp, _vp, _vp, _i, _vp, _pp(_vp)]),
@@ -75,7 +76,7 @@ SIGNATURES = {
 _lib = None
 
 
-ABI_VERSION = 2      # include/cnmf_b200.h CNMF_B200_ABI_VERSION
+ABI_VERSION = 3      # include/cnmf_b200.h CNMF_B200_ABI_VERSION
 
 
 def load():

@@ -68,7 +68,7 @@ void* cnmf_handle_s::host_buf(const std::string& name, size_t bytes) {
   return e.first;
 }
 
-int cnmf_handle_s::prof_begin(cudaStream_t s, double flops) {
+int cnmf_handle_s::prof_begin(cudaStream_t s, double work, int cls) {
   if (!profile) return -1;
   while (ev_pool.size() < ev_used + 2) {
     cudaEvent_t e;
@@ -78,7 +78,7 @@ int cnmf_handle_s::prof_begin(cudaStream_t s, double flops) {
   const int slot = (int)ev_used;
   ev_used += 2;
   cudaEventRecord(ev_pool[slot], s);
-  ev_pending.emplace_back(slot, flops);
+  ev_pending.push_back(Pending{slot, cls, work});
   return slot;
 }
 
@@ -89,10 +89,10 @@ void cnmf_handle_s::prof_end(cudaStream_t s, int slot) {
 void cnmf_handle_s::prof_collect() {
   for (auto& pr : ev_pending) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ev_pool[pr.first], ev_pool[pr.first + 1]) == cudaSuccess) {
-      prof_gemm_ms += ms;
-      prof_gemm_flops += pr.second;
-      prof_gemm_launches += 1;
+    if (cudaEventElapsedTime(&ms, ev_pool[pr.slot], ev_pool[pr.slot + 1]) == cudaSuccess) {
+      prof_ms[pr.cls] += ms;
+      prof_work[pr.cls] += pr.work;
+      prof_launches[pr.cls] += 1;
     }
   }
   ev_pending.clear();
@@ -185,8 +185,10 @@ long long cnmf_launch_count(cnmf_handle_t h) { return h ? h->launches : 0; }
 int cnmf_profile_enable(cnmf_handle_t h, int on) {
   CNMF_REQUIRE(h, "profile_enable: NULL handle");
   h->profile = on != 0;
-  h->prof_gemm_ms = h->prof_gemm_flops = 0.0;
-  h->prof_gemm_launches = 0;
+  for (int c = 0; c < cnmf_handle_s::PROF_CLASSES; ++c) {
+    h->prof_ms[c] = h->prof_work[c] = 0.0;
+    h->prof_launches[c] = 0;
+  }
   h->ev_pending.clear();
   h->ev_used = 0;
   return 0;
@@ -194,9 +196,15 @@ int cnmf_profile_enable(cnmf_handle_t h, int on) {
 
 int cnmf_profile_get(cnmf_handle_t h, double* gemm_ms, long long* gemm_launches, double* gemm_flops) {
   CNMF_REQUIRE(h, "profile_get: NULL handle");
-  if (gemm_ms) *gemm_ms = h->prof_gemm_ms;
-  if (gemm_launches) *gemm_launches = h->prof_gemm_launches;
-  if (gemm_flops) *gemm_flops = h->prof_gemm_flops;
+  return cnmf_profile_get_class(h, 0, gemm_ms, gemm_launches, gemm_flops);
+}
+
+int cnmf_profile_get_class(cnmf_handle_t h, int cls, double* ms, long long* launches, double* work) {
+  CNMF_REQUIRE(h, "profile_get_class: NULL handle");
+  CNMF_REQUIRE(cls >= 0 && cls < cnmf_handle_s::PROF_CLASSES, "profile_get_class: unknown kernel class");
+  if (ms) *ms = h->prof_ms[cls];
+  if (launches) *launches = h->prof_launches[cls];
+  if (work) *work = h->prof_work[cls];
   return 0;
 }
 

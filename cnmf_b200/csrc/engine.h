@@ -13,20 +13,22 @@ struct cnmf_handle_s {
   int device = 0;
   int sm_count = 148;
   long long launches = 0;                       // kernels launched by this library (bench: gpu_launches)
-  // optional per-launch timing of the dominant kernel (the batched GEMM) with CUDA events on the
-  // launching stream; read back by bench.py for the roofline line
-  // auxiliary low-priority stream: the K x K Gram kernels of the MU iteration run here, under the GEMM that
-  // does not depend on them (one-warp blocks that fit beside the resident GEMM CTA)
+  // optional per-launch timing of the hot kernels (batched GEMM, fused update) with CUDA events on the
+  // launching stream; read back by bench.py for the roofline lines
+  // auxiliary stream + events (kept for experiments that co-schedule streaming kernels under a GEMM)
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_upd = nullptr, ev_gram = nullptr;
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
-  std::vector<std::pair<int, double>> ev_pending;   // (index of start event in ev_pool, flops)
+  struct Pending { int slot; int cls; double work; };   // slot = index of the start event in ev_pool
+  std::vector<Pending> ev_pending;
   size_t ev_used = 0;
-  double prof_gemm_ms = 0.0, prof_gemm_flops = 0.0;
-  long long prof_gemm_launches = 0;
+  // kernel classes: 0 = batched GEMM (work = algorithmic FLOPs), 1 = fused update kernels (work = algorithmic bytes)
+  static constexpr int PROF_CLASSES = 2;
+  double prof_ms[PROF_CLASSES] = {0.0, 0.0}, prof_work[PROF_CLASSES] = {0.0, 0.0};
+  long long prof_launches[PROF_CLASSES] = {0, 0};
   double t_rng_ms = 0, t_h2d_ms = 0, t_solve_ms = 0, t_d2h_ms = 0;   // host wall-clock phases of the last cnmf_factorize
-  int prof_begin(cudaStream_t s, double flops);    // records the start event; returns slot or -1
+  int prof_begin(cudaStream_t s, double work, int cls = 0);    // records the start event; returns slot or -1
   void prof_end(cudaStream_t s, int slot);
   void prof_collect();                              // after a stream sync: fold pending pairs into the totals
   std::map<std::string, std::pair<void*, size_t>> ws;   // named grow-only device buffers

@@ -433,7 +433,9 @@ void gemm_plan(int M, int N, int Kd, int sm_count, int* splits_out, int* bn_out)
   const int max_splits = std::max(1, std::min(32, total_kb / 8));
   double best = -1.0;
   int best_s = 1, best_bn = 256;
-  const int bn_lo = N <= 256 ? ((N + 15) / 16) * 16 : 192;
+  // narrow tiles (down to 128 columns; below that the accumulate warps, not the MMA chain, pace a tile) pay off
+  // when a compacted batch leaves less than one wave of 256-wide tiles
+  const int bn_lo = N <= 256 ? ((N + 15) / 16) * 16 : 128;
   const int bn_hi = N <= 256 ? bn_lo : 256;
   for (int s = 1; s <= max_splits; ++s) {
     const int se = gemm_effective_splits(Kd, s);

@@ -115,23 +115,38 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   int R = R0, SK = SK0;     // live slots / live packed rows
   const int kp = kmax <= 16 ? 16 : 32;
   // block granularity of the streaming kernels, fixed for the whole solve (partial buffers are sized by it)
-  // update kernels: 3 blocks/SM resident -> aim for >= 8 blocks per SM; Gram kernel: 1 block/SM resident and a
-  // fixed-cost block reduction -> long blocks, about two waves
-  const int cpb_r = pick_cols_per_block(v.n_r, R0, 2048, 256, 148 * 8), cpb_c = pick_cols_per_block(v.n_c, R0, 2048, 256, 148 * 8);
+  // update kernels: 3 blocks of 128 threads per SM resident, a block walks 1-4 tiles -> aim for >= 8 blocks per SM;
+  // stand-alone Gram kernel: 1 block/SM resident and a fixed-cost block reduction -> long blocks, about two waves
+  const int tile = upd_tile_cols(kp);
+  // the update kernels' chunking follows the number of LIVE restarts (re-planned after every compaction): with few
+  // restarts left a block should hold one tile, so that the work spreads over many SMs
+  int cpb_r = 0, cpb_c = 0, chunks_r = 0, chunks_c = 0;
+  auto plan_blocks = [&](int r_live) {
+    cpb_r = pick_cols_per_block(v.n_r, r_live, 4 * tile, tile, 148 * 8);
+    cpb_c = pick_cols_per_block(v.n_c, r_live, 4 * tile, tile, 148 * 8);
+    chunks_r = (v.n_r + cpb_r - 1) / cpb_r;
+    chunks_c = (v.n_c + cpb_c - 1) / cpb_c;
+  };
   const int gcpb_r = pick_cols_per_block(v.n_r, R0, 8192, 1024, 148 * 2), gcpb_c = pick_cols_per_block(v.n_c, R0, 8192, 1024, 148 * 2);
-  const int chunks_r = (v.n_r + cpb_r - 1) / cpb_r, chunks_c = (v.n_c + cpb_c - 1) / cpb_c;
-  const int chunks_max = std::max(chunks_r, chunks_c);
+  const int chunks_cap = std::max((v.n_r + tile - 1) / tile, (v.n_c + tile - 1) / tile);   // finest chunking possible
   const int gchunks_max = std::max((v.n_r + gcpb_r - 1) / gcpb_r, (v.n_c + gcpb_c - 1) / gcpb_c);
+  size_t fused_part_slots = 0;      // slot-indexed partials of the fused kernels: max over live counts of R * chunks
+  for (int r = 1; r <= R0; ++r) {
+    plan_blocks(r);
+    fused_part_slots = std::max(fused_part_slots, (size_t)r * std::max(chunks_r, chunks_c));
+  }
+  plan_blocks(R0);
+  const bool fuse = kp == 16;   // the update kernels emit the Gram of the factor they write (nmf_kernels.cu)
 
   // ---- workspace
   int* d_meta = static_cast<int*>(h->dev_buf("solve.meta", sizeof(int) * 8 * R0));
   double* d_state = static_cast<double*>(h->dev_buf("solve.state", sizeof(double) * 8 * R0));
   double* d_gram = static_cast<double*>(h->dev_buf("solve.gram", sizeof(double) * 2 * R0 * KMAX * KMAX));
-  // per-chunk Gram partials of each factor (consumed directly by the update kernels; finalised K x K
-  // matrices are only formed when a convergence check needs them)
-  const size_t gpart_elems = (size_t)R0 * std::max(gchunks_max, std::max((v.n_r + 1023) / 1024, (v.n_c + 1023) / 1024)) * kp * kp;
+  // per-block Gram partials of each factor (summed by the last block of the producing launch)
+  const size_t gpart_elems = std::max((size_t)R0 * std::max(gchunks_max, std::max((v.n_r + 1023) / 1024, (v.n_c + 1023) / 1024)),
+                                      fused_part_slots) * kp * kp;
   double* d_gram_part = static_cast<double*>(h->dev_buf("solve.gram_part", sizeof(double) * 2 * gpart_elems));
-  double* d_scal_part = static_cast<double*>(h->dev_buf("solve.scal_part", sizeof(double) * 2 * (size_t)R0 * chunks_max));
+  double* d_scal_part = static_cast<double*>(h->dev_buf("solve.scal_part", sizeof(double) * 2 * (size_t)R0 * chunks_cap));
   if (!d_meta || !d_state || !d_gram || !d_gram_part || !d_scal_part) return -2;
 
   GemmPlan plan_r, plan_c;   // plan_r: NUM_r = Fc * B_rows^T (reduce over n_c); plan_c: NUM_c = Fr * B_cols^T
@@ -174,6 +189,7 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   int* d_rid = d_meta + 2 * R0;    // [slots]
   int* d_done = d_meta + 3 * R0;   // [rid]
   int* d_niter = d_meta + 4 * R0;  // [rid]
+  int* d_ticket = d_meta + 5 * R0; // [rid] last-block tickets of the fused update kernels (self-resetting)
   auto upload_slots = [&]() -> int {
     std::vector<int> hm(3 * R0, 0);
     std::memcpy(hm.data(), s_off.data(), sizeof(int) * R);
@@ -184,7 +200,7 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     return 0;
   };
   CNMF_TRY(upload_slots());
-  CNMF_CUDA_CHECK(cudaMemsetAsync(d_done, 0, sizeof(int) * 2 * R0, s));
+  CNMF_CUDA_CHECK(cudaMemsetAsync(d_done, 0, sizeof(int) * 3 * R0, s));   // done, n_iter, tickets
   CNMF_CUDA_CHECK(cudaMemsetAsync(d_state, 0, sizeof(double) * 8 * R0, s));
   ConvState st{d_state, d_state + R0, d_state + 2 * R0, d_done, d_niter};
   double* d_crossA = d_state + 3 * R0;   // finalised scalars: cross / violation of the row half
@@ -192,10 +208,9 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   double* d_gramR = d_gram;                            // Gram of Fr (e.g. W^T W), by rid
   double* d_gramC = d_gram + (size_t)R0 * KMAX * KMAX; // Gram of Fc (e.g. H H^T), by rid
   double* d_scalA = d_scal_part;
-  double* d_scalB = d_scal_part + (size_t)R0 * chunks_max;
+  double* d_scalB = d_scal_part + (size_t)R0 * chunks_cap;
   double* d_gpartR = d_gram_part;                      // partials of Gram(Fr)
   double* d_gpartC = d_gram_part + gpart_elems;        // partials of Gram(Fc)
-  int gchR = 1, gchC = 1;                              // chunk counts of the partials currently stored
 
   // working factor arrays (start in the caller's buffers; compaction ping-pongs to "solve.alt.*")
   float *wFr = io.Fr, *wFr_hi = io.Fr_hi, *wFr_lo = io.Fr_lo, *wFc = io.Fc, *wFc_hi = io.Fc_hi, *wFc_lo = io.Fc_lo;
@@ -212,41 +227,40 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     if (!io.update_cols) { f.F_hi = nullptr; f.F_lo = nullptr; }   // never rewritten
     return f;
   };
-  // side: 0 = row factor Fr, 1 = column factor Fc.  Writes the per-chunk partials only.
-  auto gram_of = [&](const FactorView& f, double* /*unused*/, int side_is_c) -> int {
-    h->launches += 1;
-    double* part = side_is_c ? d_gpartC : d_gpartR;
-    (side_is_c ? gchC : gchR) = gram_chunks(f);
-    return launch_gram_partial(f, bm(), part, s);
-  };
-  auto gref_R = [&]() { return GramRef{d_gpartR, gchR, kp * kp}; };
-  auto gref_C = [&]() { return GramRef{d_gpartC, gchC, kp * kp}; };
-  auto finalize_grams = [&](const BatchMeta& m) -> int {   // K x K matrices for the error / check kernels
+  // side: 0 = row factor Fr, 1 = column factor Fc.  Stand-alone Gram: partial launch + finalize (initial factors,
+  // fixed factors of a refit, batches with K > 16).
+  auto gram_full = [&](const FactorView& f, int side_is_c) -> int {
     h->launches += 2;
-    CNMF_TRY(launch_finalize(d_gpartR, d_gramR, nullptr, nullptr, gchR, m, s));
-    return launch_finalize(d_gpartC, d_gramC, nullptr, nullptr, gchC, m, s);
+    double* part = side_is_c ? d_gpartC : d_gpartR;
+    CNMF_TRY(launch_gram_partial(f, bm(), part, s));
+    return launch_finalize(part, side_is_c ? d_gramC : d_gramR, nullptr, nullptr, gram_chunks(f), bm(), s);
   };
-  // Overlapped form (MU iteration): the Gram of a freshly updated factor is not needed by the GEMM that follows
-  // the update, only by the update after it.  Run it on the auxiliary stream in one-warp blocks (they fit beside
-  // the resident GEMM CTA: 8 K registers, 2 KB smem) and join before the consumer.  Opt-in (CNMF_OVERLAP=1):
-  // measured +4 % restarts/s on c2 but the co-running Gram slows the GEMM itself by ~11 %, which muddies the
-  // per-kernel roofline measurement, so the default keeps one kernel at a time on the device.
-  static const bool overlap_env = [] { const char* e = std::getenv("CNMF_OVERLAP"); return e && e[0] == '1'; }();
-  const bool overlap = overlap_env && mu && io.update_cols && h->aux && h->ev_upd && h->ev_gram;
-  const int gcpb_small = 1024;
-  auto gram_async = [&](FactorView f, double* /*unused*/, int side_is_c) -> int {   // enqueue on aux after everything on s so far
-    f.gcpb = gcpb_small;
-    CNMF_CUDA_CHECK(cudaEventRecord(h->ev_upd, s));
-    CNMF_CUDA_CHECK(cudaStreamWaitEvent(h->aux, h->ev_upd, 0));
+  auto gram_after = [&](const FactorView& f, int side_is_c) -> int {   // Gram of a factor the update kernel just wrote
+    return fuse ? 0 : gram_full(f, side_is_c);
+  };
+  // algorithmic bytes of one update launch: factor read, product slices read, factor (+ tf32 pieces) written
+  auto upd_bytes = [&](int n_items, int nsplit, bool pieces) {
+    return 4.0 * (double)SK * (double)n_items * (double)(2 + nsplit + (pieces ? 2 : 0));
+  };
+  auto update = [&](bool cd, const FactorView& f, const float* NUM, const GemmPlan& pl, const double* gram_in, float l1,
+                    float l2, const FusedOut& out) -> int {
     h->launches += 1;
-    (side_is_c ? gchC : gchR) = gram_chunks(f);
-    CNMF_TRY(launch_gram_partial(f, bm(), side_is_c ? d_gpartC : d_gpartR, h->aux, true));
-    CNMF_CUDA_CHECK(cudaEventRecord(h->ev_gram, h->aux));
-    return 0;
+    const int slot = h->prof_begin(s, upd_bytes(f.n, pl.splits, f.F_hi != nullptr), 1);
+    const int rc = cd ? launch_cd_update(f, NUM, pl.splits, pl.split_stride, gram_in, bm(), l1, l2, out, s)
+                      : launch_mu_update(f, NUM, pl.splits, pl.split_stride, gram_in, bm(), l1, l2, out, s);
+    h->prof_end(s, slot);
+    return rc;
   };
-  auto gram_join = [&]() -> int {                                    // s waits for the last gram_async
-    CNMF_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_gram, 0));
-    return 0;
+  auto fused_out = [&](int side_is_c, bool want_gram, double* scal_part, double* scal) {
+    FusedOut o{};
+    if (want_gram && fuse) {
+      o.gram_part = side_is_c ? d_gpartC : d_gpartR;
+      o.gram = side_is_c ? d_gramC : d_gramR;
+    }
+    o.scal_part = scal_part;
+    o.scal = scal;
+    o.counter = d_ticket;
+    return o;
   };
   auto finalize_scal = [&](const double* part, double* out, int chunks) -> int {
     h->launches += 1;
@@ -294,11 +308,10 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     CNMF_CUDA_CHECK(cudaMemsetAsync(d_zero, 0, sizeof(int) * 2 * R0, s));
     BatchMeta bm0{d_off, d_k, d_rid, d_zero, R, kp};
     h->launches += 7;
-    gchR = gram_chunks(fr());
-    gchC = gram_chunks(fc());
     CNMF_TRY(launch_gram_partial(fr(), bm0, d_gpartR, s));
     CNMF_TRY(launch_gram_partial(fc(), bm0, d_gpartC, s));
-    CNMF_TRY(finalize_grams(bm0));
+    CNMF_TRY(launch_finalize(d_gpartR, d_gramR, nullptr, nullptr, gram_chunks(fr()), bm0, s));
+    CNMF_TRY(launch_finalize(d_gpartC, d_gramC, nullptr, nullptr, gram_chunks(fc()), bm0, s));
     if (io.update_cols) {
       CNMF_TRY(launch_cross(fc(), NUMc, plan_c.splits, plan_c.split_stride, bm0, d_scalB, s));
       CNMF_TRY(launch_finalize(nullptr, nullptr, d_scalB, d_crossB, chunks_c, bm0, s));
@@ -368,6 +381,7 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     CNMF_TRY(upload_slots());      // synchronises the stream: the gather ring can be reused
     gslot = 0;
     plan_gemms();
+    plan_blocks(R);
     compacted = true;
     return 0;
   };
@@ -385,9 +399,8 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
 
   if (mu) {
     // ---------------- multiplicative update (sklearn _nmf.py:726-888) ----------------
-    CNMF_TRY(gram_of(fc(), d_gramC, 1));
-    CNMF_TRY(gram_of(fr(), d_gramR, 0));
-    CNMF_TRY(finalize_grams(bm()));
+    CNMF_TRY(gram_full(fc(), 1));
+    CNMF_TRY(gram_full(fr(), 0));
     if (io.update_cols) {
       CNMF_TRY(gemm_cols());
       h->launches += 1;
@@ -402,36 +415,22 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     h->launches += 1;
     CNMF_TRY(launch_mu_check(st, d_crossB, d_gramR, d_gramC, normX2, bm(), 0, p.tol, p.max_iter, s));
 
+    // one iteration = GEMM, update(+Gram), GEMM, update(+Gram): the update kernels leave the finalised Gram of the
+    // factor they wrote (and, at check iterations, <NUM, F>) behind, so nothing else sits between the GEMMs
     for (it = 1; it <= p.max_iter; ++it) {
-      if (io.update_cols) CNMF_TRY(gemm_rows());                    // overlaps gram(Fc) of the previous iteration
-      if (overlap && it > 1) CNMF_TRY(gram_join());                 // update of Fr needs Gram(Fc)
-      h->launches += 1;
-      CNMF_TRY(launch_mu_update(fr(), NUMr, plan_r.splits, plan_r.split_stride, gref_C(), bm(), l1W, l2W,
-                                io.update_cols ? nullptr : d_scalA, s));
-      if (io.update_cols) {
-        if (overlap) {
-          CNMF_TRY(gram_async(fr(), d_gramR, 0));                   // runs under gemm_cols
-          CNMF_TRY(gemm_cols());
-          CNMF_TRY(gram_join());                                    // update of Fc needs Gram(Fr)
-        } else {
-          CNMF_TRY(gram_of(fr(), d_gramR, 0));
-          CNMF_TRY(gemm_cols());
-        }
-        h->launches += 1;
-        CNMF_TRY(launch_mu_update(fc(), NUMc, plan_c.splits, plan_c.split_stride, gref_R(), bm(), l1H, l2H, d_scalB, s));
-        if (overlap) CNMF_TRY(gram_async(fc(), d_gramC, 1));        // runs under the next gemm_rows
-        else CNMF_TRY(gram_of(fc(), d_gramC, 1));
-      }
       const bool check = (p.tol > 0 && it % 10 == 0) || it == p.max_iter;
+      if (io.update_cols) {
+        CNMF_TRY(gemm_rows());
+        CNMF_TRY(update(false, fr(), NUMr, plan_r, d_gramC, l1W, l2W, fused_out(0, true, nullptr, nullptr)));
+        CNMF_TRY(gram_after(fr(), 0));
+        CNMF_TRY(gemm_cols());
+        CNMF_TRY(update(false, fc(), NUMc, plan_c, d_gramR, l1H, l2H, fused_out(1, true, check ? d_scalB : nullptr, d_crossB)));
+        CNMF_TRY(gram_after(fc(), 1));
+      } else {
+        CNMF_TRY(update(false, fr(), NUMr, plan_r, d_gramC, l1W, l2W, fused_out(0, check, check ? d_scalA : nullptr, d_crossB)));
+        if (check) CNMF_TRY(gram_after(fr(), 0));
+      }
       if (check) {
-        if (overlap) CNMF_TRY(gram_join());                         // the error needs both Grams
-        if (io.update_cols) {
-          CNMF_TRY(finalize_scal(d_scalB, d_crossB, chunks_c));
-        } else {
-          CNMF_TRY(gram_of(fr(), d_gramR, 0));
-          CNMF_TRY(finalize_scal(d_scalA, d_crossB, chunks_r));
-        }
-        CNMF_TRY(finalize_grams(bm()));
         h->launches += 1;
         // at it == max_iter with it % 10 != 0 sklearn does not test; tol = -1 makes the test never fire
         const double tol_eff = (p.tol > 0 && it % 10 == 0) ? p.tol : -1.0;
@@ -441,24 +440,18 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
         if (all) break;
       }
     }
-    if (overlap) CNMF_CUDA_CHECK(cudaStreamSynchronize(h->aux));
   } else {
     // ---------------- coordinate descent (sklearn _nmf.py:399-518, shuffle=False) ----------------
     const int poll_every = 4;
     for (it = 1; it <= p.max_iter; ++it) {
-      if (io.update_cols || it == 1) {
-        CNMF_TRY(gram_of(fc(), d_gramC, 1));
-        CNMF_TRY(gemm_rows());
-      }
-      h->launches += 1;
-      CNMF_TRY(launch_cd_update(fr(), NUMr, plan_r.splits, plan_r.split_stride, gref_C(), bm(), l1W, l2W, d_scalA, s));
-      CNMF_TRY(finalize_scal(d_scalA, d_crossA, chunks_r));
+      if (it == 1) CNMF_TRY(gram_full(fc(), 1));     // afterwards: left behind by the sweep over Fc
+      if (io.update_cols || it == 1) CNMF_TRY(gemm_rows());
+      CNMF_TRY(update(true, fr(), NUMr, plan_r, d_gramC, l1W, l2W, fused_out(0, io.update_cols, d_scalA, d_crossA)));
       if (io.update_cols) {
-        CNMF_TRY(gram_of(fr(), d_gramR, 0));
+        CNMF_TRY(gram_after(fr(), 0));
         CNMF_TRY(gemm_cols());
-        h->launches += 1;
-        CNMF_TRY(launch_cd_update(fc(), NUMc, plan_c.splits, plan_c.split_stride, gref_R(), bm(), l1H, l2H, d_scalB, s));
-        CNMF_TRY(finalize_scal(d_scalB, d_crossB, chunks_c));
+        CNMF_TRY(update(true, fc(), NUMc, plan_c, d_gramR, l1H, l2H, fused_out(1, true, d_scalB, d_crossB)));
+        CNMF_TRY(gram_after(fc(), 1));
       }
       h->launches += 1;
       CNMF_TRY(launch_cd_check(st, d_crossA, io.update_cols ? d_crossB : nullptr, bm(), it, p.tol, p.max_iter, s));

@@ -169,118 +169,394 @@ __global__ void sums_final_kernel(const double* __restrict__ part, int nblocks, 
   }
 }
 
-// ------------------------------------------------------------------ update kernels
-// Thread = one item (cell / gene) column of one restart.  The unrolled K x K work is instantiated at a
-// granularity of 4 components (KP = K rounded up to a multiple of 4) and dispatched per restart INSIDE the
-// kernel (block-uniform switch), so a K = 10 restart runs the 12 x 12 body even when the batch also holds
-// K = 13 restarts.  KPMAX (16 or 32, from the batch maximum) only bounds which bodies exist, i.e. the
-// kernel's register budget: 80 registers / 3 blocks per SM for KPMAX = 16.  The K x K Gram is re-read
-// from shared memory for every column through a volatile pointer (broadcast LDS.128) instead of being
-// hoisted into ~256 registers (that version ran at ~1 TB/s).
-__device__ __forceinline__ void load_gram_smem(float* G, const GramRef& gram, int r, int K, int KP, float diag_add) {
+// ------------------------------------------------------------------ update kernels (fused with the Gram)
+// Thread = VEC consecutive items (cells / genes) of one restart, held as packed fp32 pairs: every array is
+// touched with one 16-byte (VEC = 4) access per component, and the K x K contraction with the Gram of the
+// other factor runs on FFMA2 (two items per instruction, the Gram entry a broadcast operand read from shared
+// memory as LDS.128 = 4 entries x 2 pairs = 8 packed FMAs per shared-memory instruction).  The quotient is
+// the branch-free MUFU.RCP + Newton sequence of common.cuh.  The unrolled body is instantiated per K rounded
+// up to 4 and dispatched per restart inside the kernel (block-uniform switch), so a K = 10 restart runs the
+// 12 x 12 body even when the batch also holds K = 13 restarts.
+//
+// The Gram of the UPDATED factor (needed by the next half-iteration's update and by the trace-form error) is
+// accumulated in the same launch: the block parks its new values in a shared-memory tile (components x
+// tile columns), the warps split the K x K entries by rows and walk the tile with packed FMAs, per-thread
+// fp32 sums over at most 16 columns go through shared memory into per-block fp64 sums (fixed order), and the
+// last block of a restart adds the per-block partials in chunk order (FusedOut).  The first version -- a scalar
+// thread-per-item update (1 052 warp instructions per item at K = 10: 4-byte accesses, 3-register FFMA,
+// IEEE division) plus a separate Gram launch re-reading the factor -- spent 168 us per W half at c2 against 107 us
+// of DRAM time; see profiles/r1e_ncu_full_summary.txt.
+template <int VEC> struct VecIO;
+template <> struct VecIO<4> {
+  static constexpr int NP = 2;
+  static __device__ __forceinline__ void ld(const float* p, float2 (&v)[2]) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = make_float2(q.x, q.y);
+    v[1] = make_float2(q.z, q.w);
+  }
+  static __device__ __forceinline__ void st(float* p, const float2 (&v)[2]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+  }
+};
+template <> struct VecIO<2> {
+  static constexpr int NP = 1;
+  static __device__ __forceinline__ void ld(const float* p, float2 (&v)[1]) { v[0] = *reinterpret_cast<const float2*>(p); }
+  static __device__ __forceinline__ void st(float* p, const float2 (&v)[1]) { *reinterpret_cast<float2*>(p) = v[0]; }
+};
+
+constexpr float FLT_MIN_NORMAL = 1.17549435e-38f;
+// KPMAX x TILE is 16 x 512 = 32 x 256 = 8192 floats for both kernel families; the Gram scratch needs
+// UPD_THREADS x 68 = 8704 floats (FusedGramCfg<16>::STRIDE)
+constexpr int UPD_TILE_N_FLOATS = 8192;
+constexpr int UPD_TILE_F_FLOATS = 8192 + 1024;
+
+// finalised Gram of the other factor -> shared memory (KP x KP fp32, zero beyond K), + diag_add on the diagonal
+__device__ __forceinline__ void load_gram_smem(float* G, const double* __restrict__ gram_in, int r, int K, int KP,
+                                               float diag_add) {
+  const double* g = gram_in + (long long)r * KMAX * KMAX;
   for (int idx = threadIdx.x; idx < KP * KP; idx += blockDim.x) {
     const int c = idx / KP, i = idx % KP;
-    double a = 0.0;
-    if (c < K && i < K) {
-      const double* p = gram.part + (long long)r * gram.chunks * gram.stride + idx;
-      for (int ch = 0; ch < gram.chunks; ++ch) a += p[(long long)ch * gram.stride];    // fixed order: deterministic
-    }
-    float g = (float)a;
-    if (c == i && c < K) g += diag_add;
-    G[idx] = g;
+    float v = (c < K && i < K) ? (float)g[c * KMAX + i] : 0.f;
+    if (c == i && c < K) v += diag_add;
+    G[idx] = v;
   }
-  __syncthreads();
 }
 
-template <int KP>
-__device__ __forceinline__ void load_column(const FactorView& f, const float* __restrict__ NUM, int nsplit,
-                                            long long sstride, int K, int o, int col, float (&fv)[KP], float (&nv)[KP]) {
-  // all loads of this column first (2K independent requests in flight per thread)
+// A thread's VEC items of one array: base pointer of component 0 plus a 32-bit element offset per component
+// (one IMAD.WIDE per access instead of a 64-bit multiply-add chain)
+template <int KP, int VEC>
+__device__ __forceinline__ void load_items(const float* __restrict__ pF, const float* __restrict__ pN, int nsplit,
+                                           long long sstride, int K, unsigned ld, int n_left,
+                                           float2 (&fv)[KP][VecIO<VEC>::NP], float2 (&nv)[KP][VecIO<VEC>::NP]) {
+  constexpr int NP = VecIO<VEC>::NP;
+  // all loads of this item group first (2K independent 16-byte requests in flight per thread)
 #pragma unroll
   for (int i = 0; i < KP; ++i) {
-    const long long e = (long long)(o + i) * f.ld + col;
-    fv[i] = (i < K) ? f.F[e] : 0.f;
-    float num = (i < K) ? NUM[e] : 0.f;
-    for (int s = 1; s < nsplit; ++s) num += (i < K) ? NUM[s * sstride + e] : 0.f;
-    nv[i] = num;
-  }
-}
-
-__device__ __forceinline__ void store_elem(const FactorView& f, long long e, float v, float pscale) {
-  f.F[e] = v;
-  if (f.F_hi) {
-    float h, l;
-    split_tf32(v * pscale, h, l);
-    f.F_hi[e] = h;
-    f.F_lo[e] = l;
-  }
-}
-
-template <int KP>
-__device__ __forceinline__ double mu_body(const FactorView& f, const float* __restrict__ NUM, int nsplit, long long sstride,
-                                          const float* G, int K, int o, float l1, float l2, int col_begin, int col_end,
-                                          bool want_cross) {
-  const volatile float4* Gv = reinterpret_cast<const volatile float4*>(G);
-  double cross = 0.0;
-  for (int col = col_begin + threadIdx.x; col < col_end; col += UPD_THREADS) {
-    float fv[KP], nv[KP];
-    load_column<KP>(f, NUM, nsplit, sstride, K, o, col, fv, nv);
-    const float pscale = f.piece_scale ? f.piece_scale[col] : 1.f;
+    if (i < K) {
+      const unsigned off = (unsigned)i * ld;
+      VecIO<VEC>::ld(pF + off, fv[i]);
+      VecIO<VEC>::ld(pN + off, nv[i]);
+    } else {
 #pragma unroll
-    for (int c = 0; c < KP; ++c) {
-      if (c < K) {
-        float den = 0.f;
+      for (int p = 0; p < NP; ++p) {
+        fv[i][p] = make_float2(0.f, 0.f);
+        nv[i][p] = make_float2(0.f, 0.f);
+      }
+    }
+  }
+  if (nsplit > 1) {                                  // split-K slices, added in slice order
+    for (int s = 1; s < nsplit; ++s) {
+      const float* pS = pN + s * sstride;
+#pragma unroll
+      for (int i = 0; i < KP; ++i) {
+        if (i < K) {
+          float2 t[NP];
+          VecIO<VEC>::ld(pS + (unsigned)i * ld, t);
+#pragma unroll
+          for (int p = 0; p < NP; ++p) nv[i][p] = add2(nv[i][p], t[p]);
+        }
+      }
+    }
+  }
+  if (n_left < VEC) {                                // ragged tail: product columns >= n are not defined
+#pragma unroll
+    for (int i = 0; i < KP; ++i)
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        if (2 * p >= n_left) { nv[i][p].x = 0.f; fv[i][p].x = 0.f; }
+        if (2 * p + 1 >= n_left) { nv[i][p].y = 0.f; fv[i][p].y = 0.f; }
+      }
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_items(float* pF, float* pH, float* pL, unsigned off,
+                                            const float2 (&v)[VecIO<VEC>::NP], const float2 (&pscale)[VecIO<VEC>::NP]) {
+  constexpr int NP = VecIO<VEC>::NP;
+  VecIO<VEC>::st(pF + off, v);
+  if (pH) {
+    float2 h[NP], l[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const float2 sv = mul2(v[p], pscale[p]);
+      h[p] = make_float2(to_tf32(sv.x), to_tf32(sv.y));
+      const float2 rest = add2(sv, neg2(h[p]));
+      l[p] = make_float2(to_tf32(rest.x), to_tf32(rest.y));
+    }
+    VecIO<VEC>::st(pH + off, h);
+    VecIO<VEC>::st(pL + off, l);
+  }
+}
+
+// per-KP partition of the fused Gram: TPC warps split the K x K entries by rows (RB rows each), the warps
+// that share a row block split the tile's column pairs
+template <int KP> struct FusedGramCfg {
+  static constexpr int WARPS = UPD_THREADS / 32;
+  static constexpr int TPC = KP <= 4 ? 1 : (KP <= 8 ? 2 : 4);
+  static constexpr int RB = KP / TPC;
+  static constexpr int NG = WARPS / TPC;                      // warps per row block
+  static constexpr int VALS = RB * KP;                        // sums per thread
+  static constexpr int STRIDE = (VALS / 4) % 2 ? VALS : VALS + 4;   // odd number of 16-byte units: conflict-free STS.128
+};
+
+// tile: KP x TILE fp32 (new factor values of this pass, zero rows beyond K); gsum[KP*KP] += Gram of the tile.
+// `scratch` aliases the tile (it is consumed before it is overwritten).
+template <int KP, int TILE>
+__device__ __forceinline__ void fused_gram_tile(float* tile, double* gsum) {
+  using C = FusedGramCfg<KP>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rb = warp % C::TPC, grp = warp / C::TPC;
+  float2 acc[C::RB][KP];
+#pragma unroll
+  for (int a = 0; a < C::RB; ++a)
+#pragma unroll
+    for (int i = 0; i < KP; ++i) acc[a][i] = make_float2(0.f, 0.f);
+  const float4* t4 = reinterpret_cast<const float4*>(tile);
+  constexpr int QUADS = TILE / 4, ROW4 = TILE / 4;
+#pragma unroll 1
+  for (int q = grp * 32 + lane; q < QUADS; q += 32 * C::NG) {    // 4 columns = two packed pairs per LDS.128
+    float4 v[KP], va[C::RB];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) v[i] = t4[i * ROW4 + q];
+#pragma unroll
+    for (int a = 0; a < C::RB; ++a) va[a] = t4[(rb * C::RB + a) * ROW4 + q];
+#pragma unroll
+    for (int a = 0; a < C::RB; ++a)
+#pragma unroll
+      for (int i = 0; i < KP; ++i) {
+        acc[a][i] = fma2(make_float2(va[a].x, va[a].y), make_float2(v[i].x, v[i].y), acc[a][i]);
+        acc[a][i] = fma2(make_float2(va[a].z, va[a].w), make_float2(v[i].z, v[i].w), acc[a][i]);
+      }
+  }
+  __syncthreads();                                            // every warp is done reading the tile
+  float* scratch = tile + threadIdx.x * C::STRIDE;
+#pragma unroll
+  for (int a = 0; a < C::RB; ++a)
+#pragma unroll
+    for (int i4 = 0; i4 < KP / 4; ++i4) {
+      float4 q;
+      q.x = acc[a][4 * i4 + 0].x + acc[a][4 * i4 + 0].y;
+      q.y = acc[a][4 * i4 + 1].x + acc[a][4 * i4 + 1].y;
+      q.z = acc[a][4 * i4 + 2].x + acc[a][4 * i4 + 2].y;
+      q.w = acc[a][4 * i4 + 3].x + acc[a][4 * i4 + 3].y;
+      *reinterpret_cast<float4*>(scratch + a * KP + 4 * i4) = q;
+    }
+  __syncthreads();
+  for (int e = threadIdx.x; e < KP * KP; e += UPD_THREADS) {  // entry (row, i): fixed-order fp64 sum over its threads
+    const int row = e / KP, i = e % KP;
+    const int erb = row / C::RB, a = row % C::RB;
+    double sum = 0.0;
+#pragma unroll
+    for (int g = 0; g < C::NG; ++g) {
+      const float* src = tile + (size_t)((erb + C::TPC * g) * 32) * C::STRIDE + a * KP + i;
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) sum += (double)src[l * C::STRIDE];
+    }
+    gsum[e] += sum;
+  }
+  __syncthreads();                                            // scratch (= tile) free again
+}
+
+// Multiplicative update, rolled over the components: the thread's old values stay in registers for the K x K
+// contraction (static indices), while the two values that are addressed by the loop variable -- F[c] and NUM[c] of
+// the thread's items -- are read back from the shared-memory tiles the load phase parked them in (tileF doubles as
+// the Gram tile: row c is overwritten with the new values once iteration c is done with it).  One compact loop
+// body (~80 instructions) instead of K unrolled copies: no per-component predicates for K < KP, and the code
+// stays resident in the instruction cache (the unrolled version stalled on instruction fetch, profiles/r1g_*).
+// Returns <NUM, F_new> over the thread's items (fp32 within a tile, fp64 across tiles).
+template <int KP, int VEC, bool GRAM>
+__device__ __forceinline__ double mu_body(const FactorView& f, const float* __restrict__ NUM, int nsplit,
+                                          long long sstride, const float* G, int K, int o, float l1, float l2,
+                                          int col_begin, int col_end, float* tileF, float* tileN, double* gsum) {
+  constexpr int NP = VecIO<VEC>::NP;
+  constexpr int TILE = UPD_THREADS * VEC;
+  const float4* G4 = reinterpret_cast<const float4*>(G);
+  const unsigned ld = (unsigned)f.ld;
+  float* const myF = tileF + VEC * threadIdx.x;
+  float* const myN = tileN + VEC * threadIdx.x;
+  double scal = 0.0;
+#pragma unroll 1
+  for (int t0 = col_begin; t0 < col_end; t0 += TILE) {
+    const int col = t0 + VEC * threadIdx.x;
+    if (col < col_end) {
+      const long long e0 = (long long)o * f.ld + col;
+      float* const pF = f.F + e0;
+      float* const pH = f.F_hi ? f.F_hi + e0 : nullptr;
+      float* const pL = f.F_hi ? f.F_lo + e0 : nullptr;
+      float2 fv[KP][NP];
+      {
+        float2 nv[KP][NP];
+        load_items<KP, VEC>(pF, NUM + e0, nsplit, sstride, K, ld, f.n - col, fv, nv);
+#pragma unroll
+        for (int i = 0; i < KP; ++i) {               // rows >= K hold zeros (load_items): the Gram tile needs them
+          VecIO<VEC>::st(myF + i * TILE, fv[i]);
+          VecIO<VEC>::st(myN + i * TILE, nv[i]);
+        }
+      }
+      float2 pscale[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) pscale[p] = make_float2(1.f, 1.f);
+      if (f.piece_scale) VecIO<VEC>::ld(f.piece_scale + col, pscale);
+      float2 sacc = make_float2(0.f, 0.f);
+      unsigned off = 0;
+#pragma unroll 1
+      for (int c = 0; c < K; ++c, off += ld) {
+        float2 den[NP];                              // summed in component order, like the reference's W @ HHt row
 #pragma unroll
         for (int i4 = 0; i4 < KP / 4; ++i4) {
-          const volatile float4& gq = Gv[c * (KP / 4) + i4];
-          den = fmaf(gq.x, fv[4 * i4 + 0], den);
-          den = fmaf(gq.y, fv[4 * i4 + 1], den);
-          den = fmaf(gq.z, fv[4 * i4 + 2], den);
-          den = fmaf(gq.w, fv[4 * i4 + 3], den);
+          const float4 gq = G4[c * (KP / 4) + i4];
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            den[p] = i4 == 0 ? mul2(bcast2(gq.x), fv[0][p]) : fma2(bcast2(gq.x), fv[4 * i4 + 0][p], den[p]);
+            den[p] = fma2(bcast2(gq.y), fv[4 * i4 + 1][p], den[p]);
+            den[p] = fma2(bcast2(gq.z), fv[4 * i4 + 2][p], den[p]);
+            den[p] = fma2(bcast2(gq.w), fv[4 * i4 + 3][p], den[p]);
+          }
         }
-        if (l1 > 0.f) den += l1;
-        if (l2 > 0.f) den += l2 * fv[c];
-        if (den == 0.f) den = EPSILON_F32;
-        const float fn = fv[c] * (nv[c] / den);
-        store_elem(f, (long long)(o + c) * f.ld + col, fn, pscale);
-        if (want_cross) cross += (double)nv[c] * (double)fn;
+        float2 fvc[NP], nvc[NP], out[NP];
+        VecIO<VEC>::ld(myF + c * TILE, fvc);
+        VecIO<VEC>::ld(myN + c * TILE, nvc);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          // regularisation terms unconditionally: adding l1 = 0 and l2 * F = 0 is exact, a uniform branch costs more
+          const float2 d0 = fma2(bcast2(l2), fvc[p], add2(den[p], bcast2(l1)));
+          float2 d = d0;
+          // zero denominators -> eps (sklearn _nmf.py:615,701); the Newton quotient needs a normal number
+          d.x = (d.x < FLT_MIN_NORMAL) ? EPSILON_F32 : d.x;
+          d.y = (d.y < FLT_MIN_NORMAL) ? EPSILON_F32 : d.y;
+          out[p] = mul2(fvc[p], div_nr2(nvc[p], d));
+          sacc = fma2(nvc[p], out[p], sacc);
+        }
+        store_items<VEC>(pF, pH, pL, off, out, pscale);
+        if constexpr (GRAM) VecIO<VEC>::st(myF + c * TILE, out);
       }
+      scal += (double)(sacc.x + sacc.y);
+    } else if constexpr (GRAM) {
+      float2 z[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) z[p] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < KP; ++c) VecIO<VEC>::st(myF + c * TILE, z);
+    }
+    if constexpr (GRAM) {
+      __syncthreads();
+      fused_gram_tile<KP, TILE>(tileF, gsum);
     }
   }
-  return cross;
+  return scal;
 }
 
-template <int KP>
-__device__ __forceinline__ double cd_body(const FactorView& f, const float* __restrict__ NUM, int nsplit, long long sstride,
-                                          const float* G, int K, int o, float l1, int col_begin, int col_end) {
+// MU: returns <NUM, F_new> over the thread's items (fp32 within a tile, fp64 across tiles).
+// CD: returns sum |projected gradient|.
+template <int KP, int VEC, bool CD, bool GRAM>
+__device__ __forceinline__ double update_body(const FactorView& f, const float* __restrict__ NUM, int nsplit,
+                                              long long sstride, const float* G, int K, int o, float l1, float l2,
+                                              int col_begin, int col_end, float* tile, double* gsum) {
+  constexpr int NP = VecIO<VEC>::NP;
+  constexpr int TILE = UPD_THREADS * VEC;
   const volatile float4* Gv = reinterpret_cast<const volatile float4*>(G);
   const volatile float* Gs = G;
-  double viol = 0.0;
-  for (int col = col_begin + threadIdx.x; col < col_end; col += UPD_THREADS) {
-    float fv[KP], nv[KP];
-    load_column<KP>(f, NUM, nsplit, sstride, K, o, col, fv, nv);
-    const float pscale = f.piece_scale ? f.piece_scale[col] : 1.f;
+  const unsigned ld = (unsigned)f.ld;
+  double scal = 0.0;
+#pragma unroll 1
+  for (int t0 = col_begin; t0 < col_end; t0 += TILE) {
+    const int col = t0 + VEC * threadIdx.x;
+    if (col < col_end) {
+      const long long e0 = (long long)o * f.ld + col;
+      float* const pF = f.F + e0;
+      float* const pH = f.F_hi ? f.F_hi + e0 : nullptr;
+      float* const pL = f.F_hi ? f.F_lo + e0 : nullptr;
+      float2 fv[KP][NP], nv[KP][NP];
+      load_items<KP, VEC>(pF, NUM + e0, nsplit, sstride, K, ld, f.n - col, fv, nv);
+      float2 pscale[NP];
 #pragma unroll
-    for (int t = 0; t < KP; ++t) {
-      if (t < K) {
-        float g = l1 - nv[t];                           // -(XHt - l1), sklearn _nmf.py:386-388
+      for (int p = 0; p < NP; ++p) pscale[p] = make_float2(1.f, 1.f);
+      if (f.piece_scale) VecIO<VEC>::ld(f.piece_scale + col, pscale);
+      float2 sacc = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i4 = 0; i4 < KP / 4; ++i4) {           // same summation order as the Cython loop (r = 0..K-1)
-          const volatile float4& gq = Gv[t * (KP / 4) + i4];
-          g = fmaf(gq.x, fv[4 * i4 + 0], g);
-          g = fmaf(gq.y, fv[4 * i4 + 1], g);
-          g = fmaf(gq.z, fv[4 * i4 + 2], g);
-          g = fmaf(gq.w, fv[4 * i4 + 3], g);
+      for (int c = 0; c < KP; ++c) {
+        float2 out[NP];
+        if (c < K) {
+          if constexpr (!CD) {
+            float2 den[NP];
+#pragma unroll
+            for (int i4 = 0; i4 < KP / 4; ++i4) {
+              const volatile float4& gq = Gv[c * (KP / 4) + i4];
+              const float g0 = gq.x, g1 = gq.y, g2 = gq.z, g3 = gq.w;
+#pragma unroll
+              for (int p = 0; p < NP; ++p) {
+                den[p] = i4 == 0 ? mul2(bcast2(g0), fv[0][p]) : fma2(bcast2(g0), fv[4 * i4 + 0][p], den[p]);
+                den[p] = fma2(bcast2(g1), fv[4 * i4 + 1][p], den[p]);
+                den[p] = fma2(bcast2(g2), fv[4 * i4 + 2][p], den[p]);
+                den[p] = fma2(bcast2(g3), fv[4 * i4 + 3][p], den[p]);
+              }
+            }
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              if (l1 > 0.f) den[p] = add2(den[p], bcast2(l1));
+              if (l2 > 0.f) den[p] = fma2(bcast2(l2), fv[c][p], den[p]);
+              // zero denominators -> eps (sklearn _nmf.py:615,701); the Newton quotient needs a normal number
+              den[p].x = (den[p].x < FLT_MIN_NORMAL) ? EPSILON_F32 : den[p].x;
+              den[p].y = (den[p].y < FLT_MIN_NORMAL) ? EPSILON_F32 : den[p].y;
+              out[p] = mul2(fv[c][p], div_nr2(nv[c][p], den[p]));
+              sacc = fma2(nv[c][p], out[p], sacc);
+            }
+          } else {
+            // -(XHt - l1) + sum_r Gram[t, r] * F[r], summed in the order of the Cython loop (r = 0..K-1)
+            float2 g[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) g[p] = make_float2(l1 - nv[c][p].x, l1 - nv[c][p].y);
+#pragma unroll
+            for (int i4 = 0; i4 < KP / 4; ++i4) {
+              const volatile float4& gq = Gv[c * (KP / 4) + i4];
+              const float g0 = gq.x, g1 = gq.y, g2 = gq.z, g3 = gq.w;
+#pragma unroll
+              for (int p = 0; p < NP; ++p) {
+                g[p] = fma2(bcast2(g0), fv[4 * i4 + 0][p], g[p]);
+                g[p] = fma2(bcast2(g1), fv[4 * i4 + 1][p], g[p]);
+                g[p] = fma2(bcast2(g2), fv[4 * i4 + 2][p], g[p]);
+                g[p] = fma2(bcast2(g3), fv[4 * i4 + 3][p], g[p]);
+              }
+            }
+            const float h = Gs[c * KP + c];
+            const float hinv = Gs[KP * KP + c];                  // refined 1 / h (0 when h == 0)
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              const float pgx = (fv[c][p].x == 0.f) ? fminf(0.f, g[p].x) : g[p].x;
+              const float pgy = (fv[c][p].y == 0.f) ? fminf(0.f, g[p].y) : g[p].y;
+              sacc.x += fabsf(pgx);
+              sacc.y += fabsf(pgy);
+              if (h != 0.f) {                                    // block-uniform
+                float2 q = mul2(g[p], bcast2(hinv));             // g / h: quotient + residual correction
+                const float2 rem = fma2(bcast2(-h), q, g[p]);
+                q = fma2(bcast2(hinv), rem, q);
+                fv[c][p].x = fmaxf(fv[c][p].x - q.x, 0.f);
+                fv[c][p].y = fmaxf(fv[c][p].y - q.y, 0.f);
+              }
+              out[p] = fv[c][p];
+            }
+          }
+          store_items<VEC>(pF, pH, pL, (unsigned)c * ld, out, pscale);
+        } else {
+#pragma unroll
+          for (int p = 0; p < NP; ++p) out[p] = make_float2(0.f, 0.f);
         }
-        const float pg = (fv[t] == 0.f) ? fminf(0.f, g) : g;
-        viol += (double)fabsf(pg);
-        const float h = Gs[t * KP + t];
-        if (h != 0.f) fv[t] = fmaxf(fv[t] - g / h, 0.f);
-        store_elem(f, (long long)(o + t) * f.ld + col, fv[t], pscale);
+        if constexpr (GRAM) VecIO<VEC>::st(tile + c * TILE + VEC * threadIdx.x, out);
       }
+      scal += (double)(sacc.x + sacc.y);
+    } else if constexpr (GRAM) {
+      float2 z[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) z[p] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < KP; ++c) VecIO<VEC>::st(tile + c * TILE + VEC * threadIdx.x, z);
+    }
+    if constexpr (GRAM) {
+      __syncthreads();
+      fused_gram_tile<KP, TILE>(tile, gsum);
     }
   }
-  return viol;
+  return scal;
 }
 
 #define CNMF_KP_SWITCH(K, KPMAX, CALL)                                            \
@@ -295,46 +571,83 @@ __device__ __forceinline__ double cd_body(const FactorView& f, const float* __re
     default: if constexpr (KPMAX >= 32) { constexpr int KP = 32; CALL; } break;   \
   }
 
-template <int KPMAX>
+// KPMAX = 16: 4 items per thread, fused Gram available (GRAM).  KPMAX = 32: 2 items per thread, no fused Gram
+// (its K x K register tile does not fit beside the update's working set; the engine runs the stand-alone
+// Gram kernel for those batches).
+template <int KPMAX, bool CD, bool GRAM>
 __global__ void __launch_bounds__(UPD_THREADS, KPMAX == 32 ? 2 : 3)
-mu_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
-                 GramRef gram, BatchMeta b, float l1, float l2, double* __restrict__ cross_partial) {
+update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
+              const double* __restrict__ gram_in, BatchMeta b, float l1, float l2, FusedOut out) {
+  constexpr int VEC = KPMAX == 16 ? 4 : 2;
   const int slot = blockIdx.y;
   const int r = b.rid[slot];
   if (b.done[r]) return;
   const int K = b.k[slot], o = b.off[slot];
-  __shared__ __align__(16) float G[KPMAX * KPMAX];
+  const int KPr = ((K + 3) / 4) * 4;
+  __shared__ __align__(16) float G[KPMAX * KPMAX + KPMAX];   // Gram of the other factor (+ CD: 1/diag)
+  __shared__ double gsum[GRAM ? KPMAX * KPMAX : 1];
   __shared__ double red[32];
+  __shared__ int s_last;
+  // dynamic shared memory: [tileF | tileN].  tileF: KP x TILE values of the factor (MU: old, then new; CD + Gram: new)
+  // and the Gram reduction scratch; tileN (MU only): KP x TILE products
+  extern __shared__ __align__(16) float tile[];
+  load_gram_smem(G, gram_in, r, K, KPr, CD ? l2 : 0.f);       // CD: l2 on the diagonal, sklearn _nmf.py:383-385
+  if constexpr (GRAM)
+    for (int e = threadIdx.x; e < KPr * KPr; e += UPD_THREADS) gsum[e] = 0.0;
+  __syncthreads();
+  if constexpr (CD) {
+    if (threadIdx.x < KPr) {
+      const float h = G[threadIdx.x * KPr + threadIdx.x];
+      G[KPr * KPr + threadIdx.x] = (h != 0.f) ? rcp_nr(fmaxf(fabsf(h), FLT_MIN_NORMAL)) * (h < 0.f ? -1.f : 1.f) : 0.f;
+    }
+    __syncthreads();
+  }
   const int col_begin = blockIdx.x * f.cpb;
   const int col_end = min(f.n, col_begin + f.cpb);
-  double cross = 0.0;
-  CNMF_KP_SWITCH(K, KPMAX, (load_gram_smem(G, gram, r, K, KP, 0.f),
-                            cross = mu_body<KP>(f, NUM, nsplit, sstride, G, K, o, l1, l2, col_begin, col_end, cross_partial != nullptr)));
-  if (cross_partial) {
-    cross = block_sum(cross, red);
-    if (threadIdx.x == 0) cross_partial[(long long)r * gridDim.x + blockIdx.x] = cross;
+  const bool want_scal = out.scal_part != nullptr;
+  double scal = 0.0;
+  if constexpr (CD) {
+    CNMF_KP_SWITCH(K, KPMAX, (scal = update_body<KP, VEC, true, GRAM>(f, NUM, nsplit, sstride, G, K, o, l1, 0.f,
+                                                                       col_begin, col_end, tile, gsum)));
+  } else {
+    float* tileN = tile + UPD_TILE_F_FLOATS;
+    CNMF_KP_SWITCH(K, KPMAX, (scal = mu_body<KP, VEC, GRAM>(f, NUM, nsplit, sstride, G, K, o, l1, l2, col_begin, col_end,
+                                                             tile, tileN, gsum)));
   }
-}
-
-template <int KPMAX>
-__global__ void __launch_bounds__(UPD_THREADS, KPMAX == 32 ? 2 : 3)
-cd_update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
-                 GramRef gram, BatchMeta b, float l1, float l2, double* __restrict__ viol_partial) {
-  const int slot = blockIdx.y;
-  const int r = b.rid[slot];
-  if (b.done[r]) return;
-  const int K = b.k[slot], o = b.off[slot];
-  __shared__ __align__(16) float G[KPMAX * KPMAX];
-  __shared__ double red[32];
-  const int col_begin = blockIdx.x * f.cpb;
-  const int col_end = min(f.n, col_begin + f.cpb);
-  double viol = 0.0;
-  CNMF_KP_SWITCH(K, KPMAX, (load_gram_smem(G, gram, r, K, KP, l2),   // l2 on the diagonal: sklearn _nmf.py:383-385
-                            viol = cd_body<KP>(f, NUM, nsplit, sstride, G, K, o, l1, col_begin, col_end)));
-  if (viol_partial) {
-    viol = block_sum(viol, red);
-    if (threadIdx.x == 0) viol_partial[(long long)r * gridDim.x + blockIdx.x] = viol;
+  const int chunks = gridDim.x;
+  if (want_scal) {
+    scal = block_sum(scal, red);
+    if (threadIdx.x == 0) out.scal_part[(long long)slot * chunks + blockIdx.x] = scal;
   }
+  const int stride = b.kp * b.kp;
+  if constexpr (GRAM) {
+    double* part = out.gram_part + ((long long)slot * chunks + blockIdx.x) * stride;
+    for (int e = threadIdx.x; e < KPr * KPr; e += UPD_THREADS) part[e] = gsum[e];
+  }
+  if (!GRAM && !want_scal) return;
+  // ---- last block of the restart: fixed-order sums of the per-block partials
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&out.counter[r], 1) == chunks - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if constexpr (GRAM) {
+    const double* part = out.gram_part + (long long)slot * chunks * stride;
+    for (int e = threadIdx.x; e < KPr * KPr; e += UPD_THREADS) {
+      double a = 0.0;
+#pragma unroll 4
+      for (int ch = 0; ch < chunks; ++ch) a += __ldcg(part + (long long)ch * stride + e);
+      out.gram[(long long)r * KMAX * KMAX + (e / KPr) * KMAX + (e % KPr)] = a;
+    }
+  }
+  if (want_scal && threadIdx.x < 32) {
+    double a = 0.0;
+    for (int ch = threadIdx.x; ch < chunks; ch += 32) a += __ldcg(out.scal_part + (long long)slot * chunks + ch);
+    a = warp_sum(a);
+    if (threadIdx.x == 0) out.scal[r] = a;
+  }
+  if (threadIdx.x == 0) out.counter[r] = 0;
 }
 
 // ------------------------------------------------------------------ <NUM, F> without update
@@ -634,22 +947,50 @@ int launch_matrix_sums(const float* X, int rows, int cols, int ld, double* out2,
     default: set_last_error("kp must be 16 or 32"); return -1;       \
   }
 
-int launch_mu_update(const FactorView& f, const float* NUM, int nsplit, long long sstride, const GramRef& gram,
-                     const BatchMeta& b, float l1, float l2, double* cross_partial, cudaStream_t s) {
-  dim3 grid(col_chunks(f), b.R);
-  CNMF_DISPATCH_KPMAX(b.kp, (mu_update_kernel<KPMAX><<<grid, UPD_THREADS, 0, s>>>(f, NUM, nsplit, sstride, gram, b, l1,
-                                                                                    l2, cross_partial)));
+template <int KPMAX, bool CD, bool GRAM>
+static int launch_update_variant(dim3 grid, const FactorView& f, const float* NUM, int nsplit, long long sstride,
+                                 const double* gram_in, const BatchMeta& b, float l1, float l2, const FusedOut& out,
+                                 cudaStream_t s) {
+  // MU stages the thread's factor values and products in shared memory (rolled component loop); CD only needs
+  // the tile when it also emits the Gram
+  const size_t smem = sizeof(float) * (CD ? (GRAM ? (size_t)UPD_TILE_F_FLOATS : 0) : (size_t)UPD_TILE_F_FLOATS + UPD_TILE_N_FLOATS);
+  static bool attr_set = false;
+  if (!attr_set && smem > 0) {
+    CNMF_CUDA_CHECK(cudaFuncSetAttribute(update_kernel<KPMAX, CD, GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  update_kernel<KPMAX, CD, GRAM><<<grid, UPD_THREADS, smem, s>>>(f, NUM, nsplit, sstride, gram_in, b, l1, l2, out);
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
-int launch_cd_update(const FactorView& f, const float* NUM, int nsplit, long long sstride, const GramRef& gram,
-                     const BatchMeta& b, float l1, float l2, double* viol_partial, cudaStream_t s) {
+template <bool CD>
+static int launch_update(const FactorView& f, const float* NUM, int nsplit, long long sstride, const double* gram_in,
+                         const BatchMeta& b, float l1, float l2, const FusedOut& out, cudaStream_t s) {
+  CNMF_REQUIRE(f.cpb % upd_tile_cols(b.kp) == 0, "update: cpb must be a multiple of the update tile");
+  CNMF_REQUIRE(f.ld % 4 == 0, "update: ld must be a multiple of 4");
+  static_assert(16 * UPD_THREADS * 4 == UPD_TILE_N_FLOATS && 32 * UPD_THREADS * 2 == UPD_TILE_N_FLOATS, "tile sizes");
   dim3 grid(col_chunks(f), b.R);
-  CNMF_DISPATCH_KPMAX(b.kp, (cd_update_kernel<KPMAX><<<grid, UPD_THREADS, 0, s>>>(f, NUM, nsplit, sstride, gram, b, l1,
-                                                                                    l2, viol_partial)));
-  CNMF_CUDA_CHECK(cudaGetLastError());
-  return 0;
+  if (b.kp == 16) {
+    if (out.gram_part) return launch_update_variant<16, CD, true>(grid, f, NUM, nsplit, sstride, gram_in, b, l1, l2, out, s);
+    return launch_update_variant<16, CD, false>(grid, f, NUM, nsplit, sstride, gram_in, b, l1, l2, out, s);
+  }
+  if (b.kp == 32) {
+    CNMF_REQUIRE(out.gram_part == nullptr, "update: the fused Gram exists for kp == 16 batches only");
+    return launch_update_variant<32, CD, false>(grid, f, NUM, nsplit, sstride, gram_in, b, l1, l2, out, s);
+  }
+  set_last_error("kp must be 16 or 32");
+  return -1;
+}
+
+int launch_mu_update(const FactorView& f, const float* NUM, int nsplit, long long sstride, const double* gram_in,
+                     const BatchMeta& b, float l1, float l2, const FusedOut& out, cudaStream_t s) {
+  return launch_update<false>(f, NUM, nsplit, sstride, gram_in, b, l1, l2, out, s);
+}
+
+int launch_cd_update(const FactorView& f, const float* NUM, int nsplit, long long sstride, const double* gram_in,
+                     const BatchMeta& b, float l1, float l2, const FusedOut& out, cudaStream_t s) {
+  return launch_update<true>(f, NUM, nsplit, sstride, gram_in, b, l1, l2, out, s);
 }
 
 int launch_cross(const FactorView& f, const float* NUM, int nsplit, long long sstride, const BatchMeta& b,

@@ -12,7 +12,10 @@
 
 namespace cnmf {
 
-constexpr int UPD_THREADS = 256;
+constexpr int UPD_THREADS = 128;
+// columns one block of the update kernels covers per pass ("tile"): a thread owns 4 consecutive items (one 16-byte
+// access per array and component) when the batch fits the 16-component bodies, 2 otherwise (register budget)
+inline int upd_tile_cols(int kp) { return UPD_THREADS * (kp <= 16 ? 4 : 2); }
 
 struct FactorView {
   float* F;        // SK x ld, in/out
@@ -22,7 +25,7 @@ struct FactorView {
   int ld;
   const float* piece_scale;   // optional per-column scale folded into the tf32 pieces: hi + lo = F * piece_scale
                               // (exact-count datasets: the per-gene / per-cell scale of X lives in the A operand)
-  int cpb;         // columns handled by one block of the update / cross kernels (multiple of 256)
+  int cpb;         // columns handled by one block of the update / cross kernels (multiple of upd_tile_cols(kp))
   int gcpb;        // columns handled by one block of the Gram kernel (multiple of 1024)
 };
 
@@ -75,27 +78,29 @@ int launch_transpose(const float* src, int rows, int cols, int ld_src, float* ds
 int launch_matrix_sums(const float* X, int rows, int cols, int ld, double* out2, double* scratch, int scratch_len,
                        cudaStream_t s);
 
-// K x K Gram of the OTHER factor as the update kernels consume it: the per-chunk fp64 partials written by
-// launch_gram_partial, summed in fixed chunk order while the block loads its Gram into shared memory (so no
-// separate finalize launch sits on the critical path of an iteration).
-struct GramRef {
-  const double* part;   // [(rid * chunks + chunk) * stride + c * KP + i], KP = K rounded up to 4
-  int chunks;
-  int stride;           // kp * kp of the batch
+// What an update launch can emit besides the updated factor, finalised INSIDE the launch: every block writes its
+// fp64 partials, takes a ticket on the restart's counter, and the block that draws the last ticket sums all
+// partials of the restart in chunk order (deterministic) -- so neither a Gram pass over the freshly written
+// factor nor a finalize launch sits between an update and the GEMM / update that follows it.
+struct FusedOut {
+  double* gram_part;   // nullptr = no Gram.  [(slot * chunks + chunk) * kp*kp + c*KP + i], KP = K rounded up to 4
+  double* gram;        // [rid * KMAX*KMAX + c*KMAX + i]: K x K Gram of the UPDATED factor (kp == 16 batches only)
+  double* scal_part;   // nullptr = no scalar.  [slot * chunks + chunk]
+  double* scal;        // [rid]: MU <NUM, F_new> (trace-form error), CD sum |projected gradient|
+  int* counter;        // [rid] tickets; zero on entry, reset by the last block
 };
 
 // Multiplicative update (sklearn _nmf.py:535-549,610-624 / :633-635,696-721):
 //   F[c, j] <- F[c, j] * NUM[c, j] / max-style-guard( sum_i gram[c, i] F[i, j] + l1 + l2 F[c, j] )
-// NUM = sum over `nsplit` split-K slices (stride num_split_stride elements).
-// cross_partial[r * chunks + chunk] = sum NUM * F_new (fp64), used by the trace-form error.
+// NUM = sum over `nsplit` split-K slices (stride num_split_stride elements), summed in slice order.
+// gram_in = finalised K x K Gram of the OTHER factor, fp64 [rid * KMAX*KMAX + c*KMAX + i].
 int launch_mu_update(const FactorView& f, const float* NUM, int nsplit, long long num_split_stride,
-                     const GramRef& gram, const BatchMeta& b, float l1, float l2, double* cross_partial,
+                     const double* gram_in, const BatchMeta& b, float l1, float l2, const FusedOut& out,
                      cudaStream_t s);
 
-// One coordinate-descent sweep over the K coordinates of every column (sklearn _cdnmf_fast.pyx:8-37):
-//   viol_partial[r * chunks + chunk] = sum |projected gradient|
+// One coordinate-descent sweep over the K coordinates of every column (sklearn _cdnmf_fast.pyx:8-37).
 int launch_cd_update(const FactorView& f, const float* NUM, int nsplit, long long num_split_stride,
-                     const GramRef& gram, const BatchMeta& b, float l1, float l2, double* viol_partial,
+                     const double* gram_in, const BatchMeta& b, float l1, float l2, const FusedOut& out,
                      cudaStream_t s);
 
 // cross_partial[r*chunks+chunk] = sum_{c,j} NUM[c,j] * F[c,j]   (no update; used for the error at init)

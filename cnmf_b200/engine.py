@@ -100,10 +100,12 @@ class Engine:
         """Start (and reset) / stop per-launch CUDA-event timing of the batched GEMM."""
         check(self.lib.cnmf_profile_enable(self._h, 1 if on else 0))
 
-    def profile_get(self):
-        """(total GEMM device ms, GEMM launches, algorithmic FLOPs) since profile(True)."""
+    def profile_get(self, kernel_class=0):
+        """(total device ms, launches, algorithmic work) of a kernel class since profile(True):
+        0 = batched GEMM (work in FLOPs), 1 = fused update kernels (work in bytes)."""
         ms, n, fl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
-        check(self.lib.cnmf_profile_get(self._h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
+        check(self.lib.cnmf_profile_get_class(self._h, int(kernel_class), ctypes.byref(ms), ctypes.byref(n),
+                                              ctypes.byref(fl)))
         return ms.value, int(n.value), fl.value
 
     def last_timing(self):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CNMF_B200_ABI_VERSION 2
+#define CNMF_B200_ABI_VERSION 3
 #define CNMF_MAX_COMPONENTS 32          /* largest n_components per restart on the CUDA path */
 
 typedef struct cnmf_handle_s* cnmf_handle_t;
@@ -70,6 +70,9 @@ long long cnmf_launch_count(cnmf_handle_t h);
  * (2*M*N*K per launch, counted once -- not 3x for the 3xTF32 passes) */
 int cnmf_profile_enable(cnmf_handle_t h, int on);
 int cnmf_profile_get(cnmf_handle_t h, double* gemm_ms, long long* gemm_launches, double* gemm_flops);
+/* same counters per kernel class: 0 = batched GEMM (work = algorithmic FLOPs), 1 = fused update kernels
+ * (work = algorithmic bytes: factor read + product slices read + factor and tf32 pieces written) */
+int cnmf_profile_get_class(cnmf_handle_t h, int kernel_class, double* ms, long long* launches, double* work);
 
 /* host wall-clock phases (ms) of the last cnmf_factorize on this handle: host RNG, H2D of the initial
  * factors, batched solve, D2H of the results */
