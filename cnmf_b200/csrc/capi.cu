@@ -191,6 +191,13 @@ int cnmf_profile_enable(cnmf_handle_t h, int on) {
   }
   h->ev_pending.clear();
   h->ev_used = 0;
+  if (on) {       // event creation is kept out of the timed region: a pool for ~8 000 launches up front
+    while (h->ev_pool.size() < 16384) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) break;
+      h->ev_pool.push_back(e);
+    }
+  }
   return 0;
 }
 
@@ -202,6 +209,8 @@ int cnmf_profile_get(cnmf_handle_t h, double* gemm_ms, long long* gemm_launches,
 int cnmf_profile_get_class(cnmf_handle_t h, int cls, double* ms, long long* launches, double* work) {
   CNMF_REQUIRE(h, "profile_get_class: NULL handle");
   CNMF_REQUIRE(cls >= 0 && cls < cnmf_handle_s::PROF_CLASSES, "profile_get_class: unknown kernel class");
+  CNMF_CUDA_CHECK(cudaDeviceSynchronize());     // every recorded event has completed
+  h->prof_collect();
   if (ms) *ms = h->prof_ms[cls];
   if (launches) *launches = h->prof_launches[cls];
   if (work) *work = h->prof_work[cls];

@@ -813,15 +813,19 @@ __global__ void finalize_kernel(const double* __restrict__ gram_partial, double*
 __global__ void mu_check_kernel(ConvState st, const double* __restrict__ cross, const double* __restrict__ gramA,
                                 const double* __restrict__ gramB, double normX2, BatchMeta b, int it, double tol,
                                 int max_iter) {
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per restart: <gramA, gramB> over K x K entries, lanes stride the entries, fixed-order shuffle tree
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (slot >= b.R) return;
   const int r = b.rid[slot];
   if (st.done[r]) return;
   const int K = b.k[slot];
   double dot = 0.0;
-  for (int c = 0; c < K; ++c)
-    for (int i = 0; i < K; ++i)
-      dot += gramA[(long long)r * KMAX * KMAX + c * KMAX + i] * gramB[(long long)r * KMAX * KMAX + c * KMAX + i];
+  for (int e = lane; e < K * K; e += 32) {
+    const int c = e / K, i = e % K;
+    dot += gramA[(long long)r * KMAX * KMAX + c * KMAX + i] * gramB[(long long)r * KMAX * KMAX + c * KMAX + i];
+  }
+  dot = warp_sum(dot);
+  if (lane != 0) return;
   const double err = sqrt(fmax(normX2 - 2.0 * cross[r] + dot, 0.0));
   st.last[r] = err;
   if (it == 0) {
@@ -1021,7 +1025,7 @@ int launch_finalize(const double* gram_partial, double* gram, const double* scal
 
 int launch_mu_check(const ConvState& st, const double* cross, const double* gramA, const double* gramB, double normX2,
                     const BatchMeta& b, int it, double tol, int max_iter, cudaStream_t s) {
-  mu_check_kernel<<<(b.R + 127) / 128, 128, 0, s>>>(st, cross, gramA, gramB, normX2, b, it, tol, max_iter);
+  mu_check_kernel<<<(b.R + 3) / 4, 128, 0, s>>>(st, cross, gramA, gramB, normX2, b, it, tol, max_iter);
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
