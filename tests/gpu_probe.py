@@ -165,6 +165,26 @@ def stage_consensus_c4():
             solver, t1 - t0, it, t2 - t1, itr, rel(W, Wr), ds.exact), flush=True)
 
 
+def stage_consensus_kernels():
+    """One pass over the consensus kernels at BASELINE configs[3] size (R = 4000 x 2000, K = 20) -- the launch set
+    `ncu --set full -k regex:...` captures for the HBM roofline table in profiles/."""
+    from cnmf_b200 import consensus as cs
+    eng = Engine()
+    rng = np.random.RandomState(11)
+    K, R, G = 20, 4000, 2000
+    cen = np.abs(rng.gamma(0.3, 1.0, size=(K, G)))
+    pts = np.vstack([c * (1 + 0.02 * rng.randn(190, G)) for c in cen] + [np.abs(rng.gamma(0.3, 1.0, size=(200, G)))])
+    pts = np.abs(pts)[rng.permutation(R)]
+    S = cs.SpectraMatrix(eng, pts).l2_normalize()
+    dens, _ = S.local_density(int(0.3 * R / K))
+    keep = dens < 0.1
+    S2 = S.take_rows(np.where(keep)[0])
+    labels, labels_t, inertia, _ = cs.kmeans(S2, K, n_init=1)
+    med = cs.cluster_medians(S2, labels_t, K)
+    sil = cs.silhouette(S2, labels, labels_t, K)
+    print("consensus_kernels: kept %d of %d, inertia %.4f, silhouette %.4f" % (keep.sum(), R, inertia, sil), flush=True)
+
+
 def stage_big():
     """BASELINE configs[3] and [4] factorize sizes on ONE GPU (capacity / sanity: no oracle at this size):
     c4 68k x 2k, K=20 x 200 restarts; c5 200k x 5k, K=30 x 200 restarts."""
@@ -356,3 +376,5 @@ if __name__ == "__main__":
         stage_cd()
     elif st == "big":
         stage_big()
+    elif st == "consensus_kernels":
+        stage_consensus_kernels()
