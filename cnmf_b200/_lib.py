@@ -55,6 +55,9 @@ SIGNATURES = {
     "cnmf_dataset_sums": (_i, [_vp, _pp(_d), _pp(_d)]),
     "cnmf_dataset_min": (_i, [_vp, _pp(_c.c_float), _vp]),
     "cnmf_dataset_col_stats": (_i, [_vp, _vp, _vp, _vp]),
+    "cnmf_dataset_row_sums": (_i, [_vp, _vp, _vp]),
+    "cnmf_dataset_scaled_col_stats": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "cnmf_dataset_scale_rows": (_i, [_vp, _vp, _vp, _pp(_vp)]),
     "cnmf_random_init_host": (_i, [_c.c_uint32, _d, _i, _i, _i, _vp, _ll, _vp, _ll]),
     "cnmf_random_init_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "cnmf_factorize": (_i, [_vp, _i, _vp, _vp, _pp(NmfParams), _vp, _vp, _vp, _vp, _vp]),
@@ -76,7 +79,7 @@ SIGNATURES = {
 _lib = None
 
 
-ABI_VERSION = 3      # include/cnmf_b200.h CNMF_B200_ABI_VERSION
+ABI_VERSION = 4      # include/cnmf_b200.h CNMF_B200_ABI_VERSION
 
 
 def load():

@@ -26,19 +26,59 @@ __global__ void fill_kernel(float* p, float v, int rows, int n, int ld) {
     p[(i / n) * ld + (i % n)] = v;
 }
 
-__global__ void col_stats_kernel(const float* __restrict__ X, int rows, int cols, int ld, double* __restrict__ mean,
-                                 double* __restrict__ var) {
-  // one warp-wide column strip per block.x: threads own columns (coalesced), loop over rows in fp64
+// column sums of v and v^2 with v = X[r, c] * (row_scale ? row_scale[r] : 1), fp64.  Threads own columns (coalesced),
+// blockIdx.y owns a fixed strip of rows: partial[y][c], reduced in strip order by col_stats_reduce_kernel
+// (deterministic: the HVG ranking of prepare() is a sort of these numbers).
+__global__ void col_stats_kernel(const float* __restrict__ X, int rows, int cols, int ld,
+                                 const double* __restrict__ row_scale, double* __restrict__ part) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
+  const int per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
   double s = 0.0, q = 0.0;
-  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
-    const double v = X[(long long)r * ld + c];
+  for (int r = r0; r < r1; ++r) {
+    double v = X[(long long)r * ld + c];
+    if (row_scale) v *= row_scale[r];
     s += v;
     q += v * v;
   }
-  atomicAdd(&mean[c], s);
-  atomicAdd(&var[c], q);
+  part[((long long)blockIdx.y * 2) * cols + c] = s;
+  part[((long long)blockIdx.y * 2 + 1) * cols + c] = q;
+}
+
+__global__ void col_stats_reduce_kernel(const double* __restrict__ part, int strips, int cols, double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double s = 0.0, q = 0.0;
+  for (int y = 0; y < strips; ++y) {
+    s += part[((long long)y * 2) * cols + c];
+    q += part[((long long)y * 2 + 1) * cols + c];
+  }
+  out[c] = s;
+  out[cols + c] = q;
+}
+
+// one warp per row: fp64 sum of the row (cell totals: the TPM denominators of cnmf.py:245-251)
+__global__ void row_sums_kernel(const float* __restrict__ X, int rows, int cols, int ld, double* __restrict__ out) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* row = X + (long long)r * ld;
+  double s = 0.0;
+  for (int c = lane; c < cols; c += 32) s += (double)row[c];
+  s = warp_sum(s);
+  if (lane == 0) out[r] = s;
+}
+
+__global__ void scale_rows_kernel(const float* __restrict__ src, int rows, int cols, int ld, const float* __restrict__ rs,
+                                  float* __restrict__ dst) {
+  const long long total = (long long)rows * (ld / 4);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (ld / 4));
+    float4 v = reinterpret_cast<const float4*>(src)[i];
+    const float f = rs[r];
+    v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+    reinterpret_cast<float4*>(dst)[i] = v;
+  }
 }
 
 __global__ void combine_scale_kernel(const float* __restrict__ scale, const float* __restrict__ src_cs,
@@ -51,27 +91,36 @@ __global__ void combine_scale_kernel(const float* __restrict__ scale, const floa
 __global__ void gather_cols_kernel(const float* __restrict__ src, int rows, int ld_src, const int* __restrict__ cols,
                                    const float* __restrict__ scale, int n_cols, float* __restrict__ dst, int ld_dst) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = blockIdx.y;
   if (c >= n_cols) return;
-  dst[(long long)r * ld_dst + c] = src[(long long)r * ld_src + cols[c]] * scale[c];
+  const int sc = cols[c];
+  const float f = scale[c];
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) dst[(long long)r * ld_dst + c] = src[(long long)r * ld_src + sc] * f;
 }
 
 }  // namespace
 
 extern "C" {
 
-int cnmf_dataset_col_stats(cnmf_dataset_t d, double* mean_host, double* var_host, void* stream) {
+static int col_stats_impl(cnmf_dataset_t d, const double* row_scale_host, double* mean_host, double* var_host, void* stream) {
   CNMF_REQUIRE(d && mean_host && var_host, "col_stats: NULL argument");
   cnmf_handle_s* h = d->h;
   cudaStream_t s = as_stream(stream);
   CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  const int strips = std::max(1, std::min(64, d->n_rows / 64));
+  double* part = static_cast<double*>(h->dev_buf("colstats.part", sizeof(double) * 2 * (size_t)strips * d->n_cols));
   double* buf = static_cast<double*>(h->dev_buf("colstats", sizeof(double) * 2 * d->n_cols));
-  if (!buf) return -2;
-  CNMF_CUDA_CHECK(cudaMemsetAsync(buf, 0, sizeof(double) * 2 * d->n_cols, s));
-  dim3 grid((d->n_cols + 127) / 128, std::min(d->n_rows, 256));
-  col_stats_kernel<<<grid, 128, 0, s>>>(d->X, d->n_rows, d->n_cols, d->ld_c, buf, buf + d->n_cols);
+  double* d_rs = nullptr;
+  if (row_scale_host) {
+    d_rs = static_cast<double*>(h->dev_buf("colstats.rs", sizeof(double) * d->n_rows));
+    if (!d_rs) return -2;
+    CNMF_CUDA_CHECK(cudaMemcpyAsync(d_rs, row_scale_host, sizeof(double) * d->n_rows, cudaMemcpyHostToDevice, s));
+  }
+  if (!part || !buf) return -2;
+  dim3 grid((d->n_cols + 127) / 128, strips);
+  col_stats_kernel<<<grid, 128, 0, s>>>(d->X, d->n_rows, d->n_cols, d->ld_c, d_rs, part);
+  col_stats_reduce_kernel<<<(d->n_cols + 127) / 128, 128, 0, s>>>(part, strips, d->n_cols, buf);
   CNMF_CUDA_CHECK(cudaGetLastError());
-  h->launches += 1;
+  h->launches += 2;
   CNMF_CUDA_CHECK(cudaMemcpyAsync(mean_host, buf, sizeof(double) * d->n_cols, cudaMemcpyDeviceToHost, s));
   CNMF_CUDA_CHECK(cudaMemcpyAsync(var_host, buf + d->n_cols, sizeof(double) * d->n_cols, cudaMemcpyDeviceToHost, s));
   CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -81,6 +130,31 @@ int cnmf_dataset_col_stats(cnmf_dataset_t d, double* mean_host, double* var_host
     mean_host[c] = m;
     var_host[c] = std::max(var_host[c] / n - m * m, 0.0);
   }
+  return 0;
+}
+
+int cnmf_dataset_col_stats(cnmf_dataset_t d, double* mean_host, double* var_host, void* stream) {
+  return col_stats_impl(d, nullptr, mean_host, var_host, stream);
+}
+
+int cnmf_dataset_scaled_col_stats(cnmf_dataset_t d, const double* row_scale_host, double* mean_host, double* var_host,
+                                  void* stream) {
+  CNMF_REQUIRE(row_scale_host, "scaled_col_stats: NULL row scale");
+  return col_stats_impl(d, row_scale_host, mean_host, var_host, stream);
+}
+
+int cnmf_dataset_row_sums(cnmf_dataset_t d, double* row_sums_host, void* stream) {
+  CNMF_REQUIRE(d && row_sums_host, "row_sums: NULL argument");
+  cnmf_handle_s* h = d->h;
+  cudaStream_t s = as_stream(stream);
+  CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  double* buf = static_cast<double*>(h->dev_buf("rowsums", sizeof(double) * d->n_rows));
+  if (!buf) return -2;
+  row_sums_kernel<<<(d->n_rows + 7) / 8, 256, 0, s>>>(d->X, d->n_rows, d->n_cols, d->ld_c, buf);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  h->launches += 1;
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(row_sums_host, buf, sizeof(double) * d->n_rows, cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
   return 0;
 }
 
@@ -115,15 +189,10 @@ int cnmf_dataset_from_columns(cnmf_dataset_t src, const int32_t* cols_host, cons
     if (e != cudaSuccess) rc = -2;
   }
   if (rc == 0) {
-    dim3 grid((n_cols + 127) / 128, d->n_rows);
-    if (d->n_rows > 65535) {
-      set_last_error("dataset_from_columns: more than 65535 rows per launch not supported yet");
-      rc = -3;
-    } else {
-      gather_cols_kernel<<<grid, 128, 0, s>>>(src->X, d->n_rows, src->ld_c, d_cols, d_scale, n_cols, d->X, d->ld_c);
-      h->launches += 1;
-      if (cudaGetLastError() != cudaSuccess) rc = -2;
-    }
+    dim3 grid((n_cols + 127) / 128, std::min(d->n_rows, 16384));
+    gather_cols_kernel<<<grid, 128, 0, s>>>(src->X, d->n_rows, src->ld_c, d_cols, d_scale, n_cols, d->X, d->ld_c);
+    h->launches += 1;
+    if (cudaGetLastError() != cudaSuccess) rc = -2;
   }
   if (rc == 0 && src->exact) {
     // an exact-count source stays exact: same integer matrix (the selected columns), same row scale, and the
@@ -141,6 +210,38 @@ int cnmf_dataset_from_columns(cnmf_dataset_t src, const int32_t* cols_host, cons
         rc = -2;
     }
   }
+  if (rc == 0) rc = cnmf_dataset_finish_internal(d, stream);
+  if (rc != 0) {
+    cnmf_dataset_destroy(d);
+    return rc;
+  }
+  *out = d;
+  return 0;
+}
+
+int cnmf_dataset_scale_rows(cnmf_dataset_t src, const float* row_scale_host, void* stream, cnmf_dataset_t* out) {
+  CNMF_REQUIRE(src && row_scale_host && out, "dataset_scale_rows: bad arguments");
+  cnmf_handle_s* h = src->h;
+  cudaStream_t s = as_stream(stream);
+  CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  float* d_rs = static_cast<float*>(h->dev_buf("scalerows.rs", sizeof(float) * src->n_rows));
+  if (!d_rs) return -2;
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(d_rs, row_scale_host, sizeof(float) * src->n_rows, cudaMemcpyHostToDevice, s));
+  auto* d = new cnmf_dataset_s();
+  d->h = h;
+  d->n_rows = src->n_rows;
+  d->n_cols = src->n_cols;
+  d->ld_c = src->ld_c;
+  d->ld_r = src->ld_r;
+  d->precision = src->precision;
+  d->allow_exact = src->allow_exact;
+  int rc = cnmf_dataset_alloc_internal(d, &d->X, (size_t)d->n_rows * d->ld_c);
+  if (rc == 0) {
+    scale_rows_kernel<<<148 * 8, 256, 0, s>>>(src->X, d->n_rows, d->n_cols, d->ld_c, d_rs, d->X);
+    h->launches += 1;
+    if (cudaGetLastError() != cudaSuccess) rc = -2;
+  }
+  // exact-count detection runs from scratch in finish(): counts x (1e6 / cell total) is again scaled integers
   if (rc == 0) rc = cnmf_dataset_finish_internal(d, stream);
   if (rc != 0) {
     cnmf_dataset_destroy(d);

@@ -209,11 +209,32 @@ class Dataset:
         check(self.lib.cnmf_dataset_sums(self._d, ctypes.byref(s), ctypes.byref(q)))
         return s.value, q.value
 
-    def col_stats(self):
+    def col_stats(self, row_scale=None):
+        """Per-column (mean, population variance) in float64; with row_scale: of diag(row_scale) @ X, accumulated
+        from the stored values (TPM gene statistics straight from the raw counts, cnmf.py:192-242, 436-445)."""
         g = self.shape[1]
         mean, var = np.empty(g), np.empty(g)
-        check(self.lib.cnmf_dataset_col_stats(self._d, ptr(mean), ptr(var), None))
+        if row_scale is None:
+            check(self.lib.cnmf_dataset_col_stats(self._d, ptr(mean), ptr(var), None))
+        else:
+            rs = np.ascontiguousarray(row_scale, dtype=np.float64)
+            assert rs.shape == (self.shape[0],)
+            check(self.lib.cnmf_dataset_scaled_col_stats(self._d, ptr(rs), ptr(mean), ptr(var), None))
         return mean, var
+
+    def row_sums(self):
+        """Per-row (cell) totals in float64 (the TPM denominators, cnmf.py:245-251)."""
+        out = np.empty(self.shape[0])
+        check(self.lib.cnmf_dataset_row_sums(self._d, ptr(out), None))
+        return out
+
+    def scale_rows(self, row_scale):
+        """New resident dataset diag(row_scale) @ X (TPM from counts without a trip through the host)."""
+        rs = f32c(row_scale)
+        assert rs.shape == (self.shape[0],)
+        out = ctypes.c_void_p()
+        check(self.lib.cnmf_dataset_scale_rows(self._d, ptr(rs), None, ctypes.byref(out)))
+        return Dataset(self.engine, None, self.precision, _handle=out)
 
     def from_columns(self, cols, scale):
         cols = np.ascontiguousarray(cols, dtype=np.int32)

@@ -61,10 +61,10 @@ def worker_filter(iterable, worker_index, total_workers):
     return (p for i, p in enumerate(iterable) if (i - worker_index) % total_workers == 0)
 
 
-def _highvar_genes(tpm, numgenes):
-    """V-score overdispersion ranking on dense TPM (cnmf.py:192-242)."""
-    mean = pd.Series(tpm.mean(axis=0).astype(float))
-    var = pd.Series(tpm.var(axis=0, ddof=0).astype(float))
+def _highvar_from_stats(mean, var, numgenes):
+    """V-score over-dispersion ranking from per-gene TPM mean / population variance (cnmf.py:192-242)."""
+    mean = pd.Series(np.asarray(mean, dtype=float))
+    var = pd.Series(np.asarray(var, dtype=float))
     fano = var / mean
     top = mean.sort_values(ascending=False)[:20].index
     A = (np.sqrt(var) / mean)[top].min()
@@ -75,6 +75,11 @@ def _highvar_genes(tpm, numgenes):
     ratio = fano / ((A ** 2) * mean + (B ** 2))
     chosen = ratio.sort_values(ascending=False).index[:numgenes]
     return ratio.index.isin(chosen)
+
+
+def _highvar_genes(tpm, numgenes):
+    """Same ranking on a dense TPM matrix held on the host."""
+    return _highvar_from_stats(tpm.mean(axis=0), tpm.var(axis=0, ddof=0), numgenes)
 
 
 class cNMF:
@@ -89,6 +94,7 @@ class cNMF:
         self.device = device
         self.paths = None
         self._engine = None
+        self._resident_norm = None      # normalised counts left in HBM by prepare(on_device=True)
         self._initialize_dirs()
 
     # ------------------------------------------------------------------ ledger
@@ -113,12 +119,27 @@ class cNMF:
     # ------------------------------------------------------------------ prepare
     def prepare(self, counts_fn, components, n_iter=100, densify=False, tpm_fn=None, seed=None,
                 beta_loss="frobenius", num_highvar_genes=2000, genes_file=None,
-                alpha_usage=0.0, alpha_spectra=0.0, init="random", max_NMF_iter=1000):
+                alpha_usage=0.0, alpha_spectra=0.0, init="random", max_NMF_iter=1000, on_device=False):
         """Same outputs as reference prepare() (cnmf.py:333-459) for dense inputs.  The CUDA path holds the
-        matrix dense, so sparse inputs are densified (numerically identical to the reference's --densify)."""
+        matrix dense, so sparse inputs are densified (numerically identical to the reference's --densify).
+
+        on_device=True (cnmf_b200 extension, `--prepare-on-device`): the raw counts are made resident and the
+        per-cell totals, the TPM gene statistics behind the over-dispersion ranking and `tpm_stats`, the per-gene
+        scale of the HVG matrix and the HVG matrix itself are computed by CUDA kernels (float64 accumulation from the
+        exact integer counts); the normalised matrix stays in HBM for factorize().  Raises without a GPU."""
         counts = cio.read_counts(counts_fn)
         C = counts.dense(np.float64)
-        if tpm_fn is None:
+        dev = None
+        if on_device:
+            if tpm_fn is not None:
+                raise ValueError("on_device=True derives TPM from the counts; it cannot be combined with tpm_fn")
+            dev = self.engine().dataset(C, precision=self.precision)       # raw counts resident in HBM
+            totals = dev.row_sums()
+            tpm_X = C / totals[:, None] * 1e6                              # host copy only for the tpm file
+            tpm = cio.CellGeneMatrix(tpm_X, counts.obs_names, counts.var_names)
+            t_mean, t_var = dev.col_stats(row_scale=1e6 / totals)
+            t_std = np.sqrt(t_var)
+        elif tpm_fn is None:
             tpm_X = C / C.sum(axis=1, keepdims=True) * 1e6           # cnmf.py:245-251
             tpm = cio.CellGeneMatrix(tpm_X, counts.obs_names, counts.var_names)
         else:
@@ -126,17 +147,29 @@ class cNMF:
             tpm = cio.CellGeneMatrix(tpm.dense(np.float64), tpm.obs_names, tpm.var_names)
         cio.write_matrix(self.paths["tpm"], tpm)
         T = tpm.X
-        stats = pd.DataFrame([T.mean(axis=0), T.std(axis=0, ddof=0)], index=["__mean", "__std"],
-                             columns=tpm.var_names).T                   # cnmf.py:439-445
+        if dev is None:
+            t_mean, t_std = T.mean(axis=0), T.std(axis=0, ddof=0)
+        stats = pd.DataFrame([t_mean, t_std], index=["__mean", "__std"], columns=tpm.var_names).T   # cnmf.py:439-445
         save_df_to_npz(stats, self.paths["tpm_stats"])
 
         if genes_file is not None:
             hvgs = open(genes_file).read().rstrip().split("\n")
+        elif dev is not None:
+            hvgs = list(tpm.var_names[_highvar_from_stats(t_mean, t_var, num_highvar_genes)])
         else:
             hvgs = list(tpm.var_names[_highvar_genes(T, num_highvar_genes)])
-        norm, _ = cio.CellGeneMatrix(C, counts.obs_names, counts.var_names).subset_genes(hvgs)
+        norm, idx = cio.CellGeneMatrix(C, counts.obs_names, counts.var_names).subset_genes(hvgs)
         X = norm.X.astype(np.float64)
-        X /= X.std(axis=0, ddof=1)                                     # cnmf.py:542 (no centring)
+        if dev is not None:
+            n = C.shape[0]
+            _, c_var = dev.col_stats()
+            std1 = np.sqrt(c_var[idx] * n / (n - 1.0))                 # std(ddof=1) of the selected count columns
+            X /= std1
+            with np.errstate(divide="ignore"):
+                self._resident_norm = dev.from_columns(idx, 1.0 / std1)   # counts[:, hvgs] / std, built on the device
+            dev.close()
+        else:
+            X /= X.std(axis=0, ddof=1)                                 # cnmf.py:542 (no centring)
         if np.isnan(X).sum() > 0:
             print("Warning NaNs in normalized counts matrix")
         norm.X = X
@@ -234,7 +267,10 @@ class cNMF:
         ks = [int(run_params.iloc[j]["n_components"]) for j in jobs]
         seeds = [int(run_params.iloc[j]["nmf_seed"]) for j in jobs]
         print("[Worker %d]. Starting %d tasks as one batch." % (worker_i, len(jobs)))
-        spectra, n_iter, _ = self._nmf_batched(norm.X, ks, seeds, kw)
+        X = norm.X
+        if self._resident_norm is not None and self._resident_norm.shape == tuple(norm.X.shape):
+            X = self._resident_norm                    # already in HBM (prepare(on_device=True)): no H2D
+        spectra, n_iter, _ = self._nmf_batched(X, ks, seeds, kw)
         if int(np.max(n_iter)) >= int(kw["max_iter"]):
             from sklearn.exceptions import ConvergenceWarning
             warnings.warn("Maximum number of iterations %d reached. Increase it to improve convergence." % kw["max_iter"],
@@ -526,6 +562,8 @@ def main():
     ap.add_argument("--local-neighborhood-size", type=float, default=0.30)
     ap.add_argument("--show-clustering", dest="show_clustering", action="store_true")
     ap.add_argument("--build-reference", dest="build_reference", action="store_true", default=True)
+    ap.add_argument("--prepare-on-device", dest="prepare_on_device", action="store_true", default=False,
+                    help="[cnmf_b200] prepare: cell totals, TPM gene statistics and the HVG matrix computed on the GPU")
     ap.add_argument("--precision", type=str, choices=["tf32x3", "fp32"], default="tf32x3",
                     help="[cnmf_b200] GEMM arithmetic: tcgen05 3xTF32 (default) or FFMA fp32")
     a = ap.parse_args()
@@ -533,7 +571,7 @@ def main():
     if a.command == "prepare":
         obj.prepare(a.counts, components=a.components, n_iter=a.n_iter, densify=a.densify, tpm_fn=a.tpm, seed=a.seed,
                     beta_loss=a.beta_loss, max_NMF_iter=a.max_nmf_iter, num_highvar_genes=a.numgenes,
-                    genes_file=a.genes_file, init=a.init)
+                    genes_file=a.genes_file, init=a.init, on_device=a.prepare_on_device)
     elif a.command == "factorize":
         obj.factorize(worker_i=a.worker_index, total_workers=a.total_workers, skip_completed_runs=a.skip_completed_runs)
     elif a.command == "combine":

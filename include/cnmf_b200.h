@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CNMF_B200_ABI_VERSION 3
+#define CNMF_B200_ABI_VERSION 4
 #define CNMF_MAX_COMPONENTS 32          /* largest n_components per restart on the CUDA path */
 
 typedef struct cnmf_handle_s* cnmf_handle_t;
@@ -101,6 +101,18 @@ int cnmf_dataset_min(cnmf_dataset_t d, float* min_host, void* stream);
 int cnmf_dataset_is_exact(cnmf_dataset_t d);
 /* per-column mean and population variance (StandardScaler(with_mean=False), cnmf.py:131-134) */
 int cnmf_dataset_col_stats(cnmf_dataset_t d, double* mean_host, double* var_host, void* stream);
+
+/* ---- device-side `prepare` numerics (cnmf.py:131-251, 487-556) on a resident counts matrix ------------- */
+/* per-row (cell) totals, fp64: the TPM denominators of compute_tpm / sc.pp.normalize_total (cnmf.py:245-251) */
+int cnmf_dataset_row_sums(cnmf_dataset_t d, double* row_sums_host, void* stream);
+/* per-column mean and population variance of diag(row_scale) * X accumulated in fp64 from the stored values:
+ * with X = raw counts and row_scale = 1e6 / cell total these are the TPM gene statistics that drive the
+ * over-dispersion ranking (get_highvar_genes, cnmf.py:192-242) and `tpm_stats` (cnmf.py:436-445), without
+ * materialising TPM */
+int cnmf_dataset_scaled_col_stats(cnmf_dataset_t d, const double* row_scale_host, double* mean_host, double* var_host,
+                                  void* stream);
+/* new dataset = diag(row_scale) * src (TPM from counts, cnmf.py:245-251); the exact-count detection runs again */
+int cnmf_dataset_scale_rows(cnmf_dataset_t src, const float* row_scale_host, void* stream, cnmf_dataset_t* out);
 
 /* ---- random init (sklearn _nmf.py:296-307; host RNG, bit-exact numpy legacy stream) -- */
 /* Writes |avg*z| as fp32: H (k x n_features, row stride ldH) first, then W stored transposed

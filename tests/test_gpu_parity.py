@@ -486,3 +486,74 @@ def test_k_selection_statistics(tmp_path):
         assert int(stats.loc[row, "k"]) == k
         assert abs(stats.loc[row, "silhouette"] - ref[2]) < 1e-4
         assert abs(stats.loc[row, "prediction_error"] - ref[3]) / ref[3] < 1e-5
+
+
+# ------------------------------------------------------------------------------------ device-side prepare
+def test_prepare_primitives_match_numpy(eng):
+    """Cell totals, row-scaled column statistics and the row-scaled dataset against float64 numpy."""
+    rng = np.random.RandomState(5)
+    C = rng.poisson(0.7, size=(3001, 517)).astype(np.float64)
+    C[:, 3] = 0.0                                   # an all-zero gene
+    C[7] = 0.0
+    C[7, 0] = 2.0
+    ds = eng.dataset(C)
+    tot = ds.row_sums()
+    assert np.array_equal(tot, C.sum(axis=1))       # integers: exact
+    rs = 1e6 / tot
+    T = C * rs[:, None]
+    mean, var = ds.col_stats(row_scale=rs)
+    assert np.allclose(mean, T.mean(axis=0), rtol=1e-13, atol=0)
+    assert np.allclose(var, T.var(axis=0), rtol=1e-10, atol=1e-9)
+    m0, v0 = ds.col_stats()
+    assert np.allclose(m0, C.mean(axis=0), rtol=1e-13) and np.allclose(v0, C.var(axis=0), rtol=1e-11, atol=1e-14)
+    tds = ds.scale_rows(rs)
+    assert tds.exact                                # TPM = integers x per-cell factor: 2-pass products
+    s, q = tds.sums()
+    assert abs(s - T.sum()) / T.sum() < 1e-6 and abs(q - (T ** 2).sum()) / (T ** 2).sum() < 1e-6
+    # columns of a tall matrix (> 65535 rows went through a per-row grid before)
+    big = eng.dataset(rng.poisson(1.0, size=(70001, 40)).astype(np.float64))
+    sub = big.from_columns([5, 1, 39], [0.5, 2.0, 1.0])
+    assert sub.shape == (70001, 3)
+    m, _ = sub.col_stats()
+    mb, _ = big.col_stats()
+    assert np.allclose(m, mb[[5, 1, 39]] * np.array([0.5, 2.0, 1.0]), rtol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["sim_mu"])
+def test_prepare_on_device_matches_reference_outputs(tmp_path, tag):
+    """prepare(on_device=True): HVG choice, normalised counts and TPM statistics equal what the reference wrote
+    (fixture), and factorize() consumes the matrix prepare left in HBM."""
+    import pandas as pd
+    from cnmf_b200 import cNMF, load_df_from_npz, save_df_to_npz
+    from cnmf_b200 import io as cio
+    g = load_golden(tag)
+    counts = g["counts"].astype(np.float64)
+    df = pd.DataFrame(counts, index=["c%d" % i for i in range(counts.shape[0])],
+                      columns=["g%d" % i for i in range(counts.shape[1])])
+    fn = str(tmp_path / "counts.df.npz")
+    save_df_to_npz(df, fn)
+    obj = cNMF(output_dir=str(tmp_path), name="dev")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        obj.prepare(fn, components=list(g["ks"]), n_iter=int(g["n_iter"]), seed=int(g["seed"]), densify=True,
+                    beta_loss=g["beta_loss_arg"], num_highvar_genes=len(g["hvg_idx"]), on_device=True)
+    hvgs = open(obj.paths["nmf_genes_list"]).read().split("\n")
+    assert [int(x[1:]) for x in hvgs] == list(g["hvg_idx"])
+    norm = cio.read_matrix(obj.paths["normalized_counts"])
+    assert np.allclose(norm.X, g["X"], rtol=1e-12, atol=0)
+    stats = load_df_from_npz(obj.paths["tpm_stats"])
+    assert np.allclose(stats["__std"].values, g["tpm_std"], rtol=1e-10)
+    assert obj._resident_norm is not None and obj._resident_norm.shape == norm.X.shape
+    s, _ = obj._resident_norm.sums()
+    assert abs(s - g["X"].sum()) / g["X"].sum() < 1e-6
+    n0 = obj.engine().launch_count
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        obj.factorize()
+    assert obj.engine().launch_count > n0
+    obj.combine()
+    k = int(g["ks"][0])
+    merged = load_df_from_npz(obj.paths["merged_spectra"] % k).values
+    ref = g["merged_k%d" % k]
+    errs = [rel(merged[i * k:(i + 1) * k], ref[i * k:(i + 1) * k]) for i in range(ref.shape[0] // k)]
+    assert np.median(errs) < 1e-5, errs
