@@ -128,28 +128,40 @@ def kmeans(S, k, n_init=10, random_state=1, max_iter=300, tol=1e-4):
         var_mean = float(var.mean())
     tol_abs = var_mean * tol
 
-    labels_t = torch.empty(R, dtype=torch.int32, device=S.t.device)
-    mind_t = torch.empty(R, dtype=torch.float32, device=S.t.device)
-    sums = np.empty((k, G), np.float64)
-    counts = np.empty(k, np.int32)
+    dev = S.t.device
+    labels_t = torch.empty(R, dtype=torch.int32, device=dev)
+    mind_t = torch.empty(R, dtype=torch.float32, device=dev)
+    # centres stay on the device across Lloyd iterations (fp64 master + fp32 copy for the E step, ping-pong):
+    # an iteration returns three scalars instead of a K x G round trip
+    C64 = [torch.empty((k, G), dtype=torch.float64, device=dev) for _ in range(2)]
+    C32 = [torch.empty((k, G), dtype=torch.float32, device=dev) for _ in range(2)]
+    sums_t = torch.empty((k, G), dtype=torch.float64, device=dev)
+    counts_t = torch.empty(k, dtype=torch.int32, device=dev)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())        # noqa: E731
     n_changed = ctypes.c_int32(0)
+    any_empty = ctypes.c_int32(0)
+    shift = ctypes.c_double(0)
     inertia = ctypes.c_double(0)
     best = None
     for _ in range(n_init):
         idx = _kmeans_plusplus(S, k, rng)
         centers = S.take_rows(idx).numpy().astype(np.float64)
+        cur = 0
+        C64[cur].copy_(torch.from_numpy(centers))
+        C32[cur].copy_(torch.from_numpy(np.ascontiguousarray(centers, dtype=np.float32)))
         labels_t.fill_(-1)
-        strict = False
         n_it = 0
         for n_it in range(max_iter):
-            c32 = np.ascontiguousarray(centers, dtype=np.float32)
-            check(lib.cnmf_kmeans_assign(h, S.p, R, G, S.ld, ptr(c32), k, ctypes.c_void_p(labels_t.data_ptr()),
-                                         ptr(sums), ptr(counts), ctypes.c_void_p(mind_t.data_ptr()),
-                                         ctypes.byref(n_changed), None, None))
-            new = sums.copy()
-            weight = counts.astype(np.float64)
-            empty = np.where(weight == 0)[0]
-            if len(empty) > 0:                      # sklearn _k_means_common.pyx:167-211
+            new = 1 - cur
+            check(lib.cnmf_kmeans_step(h, S.p, R, G, S.ld, k, vp(C32[cur]), vp(C64[cur]), vp(C64[new]), vp(C32[new]),
+                                       vp(labels_t), vp(mind_t), vp(sums_t), vp(counts_t), ctypes.byref(n_changed),
+                                       ctypes.byref(any_empty), ctypes.byref(shift), None))
+            shift_tot = shift.value
+            if any_empty.value:                       # rare: relocation rule on the host, sklearn _k_means_common.pyx:167-211
+                centers = C64[cur].cpu().numpy()
+                nc = sums_t.cpu().numpy().copy()
+                weight = counts_t.cpu().numpy().astype(np.float64)
+                empty = np.where(weight == 0)[0]
                 dist = mind_t.cpu().numpy().astype(np.float64)
                 if dist.max() != 0:
                     lab = labels_t.cpu().numpy()
@@ -157,23 +169,25 @@ def kmeans(S, k, n_init=10, random_state=1, max_iter=300, tol=1e-4):
                     rows = S.take_rows(far).numpy().astype(np.float64)
                     for j, new_id in enumerate(empty):
                         old_id = lab[far[j]]
-                        new[old_id] -= rows[j]
-                        new[new_id] = rows[j]
+                        nc[old_id] -= rows[j]
+                        nc[new_id] = rows[j]
                         weight[new_id] = 1
                         weight[old_id] -= 1
-            amax = int(np.argmax(weight))
-            for j in range(k):                      # _average_centers, _k_means_common.pyx:274-298
-                if weight[j] > 0:
-                    new[j] *= 1.0 / weight[j]
-                else:
-                    new[j] = new[amax]
-            shift_tot = float(((new - centers) ** 2).sum())
-            centers = new
+                amax = int(np.argmax(weight))
+                for j in range(k):                    # _average_centers, _k_means_common.pyx:274-298
+                    if weight[j] > 0:
+                        nc[j] *= 1.0 / weight[j]
+                    else:
+                        nc[j] = nc[amax]
+                shift_tot = float(((nc - centers) ** 2).sum())
+                C64[new].copy_(torch.from_numpy(nc))
+                C32[new].copy_(torch.from_numpy(np.ascontiguousarray(nc, dtype=np.float32)))
+            cur = new
             if n_changed.value == 0:
-                strict = True
                 break
             if shift_tot <= tol_abs:
                 break
+        centers = C64[cur].cpu().numpy()
         c32 = np.ascontiguousarray(centers, dtype=np.float32)
         # final E step (labels consistent with the final centres) + inertia
         check(lib.cnmf_kmeans_assign(h, S.p, R, G, S.ld, ptr(c32), k, ctypes.c_void_p(labels_t.data_ptr()),

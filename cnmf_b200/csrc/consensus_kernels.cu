@@ -54,18 +54,25 @@ __global__ void l2_normalize_kernel(float* __restrict__ S, int R, int G, int ld)
 }
 
 // ---------------------------------------------------------------- C2: D[i][j] = sqrt(sum_g (A_i - B_j)^2)
-// 64 x 64 output tile per block, 16 x 16 threads, 4 x 4 per thread, k-tiles of 16 through smem.
-template <bool SQRT>
+// 64 x 64 output tile per block, 16 x 16 threads, 4 x 4 per thread, k-tiles of 16 through smem.  The inner product
+// runs on packed fp32 (FADD2 with a broadcast operand, FFMA2): one instruction per element pair instead of two --
+// this kernel is FP32-issue bound, not HBM-bound (profiles/r1h_ncu_consensus_summary.txt).  SYM (A == B, the R x R
+// matrix of cnmf.py:891): only tiles on or above the diagonal are computed, each is also written transposed, so the
+// matrix is exactly symmetric with an exactly zero diagonal at half the work.
+template <bool SQRT, bool SYM>
 __global__ void __launch_bounds__(256)
 pair_dist_kernel(const float* __restrict__ A, int RA, int lda, const float* __restrict__ B, int RB, int ldb, int G,
                  float* __restrict__ D, int ldd) {
   constexpr int T = 64, TK = 16;
-  __shared__ float As[TK][T + 4];
-  __shared__ float Bs[TK][T + 4];
+  if (SYM && blockIdx.x < blockIdx.y) return;
+  __shared__ __align__(16) float As[TK][T + 4];
+  __shared__ __align__(16) float Bs[TK][T + 4];
   const int i0 = blockIdx.y * T, j0 = blockIdx.x * T;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int lrow = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;
-  float acc[4][4] = {};
+  float2 acc[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
   for (int k0 = 0; k0 < G; k0 += TK) {
     {
       float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
@@ -88,16 +95,24 @@ pair_dist_kernel(const float* __restrict__ A, int RA, int lda, const float* __re
     for (int k = 0; k < TK; ++k) {
       const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
       const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float2 nb0 = make_float2(-b.x, -b.y), nb1 = make_float2(-b.z, -b.w);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float d = av[i] - bv[j];
-          acc[i][j] = fmaf(d, d, acc[i][j]);
-        }
+      for (int i = 0; i < 4; ++i) {
+        const float2 d0 = add2(bcast2(av[i]), nb0), d1 = add2(bcast2(av[i]), nb1);
+        acc[i][0] = fma2(d0, d0, acc[i][0]);
+        acc[i][1] = fma2(d1, d1, acc[i][1]);
+      }
     }
     __syncthreads();
+  }
+  float o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o[i][0] = acc[i][0].x; o[i][1] = acc[i][0].y; o[i][2] = acc[i][1].x; o[i][3] = acc[i][1].y;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (SQRT) o[i][j] = sqrtf(o[i][j]);
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -106,8 +121,63 @@ pair_dist_kernel(const float* __restrict__ A, int RA, int lda, const float* __re
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = j0 + tx * 4 + j;
-      if (c < RB) D[(long long)r * ldd + c] = SQRT ? sqrtf(acc[i][j]) : acc[i][j];
+      if (c < RB) D[(long long)r * ldd + c] = o[i][j];
     }
+  }
+  if (SYM && blockIdx.x != blockIdx.y) {             // mirror image of an off-diagonal tile
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = j0 + tx * 4 + j;
+      if (c >= RB) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i0 + ty * 4 + i;
+        if (r < RA) D[(long long)c * ldd + r] = o[i][j];
+      }
+    }
+  }
+}
+
+// k-means++ candidate scoring (sklearn _kmeans.py:231-262): squared distances from every row of S to a handful of
+// candidate rows of S.  HBM-bound form: one warp per row streams it once with 16-byte loads against the (L1-hot)
+// candidate rows, differences in fp32, squares accumulated in fp64 (sklearn scores candidates in float64).  The
+// 64 x 64-tile kernel above needed 200 us for this shape (60 blocks, latency-bound); 19 calls per init made the
+// seeding, not Lloyd, the cost of KMeans (profiles/r1h_ncu_consensus_summary.txt).
+template <int NC>
+__global__ void __launch_bounds__(256)
+cand_dist_kernel(const float* __restrict__ S, int R, int G, int ld, const int32_t* __restrict__ idx, int n_c,
+                 float* __restrict__ out /* n_c x R */) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float4* row = reinterpret_cast<const float4*>(S + (long long)r * ld);
+  const float4* cand[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) cand[c] = reinterpret_cast<const float4*>(S + (long long)idx[c < n_c ? c : 0] * ld);
+  double acc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+  const int g4 = G / 4;
+  for (int q = lane; q < g4; q += 32) {
+    const float4 x = row[q];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float4 y = cand[c][q];
+      const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+      acc[c] += (double)d0 * d0 + (double)d1 * d1 + (double)d2 * d2 + (double)d3 * d3;
+    }
+  }
+  for (int g = 4 * g4 + lane; g < G; g += 32) {      // ragged tail
+    const float x = S[(long long)r * ld + g];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float d = x - S[(long long)idx[c < n_c ? c : 0] * ld + g];
+      acc[c] += (double)d * d;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const double v = warp_sum(acc[c]);
+    if (lane == 0 && c < n_c) out[(long long)c * R + r] = (float)v;
   }
 }
 
@@ -205,6 +275,36 @@ cluster_sums_kernel(const float* __restrict__ S, int G, int ld, const int32_t* _
   double a = 0.0;
   for (int i = 0; i < n; ++i) a += (double)S[(long long)mem[i] * ld + g];
   sums[(long long)c * G + g] = a;
+}
+
+// M step, second half, on the device: new centre = sums * (1 / count) (sklearn _k_means_common.pyx:274-298),
+// squared shift against the current centre, fp32 copy for the next E step.  One block per cluster; a cluster
+// without members raises `any_empty` and is left to the host's relocation rule (the caller keeps the old centres).
+__global__ void __launch_bounds__(256)
+centre_update_kernel(const double* __restrict__ sums, const int32_t* __restrict__ counts, int G,
+                     const double* __restrict__ C64_cur, double* __restrict__ C64_new, float* __restrict__ C32_new,
+                     double* __restrict__ shift_part, int* __restrict__ any_empty) {
+  __shared__ double sm[33];
+  const int j = blockIdx.x;
+  const int w = counts[j];
+  if (w == 0) {
+    if (threadIdx.x == 0) {
+      atomicExch(any_empty, 1);
+      shift_part[j] = 0.0;
+    }
+    return;
+  }
+  const double inv = 1.0 / (double)w;
+  double acc = 0.0;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    const double nv = sums[(long long)j * G + g] * inv;
+    const double d = nv - C64_cur[(long long)j * G + g];
+    acc += d * d;
+    C64_new[(long long)j * G + g] = nv;
+    C32_new[(long long)j * G + g] = (float)nv;
+  }
+  acc = block_sum_all(acc, sm);
+  if (threadIdx.x == 0) shift_part[j] = acc;
 }
 
 __global__ void sum_float_kernel(const float* __restrict__ v, int n, double* __restrict__ out) {
@@ -344,7 +444,7 @@ int cnmf_local_density(cnmf_handle_t h, const float* S, int R, int G, int ld, in
   float* D = D_dev ? D_dev : static_cast<float*>(h->dev_buf("consensus.D", (size_t)R * R * 4));
   if (!D) return -2;
   dim3 grid((R + 63) / 64, (R + 63) / 64);
-  pair_dist_kernel<true><<<grid, 256, 0, s>>>(S, R, ld, S, R, ld, G, D, R);
+  pair_dist_kernel<true, true><<<grid, 256, 0, s>>>(S, R, ld, S, R, ld, G, D, R);
   CNMF_CUDA_CHECK(cudaGetLastError());
   knn_density_kernel<<<R, 256, 0, s>>>(D, R, R, n_neighbors + 1, n_neighbors, density_dev);
   CNMF_CUDA_CHECK(cudaGetLastError());
@@ -382,7 +482,7 @@ int cnmf_cluster_dist_sums(cnmf_handle_t h, const float* S, int R, int G, int ld
   double* out = static_cast<double*>(h->dev_buf("consensus.dsums", sizeof(double) * (size_t)R * K));
   if (!D || !out) return -2;
   dim3 grid((R + 63) / 64, (R + 63) / 64);
-  pair_dist_kernel<true><<<grid, 256, 0, s>>>(S, R, ld, S, R, ld, G, D, R);
+  pair_dist_kernel<true, true><<<grid, 256, 0, s>>>(S, R, ld, S, R, ld, G, D, R);
   cluster_dist_sums_kernel<<<R, 256, sizeof(double) * 8 * K, s>>>(D, R, labels_dev, K, out);
   CNMF_CUDA_CHECK(cudaGetLastError());
   h->launches += 2;
@@ -416,9 +516,16 @@ int cnmf_sq_dists_to_rows(cnmf_handle_t h, const float* S, int R, int G, int ld,
   int32_t* d_idx = static_cast<int32_t*>(h->dev_buf("consensus.idx", sizeof(int32_t) * std::max(n_c, 1)));
   if (!C || !out || !d_idx) return -2;
   CNMF_CUDA_CHECK(cudaMemcpyAsync(d_idx, idx_host, sizeof(int32_t) * n_c, cudaMemcpyHostToDevice, s));
-  gather_rows_idx_kernel<<<n_c, 256, 0, s>>>(S, ld, d_idx, G, C, ld);
-  dim3 grid((R + 63) / 64, (n_c + 63) / 64);
-  pair_dist_kernel<false><<<grid, 256, 0, s>>>(C, n_c, ld, S, R, ld, G, out, R);
+  if (n_c <= 8 && ld % 4 == 0) {
+    const int blocks = (R * 32 + 255) / 256;
+    if (n_c <= 2) cand_dist_kernel<2><<<blocks, 256, 0, s>>>(S, R, G, ld, d_idx, n_c, out);
+    else if (n_c <= 4) cand_dist_kernel<4><<<blocks, 256, 0, s>>>(S, R, G, ld, d_idx, n_c, out);
+    else cand_dist_kernel<8><<<blocks, 256, 0, s>>>(S, R, G, ld, d_idx, n_c, out);
+  } else {
+    gather_rows_idx_kernel<<<n_c, 256, 0, s>>>(S, ld, d_idx, G, C, ld);
+    dim3 grid((R + 63) / 64, (n_c + 63) / 64);
+    pair_dist_kernel<false, false><<<grid, 256, 0, s>>>(C, n_c, ld, S, R, ld, G, out, R);
+  }
   CNMF_CUDA_CHECK(cudaGetLastError());
   CNMF_CUDA_CHECK(cudaMemcpyAsync(out_host, out, (size_t)n_c * R * 4, cudaMemcpyDeviceToHost, s));
   CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -461,6 +568,40 @@ int cnmf_kmeans_assign(cnmf_handle_t h, const float* S, int R, int G, int ld, co
   }
   if (n_changed_host) CNMF_CUDA_CHECK(cudaMemcpyAsync(n_changed_host, n_changed, sizeof(int), cudaMemcpyDeviceToHost, s));
   CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int cnmf_kmeans_step(cnmf_handle_t h, const float* S, int R, int G, int ld, int K, const float* C32_cur,
+                     const double* C64_cur, double* C64_new, float* C32_new, int32_t* labels_dev, float* mind_dev,
+                     double* sums_dev, int32_t* counts_dev, int32_t* n_changed_host, int32_t* any_empty_host,
+                     double* shift_host, void* stream) {
+  CNMF_REQUIRE(h && S && C32_cur && C64_cur && C64_new && C32_new && labels_dev && mind_dev && sums_dev && counts_dev &&
+                   n_changed_host && any_empty_host && shift_host && K >= 1 && K <= 1024 && R > 0,
+               "kmeans_step: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  int32_t* order = static_cast<int32_t*>(h->dev_buf("kmeans.order", sizeof(int32_t) * (size_t)K * R));
+  int32_t* flags = static_cast<int32_t*>(h->dev_buf("kmeans.flags", sizeof(int32_t) * 2));
+  double* shift_part = static_cast<double*>(h->dev_buf("kmeans.shift", sizeof(double) * K));
+  struct HostOut { int32_t flags[2]; double shift[1024]; };
+  HostOut* ho = static_cast<HostOut*>(h->host_buf("kmeans.step_out", sizeof(HostOut)));
+  if (!order || !flags || !shift_part || !ho) return -2;
+  CNMF_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int32_t) * 2, s));
+  kmeans_assign_kernel<<<(R * 32 + 255) / 256, 256, 0, s>>>(S, R, G, ld, C32_cur, K, G, labels_dev, mind_dev, flags);
+  members_kernel<<<1, 1024, 0, s>>>(labels_dev, R, K, counts_dev, order);
+  dim3 grid((G + 127) / 128, K);
+  cluster_sums_kernel<<<grid, 128, 0, s>>>(S, G, ld, counts_dev, order, R, sums_dev);
+  centre_update_kernel<<<K, 256, 0, s>>>(sums_dev, counts_dev, G, C64_cur, C64_new, C32_new, shift_part, flags + 1);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  h->launches += 4;
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(ho->flags, flags, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(ho->shift, shift_part, sizeof(double) * K, cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  *n_changed_host = ho->flags[0];
+  *any_empty_host = ho->flags[1];
+  double tot = 0.0;
+  for (int j = 0; j < K; ++j) tot += ho->shift[j];      // fixed order
+  *shift_host = tot;
   return 0;
 }
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CNMF_B200_ABI_VERSION 4
+#define CNMF_B200_ABI_VERSION 5
 #define CNMF_MAX_COMPONENTS 32          /* largest n_components per restart on the CUDA path */
 
 typedef struct cnmf_handle_s* cnmf_handle_t;
@@ -193,6 +193,16 @@ int cnmf_sq_dists_to_rows(cnmf_handle_t h, const float* S_dev, int R, int G, int
 int cnmf_kmeans_assign(cnmf_handle_t h, const float* S_dev, int R, int G, int ld, const float* centers_host, int K,
                        int32_t* labels_dev, double* sums_host, int32_t* counts_host, float* mind_dev,
                        int32_t* n_changed_host, double* inertia_host, void* stream);
+/* one full Lloyd iteration with the centres resident on the device (the loop of sklearn _kmeans.py:630-758 without a
+ * K x G round trip per iteration): E step against C32_cur (labels_dev / mind_dev updated), fp64 per-cluster sums and
+ * counts (sums_dev K x G, counts_dev K), new centres = sums / count into C64_new (fp64) and C32_new (their fp32 copy
+ * for the next E step).  Host outputs: labels that changed, whether a cluster came out empty (then C*_new are not
+ * valid for it: the caller applies the relocation rule of _k_means_common.pyx:167-211 from sums_dev / counts_dev and
+ * the current centres, which this call leaves untouched), and sum((C64_new - C64_cur)^2) over the non-empty clusters. */
+int cnmf_kmeans_step(cnmf_handle_t h, const float* S_dev, int R, int G, int ld, int K, const float* C32_cur_dev,
+                     const double* C64_cur_dev, double* C64_new_dev, float* C32_new_dev, int32_t* labels_dev,
+                     float* mind_dev, double* sums_dev, int32_t* counts_dev, int32_t* n_changed_host,
+                     int32_t* any_empty_host, double* shift_host, void* stream);
 /* sums_host[i*K + c] = sum over rows j with label c of ||S_i - S_j||_2 : the per-sample cluster distance sums
  * from which sklearn.metrics.silhouette_score(metric='euclidean') is formed (cnmf.py:923, k_selection) */
 int cnmf_cluster_dist_sums(cnmf_handle_t h, const float* S_dev, int R, int G, int ld, const int32_t* labels_dev,
