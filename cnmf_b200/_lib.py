@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcnmf_b200.so")
 
 SOLVER_MU, SOLVER_CD = 0, 1
-PRECISION_FP32, PRECISION_TF32X3, PRECISION_TF32X3_GENERAL = 0, 1, 2
+PRECISION_FP32, PRECISION_TF32X3, PRECISION_TF32X3_GENERAL, PRECISION_F16X2 = 0, 1, 2, 3
 LOSS_FROBENIUS, LOSS_KULLBACK_LEIBLER, LOSS_ITAKURA_SAITO = 0, 1, 2
 MAX_COMPONENTS = 32
 
@@ -80,7 +80,7 @@ SIGNATURES = {
 _lib = None
 
 
-ABI_VERSION = 5      # include/cnmf_b200.h CNMF_B200_ABI_VERSION
+ABI_VERSION = 6      # include/cnmf_b200.h CNMF_B200_ABI_VERSION
 
 
 def load():

@@ -271,6 +271,17 @@ static int dataset_finish(cnmf_dataset_s* d, cudaStream_t s) {
       CNMF_TRY(launch_build_counts(d->X, d->n_rows, d->n_cols, d->ld_c, d->row_scale, d->col_scale, d->X_hi, s));
       CNMF_TRY(launch_transpose(d->X_hi, d->n_rows, d->n_cols, d->ld_c, d->Xt_hi, nullptr, nullptr, d->ld_r, s));
       h->launches += 2;
+      if (d->want_f16) {       // counts <= 2048 are exact in fp16: the B operands of the kind::f16 products
+        float *xh = nullptr, *xth = nullptr;
+        CNMF_TRY(dataset_alloc(d, &xh, (nx + 1) / 2));
+        CNMF_TRY(dataset_alloc(d, &xth, (nxt + 1) / 2));
+        d->X_h16 = xh;
+        d->Xt_h16 = xth;
+        CNMF_TRY(launch_to_half(d->X_hi, d->X_h16, (long long)nx, s));
+        CNMF_TRY(launch_to_half(d->Xt_hi, d->Xt_h16, (long long)nxt, s));
+        h->launches += 2;
+        d->f16 = true;
+      }
     } else {
     CNMF_TRY(dataset_alloc(d, &d->X_hi, nx));
     CNMF_TRY(dataset_alloc(d, &d->X_lo, nx));
@@ -306,7 +317,8 @@ int cnmf_dataset_create(cnmf_handle_t h, const float* X, int n_rows, int n_cols,
   CNMF_REQUIRE(h && X && out, "dataset_create: NULL argument");
   CNMF_REQUIRE(n_rows > 0 && n_cols > 0 && ld >= n_cols, "dataset_create: bad shape");
   CNMF_REQUIRE(precision == CNMF_PRECISION_FP32 || precision == CNMF_PRECISION_TF32X3 ||
-                   precision == CNMF_PRECISION_TF32X3_GENERAL, "dataset_create: bad precision");
+                   precision == CNMF_PRECISION_TF32X3_GENERAL || precision == CNMF_PRECISION_F16X2,
+               "dataset_create: bad precision");
   cudaStream_t s = as_stream(stream);
   CNMF_CUDA_CHECK(cudaSetDevice(h->device));
   auto* d = new cnmf_dataset_s();
@@ -316,7 +328,9 @@ int cnmf_dataset_create(cnmf_handle_t h, const float* X, int n_rows, int n_cols,
   d->ld_c = pad_ld(n_cols);
   d->ld_r = pad_ld(n_rows);
   d->allow_exact = precision != CNMF_PRECISION_TF32X3_GENERAL;
-  d->precision = precision == CNMF_PRECISION_TF32X3_GENERAL ? CNMF_PRECISION_TF32X3 : precision;
+  d->want_f16 = precision == CNMF_PRECISION_F16X2;
+  d->precision = (precision == CNMF_PRECISION_TF32X3_GENERAL || precision == CNMF_PRECISION_F16X2) ? CNMF_PRECISION_TF32X3
+                                                                                                : precision;
   int rc = dataset_alloc(d, &d->X, (size_t)n_rows * d->ld_c);
   if (rc == 0) {
     cudaError_t e = cudaMemsetAsync(d->X, 0, (size_t)n_rows * d->ld_c * sizeof(float), s);
@@ -360,7 +374,7 @@ int cnmf_dataset_shape(cnmf_dataset_t d, int* n_rows, int* n_cols) {
   return 0;
 }
 
-int cnmf_dataset_is_exact(cnmf_dataset_t d) { return (d && d->exact) ? 1 : 0; }
+int cnmf_dataset_is_exact(cnmf_dataset_t d) { return (d && d->exact) ? (d->f16 ? 2 : 1) : 0; }
 
 int cnmf_dataset_sums(cnmf_dataset_t d, double* sum, double* sum_sq) {
   CNMF_REQUIRE(d, "dataset_sums: NULL dataset");

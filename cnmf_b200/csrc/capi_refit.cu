@@ -183,6 +183,7 @@ int cnmf_dataset_from_columns(cnmf_dataset_t src, const int32_t* cols_host, cons
   d->ld_r = pad_ld(src->n_rows);
   d->precision = src->precision;
   d->allow_exact = src->allow_exact;
+  d->want_f16 = src->want_f16;
   int rc = cnmf_dataset_alloc_internal(d, &d->X, (size_t)d->n_rows * d->ld_c);
   if (rc == 0) {
     cudaError_t e = cudaMemsetAsync(d->X, 0, (size_t)d->n_rows * d->ld_c * sizeof(float), s);
@@ -235,6 +236,7 @@ int cnmf_dataset_scale_rows(cnmf_dataset_t src, const float* row_scale_host, voi
   d->ld_r = src->ld_r;
   d->precision = src->precision;
   d->allow_exact = src->allow_exact;
+  d->want_f16 = src->want_f16;
   int rc = cnmf_dataset_alloc_internal(d, &d->X, (size_t)d->n_rows * d->ld_c);
   if (rc == 0) {
     scale_rows_kernel<<<148 * 8, 256, 0, s>>>(src->X, d->n_rows, d->n_cols, d->ld_c, d_rs, d->X);
@@ -390,7 +392,7 @@ int cnmf_gemm_abt_host(cnmf_handle_t h, int precision, const float* A, const flo
   float* dAl = static_cast<float*>(h->dev_buf("gemmtest.Al", na * 4));
   float* dBh = static_cast<float*>(h->dev_buf("gemmtest.Bh", nb * 4));
   float* dBl = static_cast<float*>(h->dev_buf("gemmtest.Bl", nb * 4));
-  const int se = gemm_effective_splits(Kd, splits);
+  const int se = gemm_effective_splits(Kd, splits, precision == CNMF_PRECISION_F16X2 ? 1 : 0);
   float* dC = static_cast<float*>(h->dev_buf("gemmtest.C", (size_t)se * M * ldc * 4));
   if (!dA || !dB || !dAh || !dAl || !dBh || !dBl || !dC) return -2;
   CNMF_CUDA_CHECK(cudaMemsetAsync(dA, 0, na * 4, s));
@@ -403,16 +405,24 @@ int cnmf_gemm_abt_host(cnmf_handle_t h, int precision, const float* A, const flo
   GemmArgs g{};
   g.M = M; g.N = N; g.Kd = Kd; g.lda = lda; g.ldb = lda; g.ldc = ldc;
   g.C = dC; g.c_split_stride = (long long)M * ldc; g.splits = splits; g.splits_effective = se;
-  if (precision == CNMF_PRECISION_TF32X3) { g.A_hi = dAh; g.A_lo = dAl; g.B_hi = dBh; g.B_lo = dBl; }
+  const bool f16 = precision == CNMF_PRECISION_F16X2;    // B must hold integers <= 2048 (exact in fp16)
+  if (f16) {
+    float* dRs = static_cast<float*>(h->dev_buf("gemmtest.rs", sizeof(float) * M));
+    if (!dRs) return -2;
+    CNMF_TRY(launch_emit_f16(dA, M, Kd, lda, nullptr, dAh, dAl, dRs, s));
+    CNMF_TRY(launch_to_half(dB, dBh, (long long)nb, s));
+    g.A_hi = dAh; g.A_lo = dAl; g.B_hi = dBh; g.b_exact = 1; g.f16 = 1; g.out_row_scale = dRs;
+  } else if (precision == CNMF_PRECISION_TF32X3) { g.A_hi = dAh; g.A_lo = dAl; g.B_hi = dBh; g.B_lo = dBl; }
   else { g.A_hi = dA; g.B_hi = dB; }
+  const bool tc = f16 || precision == CNMF_PRECISION_TF32X3;
   cudaEvent_t e0, e1;
   CNMF_CUDA_CHECK(cudaEventCreate(&e0));
   CNMF_CUDA_CHECK(cudaEventCreate(&e1));
   if (reps < 1) reps = 1;
-  int rc = precision == CNMF_PRECISION_TF32X3 ? gemm_tf32x3(g, s) : gemm_fp32_simt(g, s);   // warm-up + result
+  int rc = tc ? gemm_tf32x3(g, s) : gemm_fp32_simt(g, s);   // warm-up + result
   if (rc == 0 && reps > 1) {
     cudaEventRecord(e0, s);
-    for (int i = 0; i < reps && rc == 0; ++i) rc = precision == CNMF_PRECISION_TF32X3 ? gemm_tf32x3(g, s) : gemm_fp32_simt(g, s);
+    for (int i = 0; i < reps && rc == 0; ++i) rc = tc ? gemm_tf32x3(g, s) : gemm_fp32_simt(g, s);
     cudaEventRecord(e1, s);
   }
   h->launches += reps;

@@ -63,6 +63,10 @@ struct cnmf_dataset_s {
   // product needs 2 tensor-core passes instead of 3.  Either scale may be nullptr (= 1).
   bool exact = false;
   bool allow_exact = true;
+  // f16x2 precision: requested at creation (want_f16); active (f16) once the dataset turned out exact.  X_h16 / Xt_h16
+  // hold the integer matrices C / C^T as fp16 (same shapes and element strides as X_hi / Xt_hi)
+  bool want_f16 = false, f16 = false;
+  void *X_h16 = nullptr, *Xt_h16 = nullptr;
   float *row_scale = nullptr, *col_scale = nullptr;    // lengths ld_r / ld_c, zero padded
   double sum = 0.0, sum_sq = 0.0;
   std::vector<std::pair<void*, size_t>> owned;
@@ -76,6 +80,7 @@ struct Operand {     // a K-major matrix as the GEMM sees it
   const float* full;
   const float* hi;     // tf32 hi piece, or the exact integer matrix when `exact`
   const float* lo;
+  const void* h16;     // the exact integer matrix as fp16 (f16x2 datasets), else nullptr
   int rows, cols, ld;
 };
 
@@ -87,6 +92,7 @@ struct DataView {
   int n_r, n_c, ld_r, ld_c;
   double sum, sum_sq;
   bool exact;               // both operands hold exact integers; scales below complete X
+  bool f16;                 // fp16 operand path active (exact datasets created with CNMF_PRECISION_F16X2)
   const float* scale_r;     // per row-item scale (length ld_r) or nullptr
   const float* scale_c;     // per column-item scale (length ld_c) or nullptr
 };

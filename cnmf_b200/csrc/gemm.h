@@ -19,15 +19,20 @@ struct GemmArgs {
   int bn;                     // tf32x3: tile width (UMMA N); 0 = choose from (M, N, Kd, splits)
   int b_exact;                // tf32x3: B_hi holds B exactly (tf32-representable values); B_lo unused -> 2 passes
   const float* out_col_scale; // optional: C[:, n] *= out_col_scale[n] (length >= ldc, 16-byte aligned, zero padded)
+  // f16 = 1 (tcgen05 path, b_exact only): A_hi / A_lo / B_hi point to __half arrays (two fp16 pieces of the row-
+  // normalised A, the integer matrix B), lda / ldb are in half elements, k-blocks hold 64 elements; kind::f16 MMAs run
+  // at twice the kind::tf32 rate and carry the same 11-bit significand per piece
+  int f16;
+  const float* out_row_scale; // optional: C[m, :] *= out_row_scale[m] (the per-row power of two the A pieces were divided by)
 };
 
-// number of non-empty split-K slices for a reduction length Kd (k-blocks of 32)
-int gemm_effective_splits(int Kd, int splits);
+// number of non-empty split-K slices for a reduction length Kd (k-blocks of 32 fp32 / 64 fp16 elements = 128 B)
+int gemm_effective_splits(int Kd, int splits, int f16 = 0);
 
 // Joint choice of the split-K factor and the tile width for the tcgen05 kernel: minimises
 // (waves of the persistent grid) x (tile cost) x (k-blocks per item + pipeline fill), with a mild penalty per
 // extra split-K slice (its partial output is written and re-read by the update kernel).
-void gemm_plan(int M, int N, int Kd, int sm_count, int* splits, int* bn);
+void gemm_plan(int M, int N, int Kd, int sm_count, int* splits, int* bn, int f16 = 0);
 
 // tcgen05 / TMEM / TMA path (gemm_tf32x3.cu)
 int gemm_tf32x3(const GemmArgs& g, cudaStream_t stream);

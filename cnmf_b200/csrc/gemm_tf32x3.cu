@@ -110,6 +110,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -126,9 +134,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
+template <bool F16>
 __device__ __forceinline__ uint32_t make_idesc(int bn) {
-  // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major A and B, N>>3 @17, M>>4 @24
-  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
+  // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a/b format @7/@10 (TF32 = 2, F16 = 0), K-major A and B, N>>3 @17, M>>4 @24
+  const uint32_t fmt = F16 ? 0u : 2u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
          (static_cast<uint32_t>(BM >> 4) << 24);
 }
 
@@ -147,13 +157,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ the kernel
-template <int BN, int STAGES, bool BEXACT>
+// F16 (with BEXACT): operands are fp16 (two pieces of A, one exact B); a k-block is still 128 B per row = 64 elements,
+// a k-step still 32 B = 16 elements (UMMA_K of kind::f16), so the smem / TMA / descriptor byte geometry is unchanged.
+template <int BN, int STAGES, bool BEXACT, bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    float* __restrict__ C, int M, int N, int ldc, long long c_split_stride,
                    int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split, int chain_kb, int bn,
-                   const float* __restrict__ out_scale) {
+                   const float* __restrict__ out_scale, const float* __restrict__ out_row_scale) {
+  static_assert(!F16 || BEXACT, "the fp16 path exists for exact integer B operands only");
+  constexpr int BKE = F16 ? 2 * BK : BK;                        // elements per k-block
   using L = SmemLayout<BN, STAGES, BEXACT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024 B alignment
@@ -209,10 +223,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           const uint32_t st = smem_base + stage * L::STAGE_BYTES;
           mbar_arrive_expect_tx(full_bar(stage),
                                 2u * L::A_BYTES + (BEXACT ? 1u : 2u) * static_cast<uint32_t>(bn) * BK * 4u);
-          tma_load_2d(st, &tmA_hi, full_bar(stage), kb * BK, mt * BM);
-          tma_load_2d(st + L::A_BYTES, &tmA_lo, full_bar(stage), kb * BK, mt * BM);
-          tma_load_2d(st + 2 * L::A_BYTES, &tmB_hi, full_bar(stage), kb * BK, nt * bn);
-          if constexpr (!BEXACT) tma_load_2d(st + 2 * L::A_BYTES + L::B_BYTES, &tmB_lo, full_bar(stage), kb * BK, nt * bn);
+          tma_load_2d(st, &tmA_hi, full_bar(stage), kb * BKE, mt * BM);
+          tma_load_2d(st + L::A_BYTES, &tmA_lo, full_bar(stage), kb * BKE, mt * BM);
+          tma_load_2d(st + 2 * L::A_BYTES, &tmB_hi, full_bar(stage), kb * BKE, nt * bn);
+          if constexpr (!BEXACT) tma_load_2d(st + 2 * L::A_BYTES + L::B_BYTES, &tmB_lo, full_bar(stage), kb * BKE, nt * bn);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -220,7 +234,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(bn);               // UMMA N = bn (multiple of 16, <= BN)
+      const uint32_t idesc = make_idesc<F16>(bn);          // UMMA N = bn (multiple of 16, <= BN)
       int stage = 0;
       uint32_t phase = 0;
       int buf = 0;
@@ -245,9 +259,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 4) >> 4);   // +32 B per k-step inside the swizzle row
-              umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, (kb > c0 || k > 0) ? 1u : 0u);   // small terms first
-              if constexpr (!BEXACT) umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1u);
-              umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, 1u);
+              if constexpr (F16) {
+                umma_f16(tmem_d, a_lo + koff, b_hi + koff, idesc, (kb > c0 || k > 0) ? 1u : 0u);    // small terms first
+                umma_f16(tmem_d, a_hi + koff, b_hi + koff, idesc, 1u);
+              } else {
+                umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, (kb > c0 || k > 0) ? 1u : 0u);   // small terms first
+                if constexpr (!BEXACT) umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1u);
+                umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, 1u);
+              }
             }
             umma_commit(empty_bar(stage));         // smem slot is free once these MMAs have read it
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -298,10 +317,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       if (row < M) {
         float* crow = C + static_cast<long long>(z) * c_split_stride + static_cast<long long>(row) * ldc;
         const int col0 = nt * bn + half * HALF;
+        const float rs = out_row_scale ? out_row_scale[row] : 1.f;   // power of two: exact
 #pragma unroll
         for (int i = 0; i < HALF; i += 4) {
           if (half * HALF + i < bn && col0 + i + 3 < ldc) {
-            float4 v = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+            float4 v = make_float4(acc[i] * rs, acc[i + 1] * rs, acc[i + 2] * rs, acc[i + 3] * rs);
             if (out_scale) {                            // per-output-column scale (length >= ldc, zero padded)
               const float4 sc = *reinterpret_cast<const float4*>(out_scale + col0 + i);
               v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
@@ -340,14 +360,15 @@ PFN_encodeTiled get_encode_fn() {
 }
 
 // 2D fp32 tensor (rows x cols, row stride ld elements), box = 32 cols x box_rows rows, 128B swizzle, zero OOB fill
-int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows) {
+int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows, bool f16 = false) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) { set_last_error("cuTensorMapEncodeTiled entry point not available"); return -2; }
+  const int esize = f16 ? 2 : 4;                      // a box row is always 128 B: 32 fp32 or 64 fp16 elements
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * esize};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esize), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -357,13 +378,14 @@ int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int
   return 0;
 }
 
-template <int BN, int STAGES, bool BEXACT>
+template <int BN, int STAGES, bool BEXACT, bool F16>
 int launch(const GemmArgs& g, cudaStream_t stream) {
   using L = SmemLayout<BN, STAGES, BEXACT>;
+  constexpr int BKE = F16 ? 2 * BK : BK;
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
-  if ((rc = make_map(&mAh, g.A_hi, g.M, g.Kd, g.lda, BM))) return rc;
-  if ((rc = make_map(&mAl, g.A_lo, g.M, g.Kd, g.lda, BM))) return rc;
+  if ((rc = make_map(&mAh, g.A_hi, g.M, g.Kd, g.lda, BM, F16))) return rc;
+  if ((rc = make_map(&mAl, g.A_lo, g.M, g.Kd, g.lda, BM, F16))) return rc;
   int dev = 0, sms = 0;
   CNMF_CUDA_CHECK(cudaGetDevice(&dev));
   CNMF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -371,7 +393,7 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   // Tile width: the UMMA N is a runtime value (multiple of 16, <= BN), normally supplied by gemm_plan().
   int bn = g.bn;
   if (bn <= 0 || bn > BN || bn % 16 != 0) {
-    const int sp = gemm_effective_splits(g.Kd, g.splits);
+    const int sp = gemm_effective_splits(g.Kd, g.splits, F16 ? 1 : 0);
     if (g.N <= BN) {
       bn = ((g.N + 15) / 16) * 16;
     } else {
@@ -388,18 +410,18 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
     static const int env_bn = [] { const char* e = std::getenv("CNMF_GEMM_BN"); return e ? std::atoi(e) : 0; }();
     if (env_bn >= 16 && env_bn <= BN && env_bn % 16 == 0) bn = env_bn;
   }
-  if ((rc = make_map(&mBh, g.B_hi, g.N, g.Kd, g.ldb, bn))) return rc;
-  if ((rc = make_map(&mBl, BEXACT ? g.B_hi : g.B_lo, g.N, g.Kd, g.ldb, bn))) return rc;
+  if ((rc = make_map(&mBh, g.B_hi, g.N, g.Kd, g.ldb, bn, F16))) return rc;
+  if ((rc = make_map(&mBl, BEXACT ? g.B_hi : g.B_lo, g.N, g.Kd, g.ldb, bn, F16))) return rc;
 
   const int n_tiles = (g.N + bn - 1) / bn;
-  const int total_kb = (g.Kd + BK - 1) / BK;
+  const int total_kb = (g.Kd + BKE - 1) / BKE;
   int splits = g.splits < 1 ? 1 : g.splits;
   if (splits > total_kb) splits = total_kb;
   const int kb_per_split = (total_kb + splits - 1) / splits;
   splits = (total_kb + kb_per_split - 1) / kb_per_split;      // no empty slices
   if (splits != g.splits_effective) { set_last_error("gemm: splits_effective mismatch (use gemm_effective_splits)"); return -1; }
 
-  auto kern = gemm_tf32x3_kernel<BN, STAGES, BEXACT>;
+  auto kern = gemm_tf32x3_kernel<BN, STAGES, BEXACT, F16>;
   static bool attr_set = false;
   if (!attr_set) {
     CNMF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
@@ -420,16 +442,17 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   }
   kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(mAh, mAl, mBh, mBl, g.C, g.M, g.N, g.ldc, g.c_split_stride,
                                                     m_tiles, n_tiles, splits, total_kb, kb_per_split,
-                                                    chain_kb, bn, g.out_col_scale);
+                                                    chain_kb, bn, g.out_col_scale, g.out_row_scale);
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 }  // namespace
 
-void gemm_plan(int M, int N, int Kd, int sm_count, int* splits_out, int* bn_out) {
+void gemm_plan(int M, int N, int Kd, int sm_count, int* splits_out, int* bn_out, int f16) {
   const int m_tiles = (M + BM - 1) / BM;
-  const int total_kb = (Kd + BK - 1) / BK;
+  const int bke = f16 ? 2 * BK : BK;
+  const int total_kb = (Kd + bke - 1) / bke;
   const int max_splits = std::max(1, std::min(32, total_kb / 8));
   double best = -1.0;
   int best_s = 1, best_bn = 256;
@@ -438,7 +461,7 @@ void gemm_plan(int M, int N, int Kd, int sm_count, int* splits_out, int* bn_out)
   const int bn_lo = N <= 256 ? ((N + 15) / 16) * 16 : 128;
   const int bn_hi = N <= 256 ? bn_lo : 256;
   for (int s = 1; s <= max_splits; ++s) {
-    const int se = gemm_effective_splits(Kd, s);
+    const int se = gemm_effective_splits(Kd, s, f16);
     if (se != s) continue;                                   // skip factors that collapse to a smaller one
     const int kbps = (total_kb + s - 1) / s;
     for (int bn = bn_hi; bn >= bn_lo; bn -= 16) {
@@ -454,8 +477,9 @@ void gemm_plan(int M, int N, int Kd, int sm_count, int* splits_out, int* bn_out)
   *bn_out = best_bn;
 }
 
-int gemm_effective_splits(int Kd, int splits) {
-  const int total_kb = (Kd + BK - 1) / BK;
+int gemm_effective_splits(int Kd, int splits, int f16) {
+  const int bke = f16 ? 2 * BK : BK;
+  const int total_kb = (Kd + bke - 1) / bke;
   if (splits < 1) splits = 1;
   if (splits > total_kb) splits = total_kb;
   const int kb_per_split = (total_kb + splits - 1) / splits;
@@ -469,8 +493,13 @@ int gemm_tf32x3(const GemmArgs& g, cudaStream_t stream) {
                 reinterpret_cast<uintptr_t>(g.B_hi) | reinterpret_cast<uintptr_t>(g.B_lo) |
                 reinterpret_cast<uintptr_t>(g.C) | reinterpret_cast<uintptr_t>(g.out_col_scale)) % 16 == 0,
                "gemm: pointers must be 16-byte aligned");
-  if (g.b_exact) return launch<256, 3, true>(g, stream);
-  return launch<256, 2, false>(g, stream);
+  if (g.f16) {
+    CNMF_REQUIRE(g.b_exact, "gemm: the fp16 path needs an exact B operand");
+    CNMF_REQUIRE(g.lda % 8 == 0 && g.ldb % 8 == 0, "gemm: fp16 leading dimensions must be multiples of 8 halves");
+    return launch<256, 3, true, true>(g, stream);
+  }
+  if (g.b_exact) return launch<256, 3, true, false>(g, stream);
+  return launch<256, 2, false, false>(g, stream);
 }
 
 }  // namespace cnmf

@@ -21,8 +21,8 @@
 namespace cnmf {
 
 DataView make_view(const cnmf_dataset_s* d, bool transposed) {
-  Operand X{d->X, d->X_hi, d->X_lo, d->n_rows, d->n_cols, d->ld_c};
-  Operand Xt{d->Xt, d->Xt_hi, d->Xt_lo, d->n_cols, d->n_rows, d->ld_r};
+  Operand X{d->X, d->X_hi, d->X_lo, d->f16 ? d->X_h16 : nullptr, d->n_rows, d->n_cols, d->ld_c};
+  Operand Xt{d->Xt, d->Xt_hi, d->Xt_lo, d->f16 ? d->Xt_h16 : nullptr, d->n_cols, d->n_rows, d->ld_r};
   DataView v;
   if (!transposed) {
     v.B_rows = X; v.B_cols = Xt;
@@ -34,6 +34,7 @@ DataView make_view(const cnmf_dataset_s* d, bool transposed) {
   v.sum = d->sum;
   v.sum_sq = d->sum_sq;
   v.exact = d->exact;
+  v.f16 = d->f16;
   v.scale_r = transposed ? d->col_scale : d->row_scale;
   v.scale_c = transposed ? d->row_scale : d->col_scale;
   return v;
@@ -60,7 +61,7 @@ struct GemmPlan {
 // C[z] (SK x N) = A (SK x Kd) * B (N x Kd)^T
 int run_gemm(cnmf_handle_s* h, int precision, const float* A, const float* A_hi, const float* A_lo, int SK, int lda,
              const Operand& B, float* C, int ldc, const GemmPlan& plan, bool exact, const float* out_scale,
-             cudaStream_t s) {
+             bool f16, const float* a_row_scale, cudaStream_t s) {
   GemmArgs g{};
   g.M = SK; g.N = B.rows; g.Kd = B.cols;
   g.lda = lda; g.ldb = B.ld; g.ldc = ldc;
@@ -76,6 +77,11 @@ int run_gemm(cnmf_handle_s* h, int precision, const float* A, const float* A_hi,
     g.A_hi = A_hi; g.A_lo = A_lo; g.B_hi = B.hi; g.B_lo = B.lo;
     g.b_exact = exact ? 1 : 0;
     g.out_col_scale = exact ? out_scale : nullptr;
+    if (f16) {       // A_hi / A_lo hold the two fp16 pieces of the row-normalised factor, B its fp16 integer matrix
+      g.f16 = 1;
+      g.B_hi = static_cast<const float*>(B.h16);
+      g.out_row_scale = a_row_scale;
+    }
     rc = gemm_tf32x3(g, s);
   } else {
     g.A_hi = A; g.A_lo = nullptr; g.B_hi = B.full; g.B_lo = nullptr;
@@ -100,6 +106,7 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   CNMF_REQUIRE(p.solver == CNMF_SOLVER_MU || p.solver == CNMF_SOLVER_CD, "solve: unknown solver");
   CNMF_REQUIRE(p.max_iter >= 1, "solve: max_iter must be >= 1");
   const bool tf32 = p.precision == CNMF_PRECISION_TF32X3;
+  const bool f16 = tf32 && v.f16;       // exact-count dataset created with CNMF_PRECISION_F16X2: kind::f16 products
   const bool mu = p.solver == CNMF_SOLVER_MU;
 
   // ---- slot tables (host mirrors); slot s holds restart rid[s] at packed rows [off[s], off[s]+k[s])
@@ -153,7 +160,7 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   float *NUMr = nullptr, *NUMc = nullptr;
   auto plan_one = [&](int sk, int n, int kd, GemmPlan* pl) {
     if (tf32) {
-      gemm_plan(sk, n, kd, h->sm_count, &pl->splits, &pl->bn);
+      gemm_plan(sk, n, kd, h->sm_count, &pl->splits, &pl->bn, f16 ? 1 : 0);
     } else {
       pl->splits = pick_splits(h->sm_count, sk, n, kd);
       pl->bn = 0;
@@ -219,11 +226,14 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   bool compacted = false;
 
   auto bm = [&]() { return BatchMeta{d_off, d_k, d_rid, d_done, R, kp}; };
+  // tf32 pieces are written by the update kernels; the fp16 pieces need the row maximum first and come from
+  // emit_pieces() after the update (the hi / lo buffers then hold halves)
+  const bool upd_pieces = tf32 && !f16;
   auto fr = [&]() {
-    return FactorView{wFr, tf32 ? wFr_hi : nullptr, tf32 ? wFr_lo : nullptr, v.n_r, v.ld_r, v.exact ? v.scale_r : nullptr, cpb_r, gcpb_r};
+    return FactorView{wFr, upd_pieces ? wFr_hi : nullptr, upd_pieces ? wFr_lo : nullptr, v.n_r, v.ld_r, v.exact ? v.scale_r : nullptr, cpb_r, gcpb_r};
   };
   auto fc = [&]() {
-    FactorView f{wFc, tf32 ? wFc_hi : nullptr, tf32 ? wFc_lo : nullptr, v.n_c, v.ld_c, v.exact ? v.scale_c : nullptr, cpb_c, gcpb_c};
+    FactorView f{wFc, upd_pieces ? wFc_hi : nullptr, upd_pieces ? wFc_lo : nullptr, v.n_c, v.ld_c, v.exact ? v.scale_c : nullptr, cpb_c, gcpb_c};
     if (!io.update_cols) { f.F_hi = nullptr; f.F_lo = nullptr; }   // never rewritten
     return f;
   };
@@ -238,6 +248,24 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   auto gram_after = [&](const FactorView& f, int side_is_c) -> int {   // Gram of a factor the update kernel just wrote
     return fuse ? 0 : gram_full(f, side_is_c);
   };
+  float* d_rs_r = nullptr;   // f16: per packed row power-of-two scales of the Fr / Fc pieces
+  float* d_rs_c = nullptr;
+  if (f16) {
+    d_rs_r = static_cast<float*>(h->dev_buf("solve.rowscale_r", sizeof(float) * SK0));
+    d_rs_c = static_cast<float*>(h->dev_buf("solve.rowscale_c", sizeof(float) * SK0));
+    if (!d_rs_r || !d_rs_c) return -2;
+  }
+  auto emit_pieces = [&](int side_is_c) -> int {   // fp16 pieces + row scales of a factor that was just (re)written
+    if (!f16) return 0;
+    h->launches += 1;
+    const int n = side_is_c ? v.n_c : v.n_r;
+    const int slot = h->prof_begin(s, 8.0 * (double)SK * (double)n, 1);   // fp32 in, two fp16 pieces out
+    const int rc = side_is_c
+        ? launch_emit_f16(wFc, SK, v.n_c, v.ld_c, v.exact ? v.scale_c : nullptr, wFc_hi, wFc_lo, d_rs_c, s)
+        : launch_emit_f16(wFr, SK, v.n_r, v.ld_r, v.exact ? v.scale_r : nullptr, wFr_hi, wFr_lo, d_rs_r, s);
+    h->prof_end(s, slot);
+    return rc;
+  };
   // algorithmic bytes of one update launch: factor read, product slices read, factor (+ tf32 pieces) written
   auto upd_bytes = [&](int n_items, int nsplit, bool pieces) {
     return 4.0 * (double)SK * (double)n_items * (double)(2 + nsplit + (pieces ? 2 : 0));
@@ -249,7 +277,8 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     const int rc = cd ? launch_cd_update(f, NUM, pl.splits, pl.split_stride, gram_in, bm(), l1, l2, out, s)
                       : launch_mu_update(f, NUM, pl.splits, pl.split_stride, gram_in, bm(), l1, l2, out, s);
     h->prof_end(s, slot);
-    return rc;
+    if (rc != 0 || !io.update_cols) return rc;   // a refit never multiplies by the factor it updates
+    return emit_pieces(f.F == wFc ? 1 : 0);
   };
   auto fused_out = [&](int side_is_c, bool want_gram, double* scal_part, double* scal) {
     FusedOut o{};
@@ -267,10 +296,12 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     return launch_finalize(nullptr, nullptr, part, out, chunks, bm(), s);
   };
   auto gemm_rows = [&]() -> int {   // NUM_r = Fc * B_rows^T
-    return run_gemm(h, p.precision, wFc, wFc_hi, wFc_lo, SK, v.ld_c, v.B_rows, NUMr, v.ld_r, plan_r, v.exact, v.scale_r, s);
+    return run_gemm(h, p.precision, wFc, wFc_hi, wFc_lo, SK, v.ld_c, v.B_rows, NUMr, v.ld_r, plan_r, v.exact, v.scale_r,
+                    f16, d_rs_c, s);
   };
   auto gemm_cols = [&]() -> int {   // NUM_c = Fr * B_cols^T
-    return run_gemm(h, p.precision, wFr, wFr_hi, wFr_lo, SK, v.ld_r, v.B_cols, NUMc, v.ld_c, plan_c, v.exact, v.scale_c, s);
+    return run_gemm(h, p.precision, wFr, wFr_hi, wFr_lo, SK, v.ld_r, v.B_cols, NUMc, v.ld_c, plan_c, v.exact, v.scale_c,
+                    f16, d_rs_r, s);
   };
 
   // gathers `cnt` restarts' rows: dst[dst_off[i] ..] <- src[src_off[i] ..].  Index triples go through a pinned
@@ -365,7 +396,7 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     CNMF_TRY(gather(wFc, resFc, f_src, f_dst, f_k, v.ld_c));
     CNMF_TRY(gather(wFr, aFr, l_src, l_dst, l_k, v.ld_r));          // live restarts -> packed front of the alt buffers
     CNMF_TRY(gather(wFc, aFc, l_src, l_dst, l_k, v.ld_c));
-    if (tf32) {
+    if (tf32 && !f16) {
       CNMF_TRY(gather(wFr_hi, aFr_hi, l_src, l_dst, l_k, v.ld_r));
       CNMF_TRY(gather(wFr_lo, aFr_lo, l_src, l_dst, l_k, v.ld_r));
       CNMF_TRY(gather(wFc_hi, aFc_hi, l_src, l_dst, l_k, v.ld_c));
@@ -382,6 +413,8 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     gslot = 0;
     plan_gemms();
     plan_blocks(R);
+    CNMF_TRY(emit_pieces(0));      // f16: pieces and row scales follow the new packing
+    CNMF_TRY(emit_pieces(1));
     compacted = true;
     return 0;
   };
@@ -396,6 +429,8 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
 
   const float l1W = (float)p.l1_reg_W, l2W = (float)p.l2_reg_W, l1H = (float)p.l1_reg_H, l2H = (float)p.l2_reg_H;
   int it = 0;
+  CNMF_TRY(emit_pieces(0));        // f16: the callers' tf32 pieces are replaced by fp16 pieces of the initial factors
+  CNMF_TRY(emit_pieces(1));
 
   if (mu) {
     // ---------------- multiplicative update (sklearn _nmf.py:726-888) ----------------

@@ -4,6 +4,8 @@
 // that feed the convergence decisions.
 #include "nmf_kernels.cuh"
 
+#include <cuda_fp16.h>
+
 namespace cnmf {
 
 namespace {
@@ -166,6 +168,79 @@ __global__ void sums_final_kernel(const double* __restrict__ part, int nblocks, 
   if (threadIdx.x == 0) {
     out2[0] = s;
     out2[1] = q;
+  }
+}
+
+// ------------------------------------------------------------------ fp16 operand pieces (f16x2 precision)
+// kind::f16 MMAs run at twice the kind::tf32 rate and fp16 carries the same 11-bit significand as tf32; what it
+// lacks is exponent range.  So a packed factor row is divided by a power of two that puts its largest entry
+// (times the per-column scale of the exact-count path) in [2^14, 2^15) -- far above fp16's subnormals -- and split
+// into hi = fp16(x), mid = fp16(x - hi): 22 significant bits like the tf32 pair, absolute error <= 2^-39 of the row
+// maximum for entries too small to keep them.  The GEMM multiplies its output row by the same power of two.
+// One block per row: pass 1 finds the maximum, pass 2 (the row again, from L2) emits the pieces.
+__global__ void __launch_bounds__(256)
+emit_f16_kernel(const float* __restrict__ F, int n, int ld, const float* __restrict__ pscale, __half* __restrict__ hi,
+                __half* __restrict__ mid, float* __restrict__ rowscale) {
+  __shared__ float sm[33];
+  const long long row = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(F + row * ld);
+  const float4* ps4 = reinterpret_cast<const float4*>(pscale);
+  const int n4 = ld / 4;
+  float m = 0.f;
+  for (int q = threadIdx.x; q < n4; q += blockDim.x) {
+    float4 v = src[q];
+    if (pscale) {
+      const float4 p = ps4[q];
+      v.x *= p.x; v.y *= p.y; v.z *= p.z; v.w *= p.w;
+    }
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mm = 0.f;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) mm = fmaxf(mm, sm[w]);
+    float sc = 1.f;
+    if (mm > 0.f && mm < 3.0e38f) {
+      int e;
+      frexpf(mm, &e);                    // mm = f * 2^e, f in [0.5, 1)
+      sc = ldexpf(1.f, e - 15);          // mm / sc in [2^14, 2^15)
+    }
+    sm[32] = sc;
+    rowscale[row] = sc;
+  }
+  __syncthreads();
+  const float inv = 1.f / sm[32];        // power of two: exact
+  uint2* dh = reinterpret_cast<uint2*>(hi + row * ld);
+  uint2* dm = reinterpret_cast<uint2*>(mid + row * ld);
+  for (int q = threadIdx.x; q < n4; q += blockDim.x) {
+    float4 v = src[q];
+    if (pscale) {
+      const float4 p = ps4[q];
+      v.x *= p.x; v.y *= p.y; v.z *= p.z; v.w *= p.w;
+    }
+    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 m01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), m23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+    uint2 oh, om;
+    oh.x = *reinterpret_cast<const uint32_t*>(&h01); oh.y = *reinterpret_cast<const uint32_t*>(&h23);
+    om.x = *reinterpret_cast<const uint32_t*>(&m01); om.y = *reinterpret_cast<const uint32_t*>(&m23);
+    dh[q] = oh;
+    dm[q] = om;
+  }
+}
+
+// dst (fp16) = src (fp32, small non-negative integers: exact), elementwise over rows x ld
+__global__ void to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);
+    reinterpret_cast<uint2*>(dst)[i] = o;
   }
 }
 
@@ -890,6 +965,25 @@ int launch_split_scaled(const float* src, float* hi, float* lo, int rows, int ld
   if (n4 == 0) return 0;
   const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
   split_scaled_kernel<<<blocks, 256, 0, s>>>(src, hi, lo, rows, ld, col_scale);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_emit_f16(const float* F, int rows, int n, int ld, const float* pscale, void* hi, void* mid, float* rowscale,
+                    cudaStream_t s) {
+  CNMF_REQUIRE(ld % 8 == 0, "emit_f16: ld must be a multiple of 8");
+  if (rows <= 0) return 0;
+  emit_f16_kernel<<<rows, 256, 0, s>>>(F, n, ld, pscale, static_cast<__half*>(hi), static_cast<__half*>(mid), rowscale);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_to_half(const float* src, void* dst, long long n_elems, cudaStream_t s) {
+  CNMF_REQUIRE(n_elems % 4 == 0, "to_half: element count must be a multiple of 4");
+  const long long n4 = n_elems / 4;
+  if (n4 == 0) return 0;
+  const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  to_half_kernel<<<blocks, 256, 0, s>>>(src, static_cast<__half*>(dst), n4);
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -57,6 +57,14 @@ int launch_split_tf32(const float* src, float* hi, float* lo, long long n_elems,
 // (hi, lo) = split(src[r, c] * col_scale[c]) over rows x ld; col_scale may be nullptr (plain split)
 int launch_split_scaled(const float* src, float* hi, float* lo, int rows, int ld, const float* col_scale, cudaStream_t s);
 
+// ---- fp16 operand pieces (f16x2 precision, exact-count datasets) ----
+// per packed row r: rowscale[r] = power of two with max_c(F[r,c] * pscale[c]) / rowscale[r] in [2^14, 2^15);
+// hi / mid (fp16, row stride ld halves) = the two pieces of F[r,:] * pscale / rowscale[r]
+int launch_emit_f16(const float* F, int rows, int n, int ld, const float* pscale, void* hi, void* mid, float* rowscale,
+                    cudaStream_t s);
+// dst (fp16) = src (fp32), elementwise; used for the exact integer count matrices
+int launch_to_half(const float* src, void* dst, long long n_elems, cudaStream_t s);
+
 // ---- exact-count detection (dataset preparation) ----
 // col_min[c] / row_min[r] = smallest strictly positive entry of the column / row (+inf if none)
 int launch_min_positive(const float* X, int rows, int cols, int ld, float* col_min, float* row_min, cudaStream_t s);

@@ -9,20 +9,22 @@ import numpy as np
 
 from . import _lib
 from ._lib import (LOSS_FROBENIUS, LOSS_ITAKURA_SAITO, LOSS_KULLBACK_LEIBLER, NmfParams, PRECISION_FP32,
-                   PRECISION_TF32X3, PRECISION_TF32X3_GENERAL, SOLVER_CD, SOLVER_MU, check, f32c, ptr)
+                   PRECISION_F16X2, PRECISION_TF32X3, PRECISION_TF32X3_GENERAL, SOLVER_CD, SOLVER_MU, check, f32c, ptr)
 
 _DEFAULT_PRECISION = PRECISION_TF32X3
 
 
 def precision_code(p):
-    """'fp32' | 'tf32x3' (default; 2-pass products when X is scaled integer counts) | 'tf32x3-general' (always 3-pass)."""
-    if p in (PRECISION_FP32, PRECISION_TF32X3, PRECISION_TF32X3_GENERAL):
+    """'fp32' | 'tf32x3' (default; 2-pass products when X is scaled integer counts) | 'f16x2' (like tf32x3, but the
+    2-pass products of scaled-integer-count matrices run on kind::f16 MMAs) | 'tf32x3-general' (always 3-pass)."""
+    if p in (PRECISION_FP32, PRECISION_TF32X3, PRECISION_TF32X3_GENERAL, PRECISION_F16X2):
         return p
-    return {"fp32": PRECISION_FP32, "tf32x3": PRECISION_TF32X3, "tf32x3-general": PRECISION_TF32X3_GENERAL}[p]
+    return {"fp32": PRECISION_FP32, "tf32x3": PRECISION_TF32X3, "tf32x3-general": PRECISION_TF32X3_GENERAL,
+            "f16x2": PRECISION_F16X2}[p]
 
 
 def _params_precision(p):
-    return PRECISION_TF32X3 if p == PRECISION_TF32X3_GENERAL else p
+    return PRECISION_TF32X3 if p in (PRECISION_TF32X3_GENERAL, PRECISION_F16X2) else p
 
 
 def make_params(nmf_kwargs, n_samples, n_features, precision):
@@ -125,7 +127,9 @@ class Engine:
         assert B.shape[1] == Kd
         C = np.empty((M, N), np.float32)
         ms = ctypes.c_float(0)
-        check(self.lib.cnmf_gemm_abt_host(self._h, _params_precision(precision_code(precision)), ptr(A), ptr(B), M, N, Kd, splits,
+        pc = precision_code(precision)
+        pc = PRECISION_TF32X3 if pc == PRECISION_TF32X3_GENERAL else pc      # f16x2: B must hold integers <= 2048
+        check(self.lib.cnmf_gemm_abt_host(self._h, pc, ptr(A), ptr(B), M, N, Kd, splits,
                                           ptr(C), reps, ctypes.byref(ms), None))
         return C, float(ms.value)
 
@@ -192,6 +196,11 @@ class Dataset:
     def exact(self):
         """True when X was recognised as scaled integer counts (2-pass tensor-core products)."""
         return bool(self.lib.cnmf_dataset_is_exact(self._d))
+
+    @property
+    def f16(self):
+        """True when the big products run as 2 kind::f16 passes (exact dataset created with precision='f16x2')."""
+        return self.lib.cnmf_dataset_is_exact(self._d) == 2
 
     def min(self):
         m = ctypes.c_float()

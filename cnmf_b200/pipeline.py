@@ -564,7 +564,7 @@ def main():
     ap.add_argument("--build-reference", dest="build_reference", action="store_true", default=True)
     ap.add_argument("--prepare-on-device", dest="prepare_on_device", action="store_true", default=False,
                     help="[cnmf_b200] prepare: cell totals, TPM gene statistics and the HVG matrix computed on the GPU")
-    ap.add_argument("--precision", type=str, choices=["tf32x3", "fp32"], default="tf32x3",
+    ap.add_argument("--precision", type=str, choices=["tf32x3", "f16x2", "fp32"], default="tf32x3",
                     help="[cnmf_b200] GEMM arithmetic: tcgen05 3xTF32 (default) or FFMA fp32")
     a = ap.parse_args()
     obj = cNMF(output_dir=a.output_dir, name=a.name, precision=a.precision)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CNMF_B200_ABI_VERSION 5
+#define CNMF_B200_ABI_VERSION 6
 #define CNMF_MAX_COMPONENTS 32          /* largest n_components per restart on the CUDA path */
 
 typedef struct cnmf_handle_s* cnmf_handle_t;
@@ -37,7 +37,11 @@ typedef struct cnmf_dataset_s* cnmf_dataset_t;
 enum { CNMF_SOLVER_MU = 0, CNMF_SOLVER_CD = 1 };            /* yaml 'solver': cnmf.py:618-631 */
 /* FFMA | tcgen05 3xTF32 with exact-count detection (default: 2 passes when X is scaled integers, else 3) |
  * tcgen05 3xTF32 always in the general 3-pass form.  Params for a dataset created with 2 use precision 1. */
-enum { CNMF_PRECISION_FP32 = 0, CNMF_PRECISION_TF32X3 = 1, CNMF_PRECISION_TF32X3_GENERAL = 2 };
+enum { CNMF_PRECISION_FP32 = 0, CNMF_PRECISION_TF32X3 = 1, CNMF_PRECISION_TF32X3_GENERAL = 2,
+       /* dataset_create only: like TF32X3, but when X is recognised as scaled integer counts the big products run as
+        * 2 kind::f16 tensor-core passes (integer operand exact in fp16, factor = two fp16 pieces of its row-normalised
+        * values: the same 22 significant bits as the tf32 pair at twice the MMA rate); params.precision stays TF32X3 */
+       CNMF_PRECISION_F16X2 = 3 };
 
 /* yaml 'beta_loss' (cnmf.py:622, CLI --beta-loss cnmf.py:1251).  'frobenius' (or 2) runs the tensor-core path with
  * either solver; 'kullback-leibler' (1) and 'itakura-saito' (0) run the multiplicative updates of sklearn
@@ -97,7 +101,8 @@ int cnmf_dataset_min(cnmf_dataset_t d, float* min_host, void* stream);
 /* 1 when the dataset was recognised as (row scale) x (integer counts <= 2048) x (column scale) -- what
  * HVG-normalised counts (cnmf.py:542) and TPM (cnmf.py:245-251) are -- and therefore runs the 2-pass
  * tensor-core products (the integer operand needs no tf32 "lo" piece); 0 = general 3-pass 3xTF32.
- * CNMF_EXACT=0 in the environment disables the detection. */
+ * CNMF_EXACT=0 in the environment disables the detection.  Returns 2 when, in addition, the dataset was created with
+ * CNMF_PRECISION_F16X2 and the 2 passes therefore run on kind::f16 MMAs. */
 int cnmf_dataset_is_exact(cnmf_dataset_t d);
 /* per-column mean and population variance (StandardScaler(with_mean=False), cnmf.py:131-134) */
 int cnmf_dataset_col_stats(cnmf_dataset_t d, double* mean_host, double* var_host, void* stream);

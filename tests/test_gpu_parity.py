@@ -47,6 +47,26 @@ def test_gemm_against_float64(eng, precision, shape):
     assert rel(C, ref) < TOL_GEMM
 
 
+@pytest.mark.parametrize("shape", [(128, 256, 64, 1), (128, 256, 2048, 1), (200, 300, 100, 1), (7, 1000, 500, 1),
+                                   (70, 40, 33, 1), (1, 5, 4, 1), (1000, 2000, 2000, 1), (300, 500, 4000, 4),
+                                   (129, 257, 65, 2), (1000, 2000, 20000, 9)])
+def test_gemm_f16x2_against_float64(eng, shape):
+    """kind::f16 path: A = two fp16 pieces of its row-normalised values (rows spanning 12 orders of magnitude and
+    heavy-tailed entries), B = integer counts; same tolerance as the tf32 pair."""
+    M, N, K, sp = shape
+    rng = np.random.RandomState(M + N + K)
+    A = (np.abs(rng.standard_cauchy((M, K))) * 10.0 ** rng.uniform(-6, 6, size=(M, 1))).astype(np.float32)
+    A[:, ::7] = 0.0
+    B = rng.poisson(1.5, size=(N, K)).astype(np.float32)
+    B[0, 0] = 2048.0
+    C, _ = eng.gemm_abt(A, B, precision="f16x2", splits=sp)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    assert not np.isnan(C).any()
+    assert rel(C, ref) < TOL_GEMM
+    rows = np.linalg.norm(C - ref, axis=1) / np.maximum(np.linalg.norm(ref, axis=1), 1e-300)
+    assert rows.max() < 4 * TOL_GEMM, rows.max()          # every row, whatever its scale
+
+
 def test_gemm_properties_full_size(eng):
     """BASELINE c2 shapes: split-K invariance, linearity, signed inputs (size-independent properties)."""
     rng = np.random.RandomState(0)
@@ -117,7 +137,7 @@ def test_exact_count_detection(eng):
     assert not eng.dataset(big).exact
 
 
-@pytest.mark.parametrize("precision", ["tf32x3", "tf32x3-hostrng", "tf32x3-general", "fp32"])
+@pytest.mark.parametrize("precision", ["tf32x3", "f16x2", "tf32x3-hostrng", "tf32x3-general", "fp32"])
 @pytest.mark.parametrize("tag", ["sim_mu", "sim_cd"])
 def test_factorize_matches_reference_fixture(eng, precision, tag):
     """Every restart of the reference's own factorize() run (fixture): same n_iter, spectra within tolerance."""
@@ -275,7 +295,7 @@ def test_itakura_saito(eng):
 
 
 # ------------------------------------------------------------------------------------ refits
-@pytest.mark.parametrize("precision", ["tf32x3", "tf32x3-general"])
+@pytest.mark.parametrize("precision", ["tf32x3", "f16x2", "tf32x3-general"])
 @pytest.mark.parametrize("tag", ["sim_mu", "sim_cd"])
 def test_refits_match_oracle(eng, tag, precision):
     from oracle import nmf_ref
