@@ -85,7 +85,7 @@ def _highvar_genes(tpm, numgenes):
 class cNMF:
     """Same constructor, attributes and methods as the reference class (cnmf.py:265)."""
 
-    def __init__(self, output_dir=".", name=None, precision="tf32x3", device=None):
+    def __init__(self, output_dir=".", name=None, precision="f16x2", device=None):
         self.output_dir = output_dir
         if name is None:
             name = "%s_%s" % (datetime.datetime.now().strftime("%Y_%m_%d"), uuid.uuid4().hex[:6])
@@ -564,8 +564,9 @@ def main():
     ap.add_argument("--build-reference", dest="build_reference", action="store_true", default=True)
     ap.add_argument("--prepare-on-device", dest="prepare_on_device", action="store_true", default=False,
                     help="[cnmf_b200] prepare: cell totals, TPM gene statistics and the HVG matrix computed on the GPU")
-    ap.add_argument("--precision", type=str, choices=["tf32x3", "f16x2", "fp32"], default="tf32x3",
-                    help="[cnmf_b200] GEMM arithmetic: tcgen05 3xTF32 (default) or FFMA fp32")
+    ap.add_argument("--precision", type=str, choices=["f16x2", "tf32x3", "fp32"], default="f16x2",
+                    help="[cnmf_b200] big products: split-fp16 tcgen05 MMAs for scaled-integer-count matrices, split-TF32 "
+                         "otherwise (default); split-TF32 always; or FFMA fp32")
     a = ap.parse_args()
     obj = cNMF(output_dir=a.output_dir, name=a.name, precision=a.precision)
     if a.command == "prepare":

@@ -94,7 +94,8 @@ def stage_c3():
     rows = restart_table(list(range(5, 14)), 100)
     print("c3 data %s in %.1fs, %d restarts, sum K = %d" % (X.shape, time.time() - t0, len(rows), sum(r[0] for r in rows)), flush=True)
     kw = dict(solver="mu", tol=1e-4, max_iter=1000)
-    ds = eng.dataset(X, precision="tf32x3")
+    ds = eng.dataset(X)
+    print("c3 dataset exact=%s f16=%s" % (ds.exact, ds.f16), flush=True)
     for rep in range(2):
         eng.profile(True)
         l0 = eng.launch_count
