@@ -407,11 +407,12 @@ int cnmf_gemm_abt_host(cnmf_handle_t h, int precision, const float* A, const flo
   g.C = dC; g.c_split_stride = (long long)M * ldc; g.splits = splits; g.splits_effective = se;
   const bool f16 = precision == CNMF_PRECISION_F16X2;    // B must hold integers <= 2048 (exact in fp16)
   if (f16) {
-    float* dRs = static_cast<float*>(h->dev_buf("gemmtest.rs", sizeof(float) * M));
+    const int tiles = (lda + 511) / 512;
+    float* dRs = static_cast<float*>(h->dev_buf("gemmtest.rs", sizeof(float) * (size_t)M * tiles));
     if (!dRs) return -2;
-    CNMF_TRY(launch_emit_f16(dA, M, Kd, lda, nullptr, dAh, dAl, dRs, s));
+    CNMF_TRY(launch_emit_f16(dA, M, Kd, lda, nullptr, dAh, dAl, dRs, tiles, s));
     CNMF_TRY(launch_to_half(dB, dBh, (long long)nb, s));
-    g.A_hi = dAh; g.A_lo = dAl; g.B_hi = dBh; g.b_exact = 1; g.f16 = 1; g.out_row_scale = dRs;
+    g.A_hi = dAh; g.A_lo = dAl; g.B_hi = dBh; g.b_exact = 1; g.f16 = 1; g.a_tile_scale = dRs; g.a_tiles = tiles;
   } else if (precision == CNMF_PRECISION_TF32X3) { g.A_hi = dAh; g.A_lo = dAl; g.B_hi = dBh; g.B_lo = dBl; }
   else { g.A_hi = dA; g.B_hi = dB; }
   const bool tc = f16 || precision == CNMF_PRECISION_TF32X3;

@@ -23,7 +23,10 @@ struct GemmArgs {
   // normalised A, the integer matrix B), lda / ldb are in half elements, k-blocks hold 64 elements; kind::f16 MMAs run
   // at twice the kind::tf32 rate and carry the same 11-bit significand per piece
   int f16;
-  const float* out_row_scale; // optional: C[m, :] *= out_row_scale[m] (the per-row power of two the A pieces were divided by)
+  // f16: the A pieces were divided by a power of two per (row, group of 512 reduction elements); the accumulate warps
+  // multiply each drained TMEM chain (128 elements, never straddling a group) by a_tile_scale[m * a_tiles + group]
+  const float* a_tile_scale;
+  int a_tiles;                // groups per row = ceil(Kd / 512)
 };
 
 // number of non-empty split-K slices for a reduction length Kd (k-blocks of 32 fp32 / 64 fp16 elements = 128 B)

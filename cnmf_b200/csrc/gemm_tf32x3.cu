@@ -165,7 +165,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    float* __restrict__ C, int M, int N, int ldc, long long c_split_stride,
                    int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split, int chain_kb, int bn,
-                   const float* __restrict__ out_scale, const float* __restrict__ out_row_scale) {
+                   const float* __restrict__ out_scale, const float* __restrict__ a_tile_scale, int a_tiles) {
   static_assert(!F16 || BEXACT, "the fp16 path exists for exact integer B operands only");
   constexpr int BKE = F16 ? 2 * BK : BK;                        // elements per k-block
   using L = SmemLayout<BN, STAGES, BEXACT>;
@@ -294,7 +294,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       float acc[HALF];
 #pragma unroll
       for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+      // f16: power-of-two scale of this thread's A row for the 512-element group a chain belongs to (8 k-blocks)
+      const int arow = mt * BM + q * 32 + lane;
+      const float* sc_row = (F16 && a_tile_scale && arow < M) ? a_tile_scale + static_cast<long long>(arow) * a_tiles : nullptr;
       for (int c0 = kb0; c0 < kb1; c0 += chain_kb) {
+        float sc = 1.f;
+        if (F16 && sc_row) sc = sc_row[c0 >> 3];
         mbar_wait(tfull_bar(buf), buf_phase, 3);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
@@ -306,7 +311,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             tmem_ld32(taddr + c, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[c + i] += __uint_as_float(r[i]);   // round-to-nearest fp32
+            for (int i = 0; i < 32; ++i) {
+              if constexpr (F16) acc[c + i] = fmaf(__uint_as_float(r[i]), sc, acc[c + i]);   // exact scaling, one rounding
+              else acc[c + i] += __uint_as_float(r[i]);   // round-to-nearest fp32
+            }
           }
         }
         tc_fence_before();
@@ -317,11 +325,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       if (row < M) {
         float* crow = C + static_cast<long long>(z) * c_split_stride + static_cast<long long>(row) * ldc;
         const int col0 = nt * bn + half * HALF;
-        const float rs = out_row_scale ? out_row_scale[row] : 1.f;   // power of two: exact
 #pragma unroll
         for (int i = 0; i < HALF; i += 4) {
           if (half * HALF + i < bn && col0 + i + 3 < ldc) {
-            float4 v = make_float4(acc[i] * rs, acc[i + 1] * rs, acc[i + 2] * rs, acc[i + 3] * rs);
+            float4 v = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
             if (out_scale) {                            // per-output-column scale (length >= ldc, zero padded)
               const float4 sc = *reinterpret_cast<const float4*>(out_scale + col0 + i);
               v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
@@ -417,7 +424,8 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   const int total_kb = (g.Kd + BKE - 1) / BKE;
   int splits = g.splits < 1 ? 1 : g.splits;
   if (splits > total_kb) splits = total_kb;
-  const int kb_per_split = (total_kb + splits - 1) / splits;
+  int kb_per_split = (total_kb + splits - 1) / splits;
+  if (F16 && (kb_per_split & 1)) ++kb_per_split;             // chains (2 k-blocks) must not straddle a 512-element scale group
   splits = (total_kb + kb_per_split - 1) / kb_per_split;      // no empty slices
   if (splits != g.splits_effective) { set_last_error("gemm: splits_effective mismatch (use gemm_effective_splits)"); return -1; }
 
@@ -440,9 +448,10 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
     }();
     chain_kb = env_chain > 0 ? env_chain : (BEXACT ? 2 : 1);
   }
+  if (F16) chain_kb = 2;     // scale groups of 512 elements = 8 k-blocks: chains of 2 never straddle one
   kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(mAh, mAl, mBh, mBl, g.C, g.M, g.N, g.ldc, g.c_split_stride,
                                                     m_tiles, n_tiles, splits, total_kb, kb_per_split,
-                                                    chain_kb, bn, g.out_col_scale, g.out_row_scale);
+                                                    chain_kb, bn, g.out_col_scale, g.a_tile_scale, g.a_tiles);
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -482,7 +491,8 @@ int gemm_effective_splits(int Kd, int splits, int f16) {
   const int total_kb = (Kd + bke - 1) / bke;
   if (splits < 1) splits = 1;
   if (splits > total_kb) splits = total_kb;
-  const int kb_per_split = (total_kb + splits - 1) / splits;
+  int kb_per_split = (total_kb + splits - 1) / splits;
+  if (f16 && (kb_per_split & 1)) ++kb_per_split;   // same rule as the launcher: slices start on even k-blocks
   return (total_kb + kb_per_split - 1) / kb_per_split;
 }
 
@@ -496,6 +506,8 @@ int gemm_tf32x3(const GemmArgs& g, cudaStream_t stream) {
   if (g.f16) {
     CNMF_REQUIRE(g.b_exact, "gemm: the fp16 path needs an exact B operand");
     CNMF_REQUIRE(g.lda % 8 == 0 && g.ldb % 8 == 0, "gemm: fp16 leading dimensions must be multiples of 8 halves");
+    CNMF_REQUIRE(!g.a_tile_scale || g.a_tiles * 512 >= g.Kd, "gemm: a_tiles does not cover the reduction length");
+    CNMF_REQUIRE(g.chain_kb == 0 || g.chain_kb == 2, "gemm: the fp16 path drains chains of 2 k-blocks");
     return launch<256, 3, true, true>(g, stream);
   }
   if (g.b_exact) return launch<256, 3, true, false>(g, stream);

@@ -61,7 +61,7 @@ struct GemmPlan {
 // C[z] (SK x N) = A (SK x Kd) * B (N x Kd)^T
 int run_gemm(cnmf_handle_s* h, int precision, const float* A, const float* A_hi, const float* A_lo, int SK, int lda,
              const Operand& B, float* C, int ldc, const GemmPlan& plan, bool exact, const float* out_scale,
-             bool f16, const float* a_row_scale, cudaStream_t s) {
+             bool f16, const float* a_tile_scale, cudaStream_t s) {
   GemmArgs g{};
   g.M = SK; g.N = B.rows; g.Kd = B.cols;
   g.lda = lda; g.ldb = B.ld; g.ldc = ldc;
@@ -80,7 +80,8 @@ int run_gemm(cnmf_handle_s* h, int precision, const float* A, const float* A_hi,
     if (f16) {       // A_hi / A_lo hold the two fp16 pieces of the row-normalised factor, B its fp16 integer matrix
       g.f16 = 1;
       g.B_hi = static_cast<const float*>(B.h16);
-      g.out_row_scale = a_row_scale;
+      g.a_tile_scale = a_tile_scale;
+      g.a_tiles = (lda + 511) / 512;
     }
     rc = gemm_tf32x3(g, s);
   } else {
@@ -226,14 +227,34 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   bool compacted = false;
 
   auto bm = [&]() { return BatchMeta{d_off, d_k, d_rid, d_done, R, kp}; };
+  float* d_rs_r = nullptr;   // f16: power-of-two scales of the Fr / Fc pieces, [packed row][512-element group]
+  float* d_rs_c = nullptr;
+  if (f16) {
+    d_rs_r = static_cast<float*>(h->dev_buf("solve.rowscale_r", sizeof(float) * (size_t)SK0 * ((v.ld_r + 511) / 512)));
+    d_rs_c = static_cast<float*>(h->dev_buf("solve.rowscale_c", sizeof(float) * (size_t)SK0 * ((v.ld_c + 511) / 512)));
+    if (!d_rs_r || !d_rs_c) return -2;
+  }
   // tf32 pieces are written by the update kernels; the fp16 pieces need the row maximum first and come from
   // emit_pieces() after the update (the hi / lo buffers then hold halves)
   const bool upd_pieces = tf32 && !f16;
+  // f16: the Gram-fused update kernels (K <= 16, factor being iterated) emit the fp16 pieces themselves, per 512-column
+  // tile; everything else (initial factors, compaction, K > 16) goes through emit_pieces() with one scale per row
+  const int ktiles_r = (v.ld_r + 511) / 512, ktiles_c = (v.ld_c + 511) / 512;
+  const bool emit_in_update = f16 && kp == 16 && io.update_cols;
   auto fr = [&]() {
-    return FactorView{wFr, upd_pieces ? wFr_hi : nullptr, upd_pieces ? wFr_lo : nullptr, v.n_r, v.ld_r, v.exact ? v.scale_r : nullptr, cpb_r, gcpb_r};
+    FactorView f{};
+    f.F = wFr; f.F_hi = upd_pieces ? wFr_hi : nullptr; f.F_lo = upd_pieces ? wFr_lo : nullptr;
+    f.n = v.n_r; f.ld = v.ld_r; f.piece_scale = v.exact ? v.scale_r : nullptr;
+    if (emit_in_update) { f.P_hi = wFr_hi; f.P_mid = wFr_lo; f.tile_scale = d_rs_r; f.n_ktiles = ktiles_r; }
+    f.cpb = cpb_r; f.gcpb = gcpb_r;
+    return f;
   };
   auto fc = [&]() {
-    FactorView f{wFc, upd_pieces ? wFc_hi : nullptr, upd_pieces ? wFc_lo : nullptr, v.n_c, v.ld_c, v.exact ? v.scale_c : nullptr, cpb_c, gcpb_c};
+    FactorView f{};
+    f.F = wFc; f.F_hi = upd_pieces ? wFc_hi : nullptr; f.F_lo = upd_pieces ? wFc_lo : nullptr;
+    f.n = v.n_c; f.ld = v.ld_c; f.piece_scale = v.exact ? v.scale_c : nullptr;
+    if (emit_in_update) { f.P_hi = wFc_hi; f.P_mid = wFc_lo; f.tile_scale = d_rs_c; f.n_ktiles = ktiles_c; }
+    f.cpb = cpb_c; f.gcpb = gcpb_c;
     if (!io.update_cols) { f.F_hi = nullptr; f.F_lo = nullptr; }   // never rewritten
     return f;
   };
@@ -248,21 +269,14 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   auto gram_after = [&](const FactorView& f, int side_is_c) -> int {   // Gram of a factor the update kernel just wrote
     return fuse ? 0 : gram_full(f, side_is_c);
   };
-  float* d_rs_r = nullptr;   // f16: per packed row power-of-two scales of the Fr / Fc pieces
-  float* d_rs_c = nullptr;
-  if (f16) {
-    d_rs_r = static_cast<float*>(h->dev_buf("solve.rowscale_r", sizeof(float) * SK0));
-    d_rs_c = static_cast<float*>(h->dev_buf("solve.rowscale_c", sizeof(float) * SK0));
-    if (!d_rs_r || !d_rs_c) return -2;
-  }
   auto emit_pieces = [&](int side_is_c) -> int {   // fp16 pieces + row scales of a factor that was just (re)written
     if (!f16) return 0;
     h->launches += 1;
     const int n = side_is_c ? v.n_c : v.n_r;
     const int slot = h->prof_begin(s, 8.0 * (double)SK * (double)n, 1);   // fp32 in, two fp16 pieces out
     const int rc = side_is_c
-        ? launch_emit_f16(wFc, SK, v.n_c, v.ld_c, v.exact ? v.scale_c : nullptr, wFc_hi, wFc_lo, d_rs_c, s)
-        : launch_emit_f16(wFr, SK, v.n_r, v.ld_r, v.exact ? v.scale_r : nullptr, wFr_hi, wFr_lo, d_rs_r, s);
+        ? launch_emit_f16(wFc, SK, v.n_c, v.ld_c, v.exact ? v.scale_c : nullptr, wFc_hi, wFc_lo, d_rs_c, ktiles_c, s)
+        : launch_emit_f16(wFr, SK, v.n_r, v.ld_r, v.exact ? v.scale_r : nullptr, wFr_hi, wFr_lo, d_rs_r, ktiles_r, s);
     h->prof_end(s, slot);
     return rc;
   };
@@ -278,6 +292,7 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
                       : launch_mu_update(f, NUM, pl.splits, pl.split_stride, gram_in, bm(), l1, l2, out, s);
     h->prof_end(s, slot);
     if (rc != 0 || !io.update_cols) return rc;   // a refit never multiplies by the factor it updates
+    if (f.P_hi && out.gram_part) return 0;       // the Gram-fused kernel emitted the pieces of every tile it wrote
     return emit_pieces(f.F == wFc ? 1 : 0);
   };
   auto fused_out = [&](int side_is_c, bool want_gram, double* scal_part, double* scal) {

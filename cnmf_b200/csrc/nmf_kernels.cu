@@ -180,7 +180,7 @@ __global__ void sums_final_kernel(const double* __restrict__ part, int nblocks, 
 // One block per row: pass 1 finds the maximum, pass 2 (the row again, from L2) emits the pieces.
 __global__ void __launch_bounds__(256)
 emit_f16_kernel(const float* __restrict__ F, int n, int ld, const float* __restrict__ pscale, __half* __restrict__ hi,
-                __half* __restrict__ mid, float* __restrict__ rowscale) {
+                __half* __restrict__ mid, float* __restrict__ tile_scale, int n_ktiles) {
   __shared__ float sm[33];
   const long long row = blockIdx.x;
   const float4* src = reinterpret_cast<const float4*>(F + row * ld);
@@ -209,9 +209,9 @@ emit_f16_kernel(const float* __restrict__ F, int n, int ld, const float* __restr
       sc = ldexpf(1.f, e - 15);          // mm / sc in [2^14, 2^15)
     }
     sm[32] = sc;
-    rowscale[row] = sc;
   }
   __syncthreads();
+  for (int g = threadIdx.x; g < n_ktiles; g += blockDim.x) tile_scale[row * n_ktiles + g] = sm[32];
   const float inv = 1.f / sm[32];        // power of two: exact
   uint2* dh = reinterpret_cast<uint2*>(hi + row * ld);
   uint2* dm = reinterpret_cast<uint2*>(mid + row * ld);
@@ -432,6 +432,63 @@ __device__ __forceinline__ void fused_gram_tile(float* tile, double* gsum) {
   __syncthreads();                                            // scratch (= tile) free again
 }
 
+// f16x2: fp16 operand pieces of the tile a block has just written, straight from the shared-memory tile (so the factor
+// is not read back from HBM by a separate launch).  Normalisation is per (row, 512-column tile): the warp that owns a
+// row takes the tile maximum of F * pscale, picks the power of two that puts it in [2^14, 2^15) and emits
+// hi = fp16(x), mid = fp16(x - hi); the GEMM multiplies each drained 128-element chain by the tile's scale.
+template <int TILE>
+__device__ __forceinline__ void emit_tile_f16(const FactorView& f, const float* tile, int K, int o, int t0) {
+  static_assert(TILE == 512, "one lane owns four 16-byte groups of a 512-column tile");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 ps[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int col = t0 + 4 * lane + 128 * j;
+    ps[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (f.piece_scale && col < f.ld) ps[j] = *reinterpret_cast<const float4*>(f.piece_scale + col);
+  }
+  const int group = t0 / TILE;
+  for (int c = warp; c < K; c += UPD_THREADS / 32) {
+    const float4* src = reinterpret_cast<const float4*>(tile + c * TILE);
+    float4 v[4];
+    float m = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = src[lane + 32 * j];
+      v[j].x *= ps[j].x; v[j].y *= ps[j].y; v[j].z *= ps[j].z; v[j].w *= ps[j].w;
+      m = fmaxf(fmaxf(m, fmaxf(v[j].x, v[j].y)), fmaxf(v[j].z, v[j].w));
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    float sc = 1.f;
+    if (m > 0.f && m < 3.0e38f) {
+      int e;
+      frexpf(m, &e);
+      sc = ldexpf(1.f, e - 15);
+    }
+    const float inv = 1.f / sc;
+    const long long rowoff = (long long)(o + c) * f.ld;
+    if (lane == 0) f.tile_scale[(long long)(o + c) * f.n_ktiles + group] = sc;
+    __half* ph = static_cast<__half*>(f.P_hi) + rowoff;
+    __half* pm = static_cast<__half*>(f.P_mid) + rowoff;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = t0 + 4 * lane + 128 * j;
+      if (col < f.ld) {
+        const float x0 = v[j].x * inv, x1 = v[j].y * inv, x2 = v[j].z * inv, x3 = v[j].w * inv;
+        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 m01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), m23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+        uint2 oh, om;
+        oh.x = *reinterpret_cast<const uint32_t*>(&h01); oh.y = *reinterpret_cast<const uint32_t*>(&h23);
+        om.x = *reinterpret_cast<const uint32_t*>(&m01); om.y = *reinterpret_cast<const uint32_t*>(&m23);
+        *reinterpret_cast<uint2*>(ph + col) = oh;
+        *reinterpret_cast<uint2*>(pm + col) = om;
+      }
+    }
+  }
+}
+
 // Multiplicative update, rolled over the components: the thread's old values stay in registers for the K x K
 // contraction (static indices), while the two values that are addressed by the loop variable -- F[c] and NUM[c] of
 // the thread's items -- are read back from the shared-memory tiles the load phase parked them in (tileF doubles as
@@ -515,6 +572,9 @@ __device__ __forceinline__ double mu_body(const FactorView& f, const float* __re
     }
     if constexpr (GRAM) {
       __syncthreads();
+      if constexpr (VEC == 4) {
+        if (f.P_hi) emit_tile_f16<TILE>(f, tileF, K, o, t0);
+      }
       fused_gram_tile<KP, TILE>(tileF, gsum);
     }
   }
@@ -628,6 +688,9 @@ __device__ __forceinline__ double update_body(const FactorView& f, const float* 
     }
     if constexpr (GRAM) {
       __syncthreads();
+      if constexpr (VEC == 4) {
+        if (f.P_hi) emit_tile_f16<TILE>(f, tile, K, o, t0);
+      }
       fused_gram_tile<KP, TILE>(tile, gsum);
     }
   }
@@ -969,11 +1032,12 @@ int launch_split_scaled(const float* src, float* hi, float* lo, int rows, int ld
   return 0;
 }
 
-int launch_emit_f16(const float* F, int rows, int n, int ld, const float* pscale, void* hi, void* mid, float* rowscale,
-                    cudaStream_t s) {
-  CNMF_REQUIRE(ld % 8 == 0, "emit_f16: ld must be a multiple of 8");
+int launch_emit_f16(const float* F, int rows, int n, int ld, const float* pscale, void* hi, void* mid, float* tile_scale,
+                    int n_ktiles, cudaStream_t s) {
+  CNMF_REQUIRE(ld % 8 == 0 && n_ktiles * 512 >= ld, "emit_f16: bad ld / n_ktiles");
   if (rows <= 0) return 0;
-  emit_f16_kernel<<<rows, 256, 0, s>>>(F, n, ld, pscale, static_cast<__half*>(hi), static_cast<__half*>(mid), rowscale);
+  emit_f16_kernel<<<rows, 256, 0, s>>>(F, n, ld, pscale, static_cast<__half*>(hi), static_cast<__half*>(mid), tile_scale,
+                                       n_ktiles);
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -25,6 +25,12 @@ struct FactorView {
   int ld;
   const float* piece_scale;   // optional per-column scale folded into the tf32 pieces: hi + lo = F * piece_scale
                               // (exact-count datasets: the per-gene / per-cell scale of X lives in the A operand)
+  // f16x2: the Gram-fused update kernels (K <= 16) also emit the fp16 operand pieces of what they write, normalised per
+  // (row, 512-column tile): P_hi / P_mid (halves, row stride ld) and tile_scale[row * n_ktiles + tile]; nullptr = off
+  void* P_hi;
+  void* P_mid;
+  float* tile_scale;
+  int n_ktiles;    // ceil(ld / 512)
   int cpb;         // columns handled by one block of the update / cross kernels (multiple of upd_tile_cols(kp))
   int gcpb;        // columns handled by one block of the Gram kernel (multiple of 1024)
 };
@@ -58,10 +64,11 @@ int launch_split_tf32(const float* src, float* hi, float* lo, long long n_elems,
 int launch_split_scaled(const float* src, float* hi, float* lo, int rows, int ld, const float* col_scale, cudaStream_t s);
 
 // ---- fp16 operand pieces (f16x2 precision, exact-count datasets) ----
-// per packed row r: rowscale[r] = power of two with max_c(F[r,c] * pscale[c]) / rowscale[r] in [2^14, 2^15);
-// hi / mid (fp16, row stride ld halves) = the two pieces of F[r,:] * pscale / rowscale[r]
-int launch_emit_f16(const float* F, int rows, int n, int ld, const float* pscale, void* hi, void* mid, float* rowscale,
-                    cudaStream_t s);
+// per packed row r: sc = power of two with max_c(F[r,c] * pscale[c]) / sc in [2^14, 2^15), written to every entry of
+// tile_scale[r * n_ktiles + 0..n_ktiles) (the GEMM looks the scale up per 512-element group; the fused update kernels
+// write a different one per group); hi / mid (fp16, row stride ld halves) = the two pieces of F[r,:] * pscale / sc
+int launch_emit_f16(const float* F, int rows, int n, int ld, const float* pscale, void* hi, void* mid, float* tile_scale,
+                    int n_ktiles, cudaStream_t s);
 // dst (fp16) = src (fp32), elementwise; used for the exact integer count matrices
 int launch_to_half(const float* src, void* dst, long long n_elems, cudaStream_t s);
 
