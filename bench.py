@@ -307,7 +307,8 @@ def run_ours(args, rank, world, local):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        traffic = tj.get("dram_bytes_per_launch_f16" if f16 else "dram_bytes_per_launch", tj.get("dram_bytes_per_launch"))
     out = {
         "metric": METRIC, "value": value, "unit": "restarts/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -329,10 +330,10 @@ def run_ours(args, rank, world, local):
                                  "recognised as scaled integer counts -> exact B operand, 2 passes" if passes == 2
                                  else "general real matrix -> 3 passes")},
         "roofline_update": {"bound": "hbm", "kernel": "update_kernel<16,mu> (multiplicative update fused with the Gram "
-                            "of the factor it writes)", "achieved": upd_gbs, "peak": hbm_peak, "unit": "GB/s",
+                            "of the factor it writes and the emission of its tensor-core operand pieces)", "achieved": upd_gbs, "peak": hbm_peak, "unit": "GB/s",
                             "frac": upd_gbs / hbm_peak, "traffic": None,
                             "note": "second kernel of the step: achieved = algorithmic bytes per launch (factor read + "
-                                    "product slices read + factor and 2 tf32 pieces written, x live rows x items x 4 B) / "
+                                    "product slices read + factor and its 2 operand pieces written: 2 x fp16 or 2 x tf32, x live rows x items) / "
                                     "CUDA-event launch time; %d launches, %.1f ms of %.1f ms timed; peak = %s" % (
                                         upd_launches, upd_ms, ms, hbm_src)},
         "n_iter": {"mean": float(np.mean(n_iter)), "max": int(np.max(n_iter))},

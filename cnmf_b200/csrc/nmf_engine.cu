@@ -281,13 +281,14 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     return rc;
   };
   // algorithmic bytes of one update launch: factor read, product slices read, factor (+ tf32 pieces) written
-  auto upd_bytes = [&](int n_items, int nsplit, bool pieces) {
-    return 4.0 * (double)SK * (double)n_items * (double)(2 + nsplit + (pieces ? 2 : 0));
+  // (pieces: two tf32 pieces = 2 floats per element, two fp16 pieces = 1)
+  auto upd_bytes = [&](int n_items, int nsplit, int piece_floats) {
+    return 4.0 * (double)SK * (double)n_items * (double)(2 + nsplit + piece_floats);
   };
   auto update = [&](bool cd, const FactorView& f, const float* NUM, const GemmPlan& pl, const double* gram_in, float l1,
                     float l2, const FusedOut& out) -> int {
     h->launches += 1;
-    const int slot = h->prof_begin(s, upd_bytes(f.n, pl.splits, f.F_hi != nullptr), 1);
+    const int slot = h->prof_begin(s, upd_bytes(f.n, pl.splits, f.F_hi ? 2 : ((f.P_hi && out.gram_part) ? 1 : 0)), 1);
     const int rc = cd ? launch_cd_update(f, NUM, pl.splits, pl.split_stride, gram_in, bm(), l1, l2, out, s)
                       : launch_mu_update(f, NUM, pl.splits, pl.split_stride, gram_in, bm(), l1, l2, out, s);
     h->prof_end(s, slot);
