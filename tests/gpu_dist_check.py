@@ -50,7 +50,7 @@ def main():
         got = merged[int(k)].values
         for it in range(ref.shape[0] // k):
             e = np.linalg.norm(got[it * k:(it + 1) * k] - ref[it * k:(it + 1) * k]) / np.linalg.norm(ref[it * k:(it + 1) * k])
-            lim = max(1e-4, 3 * float(g["fp32dev_k%d" % k][it]))
+            lim = max(1e-4, 5 * float(g["fp32dev_k%d" % k][it]))
             assert e < lim, (k, it, e)
             worst = max(worst, e)
     print("rank %d/%d: merged spectra match the reference fixture (worst rel-L2 %.2e)" % (rank, world, worst), flush=True)
