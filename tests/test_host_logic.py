@@ -211,3 +211,22 @@ def test_solver_selection_rule():
     p = make_params(dict(solver="cd", alpha_W=0.5, alpha_H="same", l1_ratio=0.25, tol=1e-3, max_iter=7), 100, 40, "fp32")
     assert (p.solver, p.max_iter, p.tol) == (1, 7, 1e-3)
     assert p.l1_reg_W == 40 * 0.5 * 0.25 and p.l2_reg_H == 100 * 0.5 * 0.75      # sklearn _nmf.py:1249-1260
+
+
+def test_precision_names_and_hvg_ranking_from_stats():
+    """Host-side pieces of the f16x2 precision and of prepare(on_device=True) that need no GPU."""
+    from cnmf_b200 import _lib
+    from cnmf_b200.engine import precision_code, _params_precision, _DEFAULT_PRECISION
+    from cnmf_b200.pipeline import _highvar_from_stats, _highvar_genes
+    assert precision_code("f16x2") == _lib.PRECISION_F16X2 == 3 and _DEFAULT_PRECISION == _lib.PRECISION_F16X2
+    # params.precision names the arithmetic class (split-operand tensor-core products): 1 for both tf32x3 and f16x2
+    assert _params_precision(precision_code("f16x2")) == _params_precision(precision_code("tf32x3")) == _lib.PRECISION_TF32X3
+    assert _params_precision(precision_code("tf32x3-general")) == _lib.PRECISION_TF32X3
+    assert _params_precision(precision_code("fp32")) == _lib.PRECISION_FP32
+    rng = np.random.RandomState(3)
+    C = rng.poisson(rng.gamma(0.5, 2.0, size=(1, 400)), size=(300, 400)).astype(np.float64) + rng.poisson(0.05, size=(300, 400))
+    C = C[:, C.sum(axis=0) > 0]
+    T = C / C.sum(axis=1, keepdims=True) * 1e6
+    a = _highvar_genes(T, 50)
+    b = _highvar_from_stats(T.mean(axis=0), T.var(axis=0), 50)
+    assert a.sum() == 50 and np.array_equal(a, b)
