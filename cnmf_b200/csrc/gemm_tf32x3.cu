@@ -58,7 +58,9 @@ struct SmemLayout {
   static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFFSET = TILE_BYTES;            // full[STAGES], empty[STAGES], tfull[2], tempty[2]
   static constexpr int TMEM_PTR_OFFSET = BAR_OFFSET + (2 * STAGES + 4) * 8;
-  static constexpr int TOTAL = TMEM_PTR_OFFSET + 16;
+  static constexpr int EPI_OFFSET = TMEM_PTR_OFFSET + 16;   // per accumulate warp: 32 x 20-float transpose patch
+  static constexpr int EPI_BYTES = NUM_EPI_WARPS * 32 * 20 * 4;
+  static constexpr int TOTAL = EPI_OFFSET + EPI_BYTES;
   static constexpr int DYN_BYTES = TOTAL + 1024;           // slack for manual 1024 B alignment
 };
 
@@ -160,6 +162,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // F16 (with BEXACT): operands are fp16 (two pieces of A, one exact B); a k-block is still 128 B per row = 64 elements,
 // a k-step still 32 B = 16 elements (UMMA_K of kind::f16), so the smem / TMA / descriptor byte geometry is unchanged.
 template <int BN, int STAGES, bool BEXACT, bool F16>
+// 320 threads = 10 warps, allocated as 12 (granularity 4): at most 65536 / (12 * 32) = 170 registers per thread --
+// __launch_bounds__ makes ptxas pick 168; a higher __maxnreg__ compiles but cannot launch
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -321,19 +325,37 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         mbar_arrive(tempty_bar(buf));
         if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
       }
-      const int row = mt * BM + q * 32 + lane;
-      if (row < M) {
-        float* crow = C + static_cast<long long>(z) * c_split_stride + static_cast<long long>(row) * ldc;
+      // Epilogue.  A thread owns one output row, so a direct store touches 32 rows x 16 B per instruction (32 cache
+      // lines: the LSU, not the tensor pipe, then paces short tiles -- the 720-tile W half ran at 0.76 of the MMA rate
+      // against 0.92 for the long-K H half).  Each warp transposes 16-column chunks through a private 32 x 20-float
+      // shared-memory patch instead, so that one store instruction writes 8 rows x 64 B.
+      {
+        float* patch = reinterpret_cast<float*>(smem_gen + L::EPI_OFFSET) + (warp - 2) * (32 * 20);
+        const int row0 = mt * BM + q * 32;
         const int col0 = nt * bn + half * HALF;
+        const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;
+        float* cbase = C + static_cast<long long>(z) * c_split_stride;
 #pragma unroll
-        for (int i = 0; i < HALF; i += 4) {
-          if (half * HALF + i < bn && col0 + i + 3 < ldc) {
-            float4 v = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
-            if (out_scale) {                            // per-output-column scale (length >= ldc, zero padded)
-              const float4 sc = *reinterpret_cast<const float4*>(out_scale + col0 + i);
-              v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+        for (int c = 0; c < HALF; c += 16) {
+          if (half * HALF + c < bn) {                     // warp-uniform (bn is a multiple of 16)
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float4 v = make_float4(acc[c + i], acc[c + i + 1], acc[c + i + 2], acc[c + i + 3]);
+              if (out_scale && col0 + c + i + 3 < ldc) {  // per-output-column scale (length >= ldc, zero padded)
+                const float4 sc = *reinterpret_cast<const float4*>(out_scale + col0 + c + i);
+                v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+              }
+              *reinterpret_cast<float4*>(patch + lane * 20 + i) = v;
             }
-            *reinterpret_cast<float4*>(crow + col0 + i) = v;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int r = sub_r + 8 * j;
+              const float4 v = *reinterpret_cast<const float4*>(patch + r * 20 + sub_c);
+              const int grow = row0 + r, gcol = col0 + c + sub_c;
+              if (grow < M && gcol + 3 < ldc) *reinterpret_cast<float4*>(cbase + static_cast<long long>(grow) * ldc + gcol) = v;
+            }
+            __syncwarp();
           }
         }
       }
