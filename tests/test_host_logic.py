@@ -230,3 +230,33 @@ def test_precision_names_and_hvg_ranking_from_stats():
     a = _highvar_genes(T, 50)
     b = _highvar_from_stats(T.mean(axis=0), T.var(axis=0), 50)
     assert a.sum() == 50 and np.array_equal(a, b)
+
+
+def test_fp16_two_piece_split_bounds():
+    """The operand representation of the default precision, restated in numpy (what emit_f16_kernel / emit_tile_f16
+    compute): a row divided by the power of two that puts its maximum in [2^14, 2^15), then hi = fp16(x),
+    mid = fp16(x - hi).  Entries down to 2^-18 of the row maximum keep >= 21 significant bits like a tf32 pair; smaller
+    ones are off by at most 2^-39 of the row maximum; integer counts <= 2048 are exact in fp16."""
+    rng = np.random.RandomState(0)
+    A = (np.abs(rng.standard_cauchy((64, 4096))) * 10.0 ** rng.uniform(-8, 8, size=(64, 1))).astype(np.float32).astype(np.float64)
+    A[:, ::11] = 0.0
+    rowmax = A.max(axis=1, keepdims=True)
+    mant, exp = np.frexp(rowmax)                       # rowmax = mant * 2^exp, mant in [0.5, 1)
+    sc = np.ldexp(1.0, exp - 15)
+    x = A / sc
+    assert x.max() < 2 ** 15 and (x.max(axis=1) >= 2 ** 14).all()
+    hi = x.astype(np.float16).astype(np.float64)
+    mid = (x - hi).astype(np.float16).astype(np.float64)
+    assert np.isfinite(hi).all() and np.isfinite(mid).all()
+    err = np.abs((hi + mid) * sc - A)
+    big = x >= 2.0 ** -3                               # both pieces normal fp16 numbers
+    assert (err[big] <= A[big] * 2.0 ** -21).all()     # two 11-bit pieces
+    assert ((err / sc)[~big] <= 2.0 ** -25).all()      # subnormal `mid`: half an fp16 subnormal step, in scaled units ...
+    assert ((err / rowmax)[~big] <= 2.0 ** -39).all()  # ... which is 2^-39 of a row maximum >= 2^14
+    C = np.arange(0, 2049, dtype=np.float64)
+    assert np.array_equal(C.astype(np.float16).astype(np.float64), C)
+    # a product against integer counts: same error class as the tf32 pair
+    X = rng.poisson(0.7, size=(4096, 32)).astype(np.float64)
+    P = A @ X
+    Pr = ((hi + mid) * sc) @ X
+    assert np.abs(Pr - P).max() / np.abs(P).max() < 2e-7
