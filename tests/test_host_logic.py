@@ -260,3 +260,19 @@ def test_fp16_two_piece_split_bounds():
     P = A @ X
     Pr = ((hi + mid) * sc) @ X
     assert np.abs(Pr - P).max() / np.abs(P).max() < 2e-7
+
+
+def test_binding_table_matches_header_prototypes():
+    """Every prototype in include/cnmf_b200.h has the same number of parameters as its ctypes signature, the ABI
+    version constants agree, and struct cnmf_nmf_params has the size the ctypes mirror assumes."""
+    header = open(os.path.join(ROOT, "include", "cnmf_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = re.findall(r"\b(?:int|long long|const char\*)\s+(cnmf_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) >= 30
+    for name, args in protos:
+        args = args.strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
+    ver = int(re.search(r"#define CNMF_B200_ABI_VERSION (\d+)", header).group(1))
+    assert ver == _lib.ABI_VERSION == ctypes.CDLL(_lib.LIB_PATH).cnmf_abi_version()
+    assert ctypes.sizeof(_lib.NmfParams) == 4 * 4 + 5 * 8 + 2 * 4
