@@ -206,7 +206,8 @@ emit_f16_kernel(const float* __restrict__ F, int n, int ld, const float* __restr
     if (mm > 0.f && mm < 3.0e38f) {
       int e;
       frexpf(mm, &e);                    // mm = f * 2^e, f in [0.5, 1)
-      sc = ldexpf(1.f, e - 15);          // mm / sc in [2^14, 2^15)
+      sc = ldexpf(1.f, max(e - 15, -126));   // mm / sc in [2^14, 2^15); rows that decayed below 2^-111 (dead components
+                                             // of an over-specified K) keep a normal scale so that 1 / sc stays finite
     }
     sm[32] = sc;
   }
@@ -464,7 +465,7 @@ __device__ __forceinline__ void emit_tile_f16(const FactorView& f, const float* 
     if (m > 0.f && m < 3.0e38f) {
       int e;
       frexpf(m, &e);
-      sc = ldexpf(1.f, e - 15);
+      sc = ldexpf(1.f, max(e - 15, -126));     // see emit_f16_kernel: 1 / sc must stay finite for decayed rows
     }
     const float inv = 1.f / sc;
     const long long rowoff = (long long)(o + c) * f.ld;
