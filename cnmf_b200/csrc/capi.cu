@@ -191,8 +191,8 @@ int cnmf_profile_enable(cnmf_handle_t h, int on) {
   }
   h->ev_pending.clear();
   h->ev_used = 0;
-  if (on) {       // event creation is kept out of the timed region: a pool for ~8 000 launches up front
-    while (h->ev_pool.size() < 16384) {
+  if (on) {       // event creation is kept out of the timed region: a pool for ~32 000 launches up front
+    while (h->ev_pool.size() < 65536) {
       cudaEvent_t e;
       if (cudaEventCreate(&e) != cudaSuccess) break;
       h->ev_pool.push_back(e);
