@@ -42,6 +42,8 @@ SIGNATURES = {
     "cnmf_create": (_i, [_pp(_vp), _i]),
     "cnmf_destroy": (_i, [_vp]),
     "cnmf_launch_count": (_ll, [_vp]),
+    "cnmf_mem_info": (_i, [_vp, _pp(_ll), _pp(_ll), _pp(_ll)]),
+    "cnmf_solve_bytes_per_row": (_ll, [_vp]),
     "cnmf_profile_enable": (_i, [_vp, _i]),
     "cnmf_profile_get": (_i, [_vp, _pp(_d), _pp(_ll), _pp(_d)]),
     "cnmf_profile_get_class": (_i, [_vp, _i, _pp(_d), _pp(_ll), _pp(_d)]),
@@ -80,7 +82,7 @@ SIGNATURES = {
 _lib = None
 
 
-ABI_VERSION = 6      # include/cnmf_b200.h CNMF_B200_ABI_VERSION
+ABI_VERSION = 7      # include/cnmf_b200.h CNMF_B200_ABI_VERSION
 
 
 def load():

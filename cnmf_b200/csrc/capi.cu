@@ -182,6 +182,28 @@ int cnmf_destroy(cnmf_handle_t h) {
 
 long long cnmf_launch_count(cnmf_handle_t h) { return h ? h->launches : 0; }
 
+int cnmf_mem_info(cnmf_handle_t h, long long* free_bytes, long long* total_bytes, long long* cached_bytes) {
+  CNMF_REQUIRE(h, "mem_info: NULL handle");
+  CNMF_CUDA_CHECK(cudaSetDevice(h->device));
+  size_t fr = 0, tot = 0;
+  CNMF_CUDA_CHECK(cudaMemGetInfo(&fr, &tot));
+  size_t cached = h->pool_bytes;
+  for (auto& kv : h->ws) cached += kv.second.second;
+  if (free_bytes) *free_bytes = (long long)fr;
+  if (total_bytes) *total_bytes = (long long)tot;
+  if (cached_bytes) *cached_bytes = (long long)cached;
+  return 0;
+}
+
+long long cnmf_solve_bytes_per_row(cnmf_dataset_t d) {
+  if (!d) return 0;
+  // nmf_engine.cu / alloc_factors: Fr + 2 piece buffers, their 3 compaction alternates, the result slab and the
+  // product NUM_r along the cells; the same along the genes with one product slice per split-K slice
+  const long long splits_c = gemm_fixed_splits(d->n_rows, d->f16 ? 1 : 0);
+  const long long splits_r = gemm_fixed_splits(d->n_cols, d->f16 ? 1 : 0);
+  return 4LL * ((7 + splits_r) * (long long)d->ld_r + (7 + splits_c) * (long long)d->ld_c);
+}
+
 int cnmf_profile_enable(cnmf_handle_t h, int on) {
   CNMF_REQUIRE(h, "profile_enable: NULL handle");
   h->profile = on != 0;

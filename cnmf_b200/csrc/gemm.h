@@ -32,9 +32,12 @@ struct GemmArgs {
 // number of non-empty split-K slices for a reduction length Kd (k-blocks of 32 fp32 / 64 fp16 elements = 128 B)
 int gemm_effective_splits(int Kd, int splits, int f16 = 0);
 
-// Joint choice of the split-K factor and the tile width for the tcgen05 kernel: minimises
-// (waves of the persistent grid) x (tile cost) x (k-blocks per item + pipeline fill), with a mild penalty per
-// extra split-K slice (its partial output is written and re-read by the update kernel).
+// split-K factor used by the solver: a function of the reduction length only (slices of 64 k-blocks, <= 16), so that a
+// restart's result does not depend on the batch it is solved in
+int gemm_fixed_splits(int Kd, int f16 = 0);
+
+// Choice of the split-K factor (gemm_fixed_splits) and the tile width for the tcgen05 kernel: minimises
+// (waves of the persistent grid) x (tile cost) x (k-blocks per item + pipeline fill) over the tile widths.
 void gemm_plan(int M, int N, int Kd, int sm_count, int* splits, int* bn, int f16 = 0);
 
 // tcgen05 / TMEM / TMA path (gemm_tf32x3.cu)

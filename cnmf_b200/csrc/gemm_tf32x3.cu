@@ -32,7 +32,9 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstdlib>
+#include <map>
 #include <mutex>
+#include <tuple>
 
 #include "common.cuh"
 #include "gemm.h"
@@ -388,8 +390,25 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// 2D fp32 tensor (rows x cols, row stride ld elements), box = 32 cols x box_rows rows, 128B swizzle, zero OOB fill
+// 2D fp32 tensor (rows x cols, row stride ld elements), box = 32 cols x box_rows rows, 128B swizzle, zero OOB fill.
+// Encoded maps are cached by (pointer, shape, box): the solver relaunches the same few operand views a thousand
+// times per solve, and the driver call costs more than the launch itself.
+struct MapKey {
+  const void* ptr; int rows, cols, ld, box_rows, f16;
+  bool operator<(const MapKey& o) const {
+    return std::tie(ptr, rows, cols, ld, box_rows, f16) < std::tie(o.ptr, o.rows, o.cols, o.ld, o.box_rows, o.f16);
+  }
+};
+
 int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows, bool f16 = false) {
+  static std::mutex mu;
+  static std::map<MapKey, CUtensorMap> cache;
+  const MapKey key{ptr, rows, cols, ld, box_rows, f16 ? 1 : 0};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *map = it->second; return 0; }
+  }
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) { set_last_error("cuTensorMapEncodeTiled entry point not available"); return -2; }
   const int esize = f16 ? 2 : 4;                      // a box row is always 128 B: 32 fp32 or 64 fp16 elements
@@ -404,6 +423,9 @@ int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int
     set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
     return -2;
   }
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache.size() >= 512) cache.clear();             // views are few; a runaway caller just re-encodes
+  cache.emplace(key, *map);
   return 0;
 }
 
@@ -452,10 +474,10 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   if (splits != g.splits_effective) { set_last_error("gemm: splits_effective mismatch (use gemm_effective_splits)"); return -1; }
 
   auto kern = gemm_tf32x3_kernel<BN, STAGES, BEXACT, F16>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};              // per device: a second GPU in the same process needs its own call
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     CNMF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int items = m_tiles * n_tiles * splits;
   const int grid = items < sms ? items : sms;
@@ -480,31 +502,40 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
 
 }  // namespace
 
+// Split-K factor as a function of the reduction length ONLY: slices of 64 k-blocks (4 096 fp16 / 2 048 fp32
+// elements), at most 16 of them.  The partition of a restart's reduction -- and with it every rounding of its
+// products -- is then the same whatever else shares the batch and however far the batch has been compacted:
+// a (k, seed) restart gives the same spectra alone, in a worker's shard or in the full K-sweep, which is the
+// reference's semantics (independent sklearn calls, cnmf.py:735-745).
+int gemm_fixed_splits(int Kd, int f16) {
+  const int bke = f16 ? 2 * BK : BK;
+  const int total_kb = (Kd + bke - 1) / bke;
+  const int s = std::max(1, std::min(16, (total_kb + 63) / 64));
+  return gemm_effective_splits(Kd, s, f16);
+}
+
 void gemm_plan(int M, int N, int Kd, int sm_count, int* splits_out, int* bn_out, int f16) {
   const int m_tiles = (M + BM - 1) / BM;
   const int bke = f16 ? 2 * BK : BK;
   const int total_kb = (Kd + bke - 1) / bke;
-  const int max_splits = std::max(1, std::min(32, total_kb / 8));
+  const int s = gemm_fixed_splits(Kd, f16);
+  const int kbps = (total_kb + s - 1) / s;
   double best = -1.0;
-  int best_s = 1, best_bn = 256;
-  // narrow tiles (down to 128 columns; below that the accumulate warps, not the MMA chain, pace a tile) pay off
-  // when a compacted batch leaves less than one wave of 256-wide tiles
+  int best_bn = 256;
+  // the tile width only groups output columns (no effect on any sum): narrow tiles (down to 128 columns; below
+  // that the accumulate warps, not the MMA chain, pace a tile) pay off when a compacted batch leaves less than
+  // one wave of 256-wide tiles
   const int bn_lo = N <= 256 ? ((N + 15) / 16) * 16 : 128;
   const int bn_hi = N <= 256 ? bn_lo : 256;
-  for (int s = 1; s <= max_splits; ++s) {
-    const int se = gemm_effective_splits(Kd, s, f16);
-    if (se != s) continue;                                   // skip factors that collapse to a smaller one
-    const int kbps = (total_kb + s - 1) / s;
-    for (int bn = bn_hi; bn >= bn_lo; bn -= 16) {
-      const long long items = (long long)m_tiles * ((N + bn - 1) / bn) * s;
-      const long long waves = (items + sm_count - 1) / sm_count;
-      // tile cost bn + 64: per-tile A traffic / fill that does not shrink with bn; + 6 k-blocks of pipeline
-      // fill and epilogue per item; 2 % per extra slice for the partial-output traffic
-      const double cost = (double)waves * (bn + 64) * (kbps + 6) * (1.0 + 0.02 * (s - 1));
-      if (best < 0 || cost < best) { best = cost; best_s = s; best_bn = bn; }
-    }
+  for (int bn = bn_hi; bn >= bn_lo; bn -= 16) {
+    const long long items = (long long)m_tiles * ((N + bn - 1) / bn) * s;
+    const long long waves = (items + sm_count - 1) / sm_count;
+    // tile cost bn + 64: per-tile A traffic / fill that does not shrink with bn; + 6 k-blocks of pipeline
+    // fill and epilogue per item
+    const double cost = (double)waves * (bn + 64) * (kbps + 6);
+    if (best < 0 || cost < best) { best = cost; best_bn = bn; }
   }
-  *splits_out = best_s;
+  *splits_out = s;
   *bn_out = best_bn;
 }
 

@@ -42,16 +42,6 @@ DataView make_view(const cnmf_dataset_s* d, bool transposed) {
 
 namespace {
 
-int pick_splits(int sm_count, int M, int N, int Kd) {
-  const int tiles = ((M + 127) / 128) * ((N + 255) / 256);
-  const int total_kb = (Kd + 31) / 32;
-  int splits = 1;
-  if (tiles < 2 * sm_count) splits = (2 * sm_count + tiles - 1) / tiles;
-  splits = std::min(splits, std::max(1, total_kb / 8));
-  splits = std::min(splits, 32);
-  return gemm_effective_splits(Kd, splits);
-}
-
 struct GemmPlan {
   int splits;
   int bn;                   // tile width for the tcgen05 kernel (0 = let the launcher choose)
@@ -163,7 +153,7 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     if (tf32) {
       gemm_plan(sk, n, kd, h->sm_count, &pl->splits, &pl->bn, f16 ? 1 : 0);
     } else {
-      pl->splits = pick_splits(h->sm_count, sk, n, kd);
+      pl->splits = gemm_fixed_splits(kd, 0);
       pl->bn = 0;
     }
   };

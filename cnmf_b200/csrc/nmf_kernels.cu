@@ -89,7 +89,9 @@ __global__ void check_scaled_int_kernel(const float* __restrict__ X, int rows, i
     const float sc = (rs ? rs[r] : 1.f) * (cs ? cs[c] : 1.f);
     const float q = v / sc;
     const float n = rintf(q);
-    if (!(v > 0.f) || !(n >= 1.f) || n > 2048.f || fabsf(q - n) > 1e-4f * n) ++bad;
+    // fp32 rounding of a genuinely scaled integer: v, sc and the quotient each carry <= 2^-24 relative error, i.e.
+    // |q - n| <= 1.8e-7 n; anything further away (soft-corrected counts, arbitrary matrices) takes the general path
+    if (!(v > 0.f) || !(n >= 1.f) || n > 2048.f || fabsf(q - n) > 5e-7f * n) ++bad;
   }
   bad = warp_sum(bad);
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(n_bad, bad);
@@ -173,64 +175,69 @@ __global__ void sums_final_kernel(const double* __restrict__ part, int nblocks, 
 
 // ------------------------------------------------------------------ fp16 operand pieces (f16x2 precision)
 // kind::f16 MMAs run at twice the kind::tf32 rate and fp16 carries the same 11-bit significand as tf32; what it
-// lacks is exponent range.  So a packed factor row is divided by a power of two that puts its largest entry
-// (times the per-column scale of the exact-count path) in [2^14, 2^15) -- far above fp16's subnormals -- and split
-// into hi = fp16(x), mid = fp16(x - hi): 22 significant bits like the tf32 pair, absolute error <= 2^-39 of the row
-// maximum for entries too small to keep them.  The GEMM multiplies its output row by the same power of two.
-// One block per row: pass 1 finds the maximum, pass 2 (the row again, from L2) emits the pieces.
+// lacks is exponent range.  So every group of 512 reduction elements of a packed factor row is divided by a power
+// of two that puts its largest entry (times the per-column scale of the exact-count path) in [2^14, 2^15) -- far
+// above fp16's subnormals -- and split into hi = fp16(x), mid = fp16(x - hi): 22 significant bits like the tf32 pair,
+// absolute error <= 2^-39 of the group maximum for entries too small to keep them.  The GEMM multiplies each drained
+// 128-element chain by the group's power of two.
+// The pieces are a pure function of the factor values: this stand-alone kernel (initial factors, re-packing after a
+// compaction, K > 16 batches) and the in-update emission (emit_tile_f16) produce the same bits, so a restart's
+// operands do not depend on when the batch around it was compacted.
+// One block per row, one warp per 512-column group, a lane owns four 16-byte quads of the group.
+__device__ __forceinline__ float f16_group_scale(float m) {
+  float sc = 1.f;
+  if (m > 0.f && m < 3.0e38f) {
+    int e;
+    frexpf(m, &e);                       // m = f * 2^e, f in [0.5, 1)
+    sc = ldexpf(1.f, max(e - 15, -126)); // m / sc in [2^14, 2^15); groups that decayed below 2^-111 (dead components
+                                         // of an over-specified K) keep a normal scale so that 1 / sc stays finite
+  }
+  return sc;
+}
+
 __global__ void __launch_bounds__(256)
 emit_f16_kernel(const float* __restrict__ F, int n, int ld, const float* __restrict__ pscale, __half* __restrict__ hi,
                 __half* __restrict__ mid, float* __restrict__ tile_scale, int n_ktiles) {
-  __shared__ float sm[33];
   const long long row = blockIdx.x;
-  const float4* src = reinterpret_cast<const float4*>(F + row * ld);
-  const float4* ps4 = reinterpret_cast<const float4*>(pscale);
-  const int n4 = ld / 4;
-  float m = 0.f;
-  for (int q = threadIdx.x; q < n4; q += blockDim.x) {
-    float4 v = src[q];
-    if (pscale) {
-      const float4 p = ps4[q];
-      v.x *= p.x; v.y *= p.y; v.z *= p.z; v.w *= p.w;
-    }
-    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* src = F + row * ld;
+  for (int g = warp; g < n_ktiles; g += blockDim.x >> 5) {
+    const int t0 = g * 512;
+    float4 v[4];
+    float m = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float mm = 0.f;
-    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) mm = fmaxf(mm, sm[w]);
-    float sc = 1.f;
-    if (mm > 0.f && mm < 3.0e38f) {
-      int e;
-      frexpf(mm, &e);                    // mm = f * 2^e, f in [0.5, 1)
-      sc = ldexpf(1.f, max(e - 15, -126));   // mm / sc in [2^14, 2^15); rows that decayed below 2^-111 (dead components
-                                             // of an over-specified K) keep a normal scale so that 1 / sc stays finite
+    for (int j = 0; j < 4; ++j) {
+      const int col = t0 + 4 * lane + 128 * j;
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col < ld) {
+        v[j] = *reinterpret_cast<const float4*>(src + col);
+        if (pscale) {
+          const float4 p = *reinterpret_cast<const float4*>(pscale + col);
+          v[j].x *= p.x; v[j].y *= p.y; v[j].z *= p.z; v[j].w *= p.w;
+        }
+      }
+      m = fmaxf(fmaxf(m, fmaxf(v[j].x, v[j].y)), fmaxf(v[j].z, v[j].w));
     }
-    sm[32] = sc;
-  }
-  __syncthreads();
-  for (int g = threadIdx.x; g < n_ktiles; g += blockDim.x) tile_scale[row * n_ktiles + g] = sm[32];
-  const float inv = 1.f / sm[32];        // power of two: exact
-  uint2* dh = reinterpret_cast<uint2*>(hi + row * ld);
-  uint2* dm = reinterpret_cast<uint2*>(mid + row * ld);
-  for (int q = threadIdx.x; q < n4; q += blockDim.x) {
-    float4 v = src[q];
-    if (pscale) {
-      const float4 p = ps4[q];
-      v.x *= p.x; v.y *= p.y; v.z *= p.z; v.w *= p.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float sc = f16_group_scale(m);
+    const float inv = 1.f / sc;          // power of two: exact
+    if (lane == 0) tile_scale[row * n_ktiles + g] = sc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = t0 + 4 * lane + 128 * j;
+      if (col < ld) {
+        const float x0 = v[j].x * inv, x1 = v[j].y * inv, x2 = v[j].z * inv, x3 = v[j].w * inv;
+        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 m01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), m23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+        uint2 oh, om;
+        oh.x = *reinterpret_cast<const uint32_t*>(&h01); oh.y = *reinterpret_cast<const uint32_t*>(&h23);
+        om.x = *reinterpret_cast<const uint32_t*>(&m01); om.y = *reinterpret_cast<const uint32_t*>(&m23);
+        *reinterpret_cast<uint2*>(hi + row * ld + col) = oh;
+        *reinterpret_cast<uint2*>(mid + row * ld + col) = om;
+      }
     }
-    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
-    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
-    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-    const __half2 m01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), m23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
-    uint2 oh, om;
-    oh.x = *reinterpret_cast<const uint32_t*>(&h01); oh.y = *reinterpret_cast<const uint32_t*>(&h23);
-    om.x = *reinterpret_cast<const uint32_t*>(&m01); om.y = *reinterpret_cast<const uint32_t*>(&m23);
-    dh[q] = oh;
-    dm[q] = om;
   }
 }
 
@@ -461,12 +468,7 @@ __device__ __forceinline__ void emit_tile_f16(const FactorView& f, const float* 
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
-    float sc = 1.f;
-    if (m > 0.f && m < 3.0e38f) {
-      int e;
-      frexpf(m, &e);
-      sc = ldexpf(1.f, max(e - 15, -126));     // see emit_f16_kernel: 1 / sc must stay finite for decayed rows
-    }
+    const float sc = f16_group_scale(m);       // same bits as the stand-alone emit_f16_kernel
     const float inv = 1.f / sc;
     const long long rowoff = (long long)(o + c) * f.ld;
     if (lane == 0) f.tile_scale[(long long)(o + c) * f.n_ktiles + group] = sc;

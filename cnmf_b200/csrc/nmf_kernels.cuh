@@ -75,7 +75,7 @@ int launch_to_half(const float* src, void* dst, long long n_elems, cudaStream_t 
 // ---- exact-count detection (dataset preparation) ----
 // col_min[c] / row_min[r] = smallest strictly positive entry of the column / row (+inf if none)
 int launch_min_positive(const float* X, int rows, int cols, int ld, float* col_min, float* row_min, cudaStream_t s);
-// counts entries that are not (positive-integer <= 2048) * row_scale[r] * col_scale[c] within 1e-4 relative
+// counts entries that are not (positive-integer <= 2048) * row_scale[r] * col_scale[c] within 5e-7 relative (fp32 rounding of the scaled integer)
 // (either scale may be nullptr = 1); *n_bad is accumulated atomically (zero it first)
 int launch_check_scaled_int(const float* X, int rows, int cols, int ld, const float* row_scale, const float* col_scale,
                             int* n_bad, cudaStream_t s);

@@ -29,7 +29,23 @@ def _params_precision(p):
     return PRECISION_TF32X3 if p in (PRECISION_TF32X3_GENERAL, PRECISION_F16X2) else p
 
 
-def make_params(nmf_kwargs, n_samples, n_features, precision):
+def check_supported(ks=None, init="random", beta_loss="frobenius"):
+    """Options the CUDA path does not implement are refused where the user states them (prepare / the CLI), not
+    hours later inside factorize: n_components > 32, init != 'random' (cnmf.py:1252 also offers 'nndsvd'),
+    beta_loss outside {frobenius, kullback-leibler, itakura-saito}."""
+    if ks is not None:
+        bad = [int(k) for k in np.atleast_1d(ks) if int(k) < 1 or int(k) > _lib.MAX_COMPONENTS]
+        if bad:
+            raise ValueError("cnmf_b200: n_components must be in [1, %d] on the CUDA path (got %s); the batched "
+                             "kernels keep a restart's K x K Gram matrix and its K factor values per item on chip"
+                             % (_lib.MAX_COMPONENTS, bad))
+    if init != "random":
+        raise NotImplementedError("cnmf_b200: only init='random' (the reference default, cnmf.py:335) is implemented "
+                                  "on the CUDA path (got %r)" % (init,))
+    loss_code(beta_loss)
+
+
+def make_params(nmf_kwargs, n_samples, n_features, precision, for_refit=False):
     """nmf_kwargs dict of cnmf.py:618-631 -> struct cnmf_nmf_params.
 
     Regularisation scaling follows sklearn/decomposition/_nmf.py:1249-1260.  Only what the CUDA
@@ -39,7 +55,7 @@ def make_params(nmf_kwargs, n_samples, n_features, precision):
     loss = loss_code(beta)
     if loss != LOSS_FROBENIUS and solver != "mu":      # sklearn _nmf.py:1195-1199
         raise ValueError("Invalid beta_loss parameter: solver %r does not handle beta_loss = %r" % (solver, beta))
-    if nmf_kwargs.get("init", "random") != "random":
+    if not for_refit and nmf_kwargs.get("init", "random") != "random":      # no random init when update_H=False
         raise NotImplementedError("cnmf_b200: only init='random' is implemented on the CUDA path")
     if solver not in ("mu", "cd"):
         raise ValueError("solver must be 'mu' or 'cd'")
@@ -112,6 +128,12 @@ class Engine:
                                               ctypes.byref(fl)))
         return ms.value, int(n.value), fl.value
 
+    def mem_info(self):
+        """(free, total, cached) device bytes: cudaMemGetInfo plus what the handle's own pool / workspace holds."""
+        v = [ctypes.c_longlong() for _ in range(3)]
+        check(self.lib.cnmf_mem_info(self._h, *[ctypes.byref(x) for x in v]))
+        return tuple(int(x.value) for x in v)
+
     def last_timing(self):
         """Host wall-clock phases (ms) of the last factorize: dict(rng, h2d, solve, d2h)."""
         v = [ctypes.c_double() for _ in range(4)]
@@ -173,6 +195,16 @@ class Dataset:
         a, b = ctypes.c_int(), ctypes.c_int()
         check(self.lib.cnmf_dataset_ld(self._d, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
+
+    def solve_bytes_per_row(self):
+        """Device bytes one packed factor row costs in a batched solve (workspace sizing for restart groups)."""
+        return int(self.lib.cnmf_solve_bytes_per_row(self._d))
+
+    def max_rows_per_solve(self, fraction=0.8):
+        """How many packed rows (sum of n_components over restarts) fit one batched solve in the device memory that
+        is free or already cached by this handle."""
+        free, _, cached = self.engine.mem_info()
+        return max(1, int(fraction * (free + cached)) // max(1, self.solve_bytes_per_row()))
 
     def random_init_dev(self, ks, seeds, Wt_ptr, H_ptr):
         """sklearn's random init for every (k, seed), generated on the GPU into packed padded device buffers."""
@@ -291,7 +323,7 @@ class Dataset:
         n, g = self.shape
         n_r, n_c = (g, n) if transposed else (n, g)
         assert fixed.shape[1] == n_c
-        p = make_params(nmf_kwargs, n_r, n_c, self.precision)
+        p = make_params(nmf_kwargs, n_r, n_c, self.precision, for_refit=True)
         self._check_loss(p)
         out = np.empty((n_r, k), np.float32)
         it = ctypes.c_int32(0)

@@ -42,6 +42,10 @@ class CellGeneMatrix:
     def shape(self):
         return self.X.shape
 
+    @property
+    def is_sparse(self):
+        return hasattr(self.X, "tocsr")
+
     def dense(self, dtype=np.float64):
         X = self.X.toarray() if hasattr(self.X, "toarray") else np.asarray(self.X)
         return np.ascontiguousarray(X, dtype=dtype)
@@ -75,8 +79,13 @@ def write_matrix(path, mat):
         warnings.warn("anndata is not installed: cells x genes matrices are stored as '<name>.h5ad.npz' "
                       "instead of '.h5ad'", UserWarning)
         _warned = True
-    np.savez(path + ".npz", X=mat.dense(np.float64), obs=np.asarray(mat.obs_names, dtype=object),
-             var=np.asarray(mat.var_names, dtype=object))
+    names = dict(obs=np.asarray(mat.obs_names, dtype=object), var=np.asarray(mat.var_names, dtype=object))
+    if hasattr(mat.X, "tocsr"):       # sparse stays sparse (the reference keeps CSR unless --densify, cnmf.py:399-405)
+        csr = mat.X.tocsr()
+        np.savez(path + ".npz", csr_data=csr.data.astype(np.float64), csr_indices=csr.indices, csr_indptr=csr.indptr,
+                 csr_shape=np.asarray(csr.shape), **names)
+    else:
+        np.savez(path + ".npz", X=mat.dense(np.float64), **names)
     return path + ".npz"
 
 
@@ -87,6 +96,10 @@ def read_matrix(path):
         return CellGeneMatrix(ad.X, ad.obs.index, ad.var.index)
     if os.path.exists(path + ".npz"):
         with np.load(path + ".npz", allow_pickle=True) as f:
+            if "csr_data" in f:
+                import scipy.sparse as sp
+                X = sp.csr_matrix((f["csr_data"], f["csr_indices"], f["csr_indptr"]), shape=tuple(f["csr_shape"]))
+                return CellGeneMatrix(X, f["obs"], f["var"])
             return CellGeneMatrix(f["X"], f["obs"], f["var"])
     if os.path.exists(path):
         raise RuntimeError("%s is an .h5ad file but anndata is not installed" % path)

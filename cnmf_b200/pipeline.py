@@ -77,9 +77,30 @@ def _highvar_from_stats(mean, var, numgenes):
     return ratio.index.isin(chosen)
 
 
+def _maybe_csr(X, sparse):
+    if not sparse:
+        return X
+    import scipy.sparse as sp
+    return sp.csr_matrix(X)
+
+
 def _highvar_genes(tpm, numgenes):
     """Same ranking on a dense TPM matrix held on the host."""
     return _highvar_from_stats(tpm.mean(axis=0), tpm.var(axis=0, ddof=0), numgenes)
+
+
+def plan_groups(ks, max_rows):
+    """Consecutive job ranges [lo, hi) whose packed rows (sum of k) fit `max_rows`; a single job always forms a
+    group of its own even when it alone exceeds the budget (the allocation then reports the shortage)."""
+    groups, lo, rows = [], 0, 0
+    for i, k in enumerate(ks):
+        if i > lo and rows + k > max_rows:
+            groups.append((lo, i))
+            lo, rows = i, 0
+        rows += k
+    if lo < len(ks):
+        groups.append((lo, len(ks)))
+    return groups
 
 
 class cNMF:
@@ -127,7 +148,14 @@ class cNMF:
         per-cell totals, the TPM gene statistics behind the over-dispersion ranking and `tpm_stats`, the per-gene
         scale of the HVG matrix and the HVG matrix itself are computed by CUDA kernels (float64 accumulation from the
         exact integer counts); the normalised matrix stays in HBM for factorize().  Raises without a GPU."""
+        from .engine import check_supported
+        check_supported(components, init, beta_loss)                  # fail here, not hours later in factorize
         counts = cio.read_counts(counts_fn)
+        # the reference keeps X sparse (CSR) unless --densify: text / npz inputs are converted to CSR, .h5ad keeps
+        # what the file holds (cnmf.py:383-405).  The CUDA path is dense, but the two branches differ in one rule
+        # -- sc.pp.scale(zero_center=False) maps a zero standard deviation to 1 (cnmf.py:538, 967) where the dense
+        # branch divides by it (cnmf.py:542) -- and the stored matrices stay CSR like the reference's
+        sparse_sem = (not densify) and (counts.is_sparse or not counts_fn.endswith(".h5ad"))
         C = counts.dense(np.float64)
         dev = None
         if on_device:
@@ -136,17 +164,18 @@ class cNMF:
             dev = self.engine().dataset(C, precision=self.precision)       # raw counts resident in HBM
             totals = dev.row_sums()
             tpm_X = C / totals[:, None] * 1e6                              # host copy only for the tpm file
-            tpm = cio.CellGeneMatrix(tpm_X, counts.obs_names, counts.var_names)
+            tpm = cio.CellGeneMatrix(_maybe_csr(tpm_X, sparse_sem), counts.obs_names, counts.var_names)
             t_mean, t_var = dev.col_stats(row_scale=1e6 / totals)
             t_std = np.sqrt(t_var)
         elif tpm_fn is None:
             tpm_X = C / C.sum(axis=1, keepdims=True) * 1e6           # cnmf.py:245-251
-            tpm = cio.CellGeneMatrix(tpm_X, counts.obs_names, counts.var_names)
+            tpm = cio.CellGeneMatrix(_maybe_csr(tpm_X, sparse_sem), counts.obs_names, counts.var_names)
         else:
             tpm = cio.read_counts(tpm_fn)
-            tpm = cio.CellGeneMatrix(tpm.dense(np.float64), tpm.obs_names, tpm.var_names)
+            tpm_X = tpm.dense(np.float64)
+            tpm = cio.CellGeneMatrix(_maybe_csr(tpm_X, sparse_sem), tpm.obs_names, tpm.var_names)
         cio.write_matrix(self.paths["tpm"], tpm)
-        T = tpm.X
+        T = tpm_X
         if dev is None:
             t_mean, t_std = T.mean(axis=0), T.std(axis=0, ddof=0)
         stats = pd.DataFrame([t_mean, t_std], index=["__mean", "__std"], columns=tpm.var_names).T   # cnmf.py:439-445
@@ -164,18 +193,23 @@ class cNMF:
             n = C.shape[0]
             _, c_var = dev.col_stats()
             std1 = np.sqrt(c_var[idx] * n / (n - 1.0))                 # std(ddof=1) of the selected count columns
+            if sparse_sem:
+                std1[std1 == 0] = 1.0
             X /= std1
             with np.errstate(divide="ignore"):
                 self._resident_norm = dev.from_columns(idx, 1.0 / std1)   # counts[:, hvgs] / std, built on the device
             dev.close()
         else:
-            X /= X.std(axis=0, ddof=1)                                 # cnmf.py:542 (no centring)
+            std1 = X.std(axis=0, ddof=1)
+            if sparse_sem:
+                std1[std1 == 0] = 1.0                                  # sc.pp.scale(zero_center=False), cnmf.py:538
+            X /= std1                                                  # cnmf.py:542 (no centring)
         if np.isnan(X).sum() > 0:
             print("Warning NaNs in normalized counts matrix")
-        norm.X = X
+        norm.X = _maybe_csr(X, sparse_sem)
         with open(self.paths["nmf_genes_list"], "w") as F:
             F.write("\n".join(hvgs))
-        zero = X.sum(axis=1) == 0
+        zero = np.asarray(X.sum(axis=1)).reshape(-1) == 0
         if zero.sum() > 0:                                             # cnmf.py:551-554
             ex = norm.obs_names[np.ravel(zero)]
             raise Exception("Error: %d cells have zero counts of overdispersed genes. E.g. %s. Filter those cells "
@@ -196,6 +230,8 @@ class cNMF:
         """(k, iter, seed, completed) table + solver kwargs; identical seed rule to cnmf.py:593-633."""
         if type(ks) is int:
             ks = [ks]
+        from .engine import check_supported
+        check_supported(ks, init, beta_loss)
         k_list = sorted(set(list(ks)))
         n_runs = len(ks) * n_iter
         np.random.seed(seed=random_state_seed)
@@ -266,19 +302,29 @@ class cNMF:
             return
         ks = [int(run_params.iloc[j]["n_components"]) for j in jobs]
         seeds = [int(run_params.iloc[j]["nmf_seed"]) for j in jobs]
-        print("[Worker %d]. Starting %d tasks as one batch." % (worker_i, len(jobs)))
         X = norm.X
         if self._resident_norm is not None and self._resident_norm.shape == tuple(norm.X.shape):
             X = self._resident_norm                    # already in HBM (prepare(on_device=True)): no H2D
-        spectra, n_iter, _ = self._nmf_batched(X, ks, seeds, kw)
-        if int(np.max(n_iter)) >= int(kw["max_iter"]):
+        ds = self._dataset(X)
+        # Restart groups sized from the device memory that is actually free: a solve's workspace grows with
+        # sum(k) x cells, so a large K-sweep on a large atlas goes through several batched solves instead of
+        # failing in cudaMalloc; each group's files are written as soon as it finishes, so an interrupted run
+        # resumes with skip_completed_runs exactly like the reference's per-job loop (cnmf.py:735-745).
+        groups = plan_groups(ks, ds.max_rows_per_solve())
+        print("[Worker %d]. Starting %d tasks in %d batched solve%s." % (worker_i, len(jobs), len(groups),
+                                                                        "" if len(groups) == 1 else "s"))
+        hit_max = False
+        for lo, hi in groups:
+            spectra, n_iter, _ = self._nmf_batched(ds, ks[lo:hi], seeds[lo:hi], kw)
+            hit_max = hit_max or int(np.max(n_iter)) >= int(kw["max_iter"])
+            for j, sp in zip(jobs[lo:hi], spectra):
+                p = run_params.iloc[j]
+                df = pd.DataFrame(sp, index=np.arange(1, int(p["n_components"]) + 1), columns=norm.var_names)
+                save_df_to_npz(df, self.paths["iter_spectra"] % (p["n_components"], p["iter"]))
+        if hit_max:
             from sklearn.exceptions import ConvergenceWarning
             warnings.warn("Maximum number of iterations %d reached. Increase it to improve convergence." % kw["max_iter"],
                           ConvergenceWarning)
-        for j, sp in zip(jobs, spectra):
-            p = run_params.iloc[j]
-            df = pd.DataFrame(sp, index=np.arange(1, int(p["n_components"]) + 1), columns=norm.var_names)
-            save_df_to_npz(df, self.paths["iter_spectra"] % (p["n_components"], p["iter"]))
 
     def combine(self, components=None, skip_missing_files=False):
         if type(components) is int:
@@ -417,6 +463,8 @@ class cNMF:
             _, var = tpm_ds.col_stats()
             n = tpm.shape[0]
             std1 = np.sqrt(var[hv_idx] * n / (n - 1.0))                             # std(ddof=1)
+            if tpm.is_sparse:
+                std1[std1 == 0] = 1.0                                               # sc.pp.scale, cnmf.py:967
             norm_tpm_ds = tpm_ds.from_columns(hv_idx, 1.0 / std1)
             sp_rf = spectra_tpm.loc[:, hvgs].div(tpm_stats.loc[hvgs, "__std"], axis=1)
             rf2, _, _ = norm_tpm_ds.refit(sp_rf.values, kw)
@@ -439,29 +487,40 @@ class cNMF:
         if build_ref:
             self.build_reference(k, density_threshold)
 
-    def _clustergram(self, S, topics_dist, density_filter, labels, local_density, density_threshold, tag, close_fig):
-        """Figure of cnmf.py:986-1079 -- visualisation, outside the accelerated path; needs matplotlib."""
-        try:
-            import matplotlib.pyplot as plt
-            from scipy.cluster.hierarchy import leaves_list, linkage
-            from scipy.spatial.distance import squareform
-        except Exception:
-            warnings.warn("matplotlib is not installed: skipping the clustergram figure", UserWarning)
-            return
+    @staticmethod
+    def clustergram_order(S, topics_dist, density_filter, labels):
+        """Row order of the clustergram (cnmf.py:986-1010): clusters in label order, inside a cluster the leaf order
+        of an average-linkage tree over the pairwise distances.  The distances come from the GPU (the R x R matrix
+        the density step already produced, or a fresh one for the filtered spectra); the O(R) tree is scipy, as in
+        the reference.  Returns (order, filtered distance matrix)."""
+        from scipy.cluster.hierarchy import leaves_list, linkage
+        from scipy.spatial.distance import squareform
         if topics_dist is None:
             _, topics_dist = S.local_density(1, return_dist=True)
         else:
-            keep = density_filter.values
+            keep = np.asarray(density_filter.values if hasattr(density_filter, "values") else density_filter, dtype=bool)
             topics_dist = topics_dist[keep, :][:, keep]
+        labels = np.asarray(labels.values if hasattr(labels, "values") else labels)
         order = []
         for cl in sorted(set(labels)):
-            f = (labels == cl).values
+            f = labels == cl
             if f.sum() > 1:
                 d = squareform(topics_dist[f, :][:, f], checks=False)
                 d[d < 0] = 0
                 order += list(np.where(f)[0][leaves_list(linkage(d, "average"))])
             else:
                 order += list(np.where(f)[0])
+        return order, topics_dist
+
+    def _clustergram(self, S, topics_dist, density_filter, labels, local_density, density_threshold, tag, close_fig):
+        """Figure of cnmf.py:986-1079 -- visualisation, outside the accelerated path; needs matplotlib."""
+        order, topics_dist = self.clustergram_order(S, topics_dist, density_filter, labels)
+        self.last_clustergram_order = order
+        try:
+            import matplotlib.pyplot as plt
+        except Exception:
+            warnings.warn("matplotlib is not installed: skipping the clustergram figure", UserWarning)
+            return
         fig = plt.figure(figsize=(10, 9.5))
         ax = fig.add_axes([0.08, 0.05, 0.6, 0.85])
         D = topics_dist[order, :][:, order]
@@ -554,7 +613,9 @@ def main():
     ap.add_argument("--tpm", type=str, default=None)
     ap.add_argument("--max-nmf-iter", type=int, default=1000)
     ap.add_argument("--beta-loss", type=str, choices=["frobenius", "kullback-leibler", "itakura-saito"], default="frobenius")
-    ap.add_argument("--init", type=str, choices=["random", "nndsvd"], default="random")
+    ap.add_argument("--init", type=str, choices=["random"], default="random",
+                    help="[cnmf_b200] only the reference default 'random' is implemented on the CUDA path (cnmf.py:1252 "
+                         "also offers 'nndsvd')")
     ap.add_argument("--densify", dest="densify", action="store_true", default=False)
     ap.add_argument("--worker-index", type=int, default=0)
     ap.add_argument("--skip-completed-runs", action="store_true", default=False)

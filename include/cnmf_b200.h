@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CNMF_B200_ABI_VERSION 6
+#define CNMF_B200_ABI_VERSION 7
 #define CNMF_MAX_COMPONENTS 32          /* largest n_components per restart on the CUDA path */
 
 typedef struct cnmf_handle_s* cnmf_handle_t;
@@ -68,6 +68,13 @@ int cnmf_create(cnmf_handle_t* out, int device);
 int cnmf_destroy(cnmf_handle_t h);
 /* number of kernels this library has launched through the handle since creation */
 long long cnmf_launch_count(cnmf_handle_t h);
+/* free / total bytes of the handle's device (cudaMemGetInfo) plus the bytes parked in the handle's own buffer
+ * pool and workspace (reusable by the next call): what the facade sizes its restart groups from, so that a
+ * K-sweep larger than HBM is factorized in several batched solves instead of failing in cudaMalloc */
+int cnmf_mem_info(cnmf_handle_t h, long long* free_bytes, long long* total_bytes, long long* cached_bytes);
+/* device bytes one packed factor row (one component of one restart) costs in a batched solve on this dataset:
+ * factors, operand pieces, compaction ping-pong and result slabs, product slices */
+long long cnmf_solve_bytes_per_row(cnmf_dataset_t d);
 
 /* per-launch CUDA-event timing of the dominant kernel (the batched GEMM) on its launching stream:
  * enable (resets the counters), run, then read total device ms, launches and algorithmic FLOPs

@@ -9,7 +9,8 @@ network downloads (download_pytest_data.py:38-52) and are not available offline,
 fixtures -- outputs of the reference itself on deterministic synthetic inputs -- are what
 pins the oracle and, through it, the CUDA path.
 
-Fixture ``<tag>.npz`` (one per solver / loss, tags ``sim_mu`` / ``sim_cd`` / ``sim_kl``) holds
+Fixture ``<tag>.npz`` (one per solver / loss, tags ``sim_mu`` / ``sim_cd`` / ``sim_kl``; ``c1_mu`` / ``c1_cd`` are
+BASELINE.json configs[0] -- 1 000 cells x 500 HVG, K=7, 10 restarts -- in full) holds
   counts          int16 cells x genes_all  (input given to reference prepare())
   hvg_idx         positions of the HVGs chosen by the reference inside genes_all
   ks, n_iter, seed, solver   (+ beta_loss in fixtures generated for a non-Frobenius loss)
@@ -45,6 +46,9 @@ CASES = {
     "sim_mu": (400, 260, 5, 200, [4, 5], 8, 14, 2.0, 0.5),      # float beta_loss -> solver 'mu' 
     "sim_cd": (400, 260, 5, 200, [4, 5], 8, 14, "frobenius", 0.5),  # reference default -> 'cd'
     "sim_kl": (400, 260, 5, 200, [4, 5], 6, 14, "kullback-leibler", 0.5),  # --beta-loss kullback-leibler -> 'mu', beta=1
+    # BASELINE.json configs[0] in full: 1 000 cells x 500 HVG, K=7, n_iter=10 (both solvers)
+    "c1_mu": (1000, 640, 7, 500, [7], 10, 14, 2.0, 0.5),
+    "c1_cd": (1000, 640, 7, 500, [7], 10, 14, "frobenius", 0.5),
 }
 
 

@@ -2,9 +2,8 @@
 and against the fixtures produced by the unmodified reference.
 
 Tolerances (BASELINE.json north_star): spectra within 1e-4 rel-L2 of the reference (float64
-scikit-learn) on identical seeds, identical iteration counts.  The CUDA path computes in fp32
-(3xTF32 tensor-core products, fp32 accumulate); a restart whose trajectory is so ill-conditioned that
-scikit-learn's OWN float32 path misses 1e-4 (fixture `fp32dev`) is held to 5x that deviation instead (the restart is chaotic: different batch compositions land between 2e-4 and 5e-4).
+scikit-learn) on identical seeds, identical iteration counts -- for EVERY restart of every fixture and of the
+sampled BASELINE configurations, with one exemption stated by name (ILL_CONDITIONED below).
 """
 import os
 import warnings
@@ -18,6 +17,10 @@ pytestmark = pytest.mark.gpu
 
 TOL_SPECTRA = 1e-4       # north star: spectra within 1e-4 rel-L2
 TOL_GEMM = 2e-6          # fp32-class GEMM vs float64
+# The single exemption from TOL_SPECTRA: fixture sim_mu, K=4, iter 0 (360 MU iterations along a nearly flat valley).  scikit-learn's OWN float32 path ends 1.75e-4 away from its float64 path on this restart
+# (fixture `fp32dev_k4[0]`; every other restart of every fixture: <= 1e-5), so no implementation that stores its
+# factors in fp32 can hold 1e-4 here; it is held to 1e-3 and must still reproduce the iteration count.
+ILL_CONDITIONED = {("sim_mu", 4, 0): 1e-3}
 
 
 def rel(a, b):
@@ -137,10 +140,20 @@ def test_exact_count_detection(eng):
     assert not eng.dataset(big).exact
 
 
-@pytest.mark.parametrize("precision", ["tf32x3", "f16x2", "tf32x3-hostrng", "tf32x3-general", "fp32"])
-@pytest.mark.parametrize("tag", ["sim_mu", "sim_cd"])
+def _fixture_cases():
+    out = []
+    for tag in ("sim_mu", "sim_cd"):
+        for precision in ("tf32x3", "f16x2", "tf32x3-hostrng", "tf32x3-general", "fp32"):
+            out.append((tag, precision))
+    for tag in ("c1_mu", "c1_cd"):          # BASELINE configs[0] in full: 1 000 x 500, K=7, 10 restarts
+        for precision in ("f16x2", "tf32x3-general"):
+            out.append((tag, precision))
+    return out
+
+
+@pytest.mark.parametrize("tag,precision", _fixture_cases())
 def test_factorize_matches_reference_fixture(eng, precision, tag):
-    """Every restart of the reference's own factorize() run (fixture): same n_iter, spectra within tolerance."""
+    """Every restart of the reference's own factorize() run (fixture): same n_iter, spectra within 1e-4."""
     from oracle import nmf_ref
     g = load_golden(tag)
     rng = "host" if precision.endswith("-hostrng") else "device"
@@ -155,15 +168,60 @@ def test_factorize_matches_reference_fixture(eng, precision, tag):
         ref = g["merged_k%d" % k][it * k:(it + 1) * k]
         e = rel(sp[r], ref)
         errs.append(e)
-        limit = max(TOL_SPECTRA, 5.0 * float(g["fp32dev_k%d" % k][it]))
+        limit = ILL_CONDITIONED.get((tag, int(k), int(it)), TOL_SPECTRA)
         assert e < limit, (tag, precision, k, it, e, limit)
         Wo, Ho, n_o = nmf_ref.nmf(g["X"], int(k), int(seed), solver=g["solver"])
         assert n_o == int(n_iter[r]), (tag, precision, k, it, n_o, int(n_iter[r]))
         # reported final error = ||X - W H||_F of the returned factors
         e_true = nmf_ref.frobenius_error(g["X"], us[r].astype(np.float64), sp[r].astype(np.float64))
         assert abs(err[r] - e_true) / e_true < 1e-5
-    errs = np.array(errs)
-    assert np.median(errs) < 1e-5 and (errs < TOL_SPECTRA).mean() >= 0.9, errs
+    assert np.median(errs) < 1e-5, errs
+
+
+# ------------------------------------------------------------------------------------ BASELINE configurations, sampled
+def _big_samples():
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "big_samples.npz"))
+    out = {}
+    for key in z.files:
+        if key.startswith("H_"):
+            tag = key[2:]
+            out[tag] = (z[key], int(z["it_" + tag]), z["meta_" + tag])
+    return out
+
+
+@pytest.mark.parametrize("case", ["c2", "c3", "k20", "k30"])
+def test_factorize_baseline_configs_sampled(eng, case):
+    """BASELINE.json configs[1] (20k x 2k, K=10), configs[2] (50k x 2k, K=5..13) and the K > 16 kernel path
+    (configs[3]/[4]-shaped: K=20 on 4k x 2k, K=30 on 2k x 1k): restarts sampled from the configuration's own job table,
+    solved in ONE mixed batch together with their neighbours in the table, against the reference's own call
+    (sklearn non_negative_factorization float64 as cnmf.py:672 issues it; outputs stored by oracle/make_golden_big.py):
+    identical n_iter, spectra within 1e-4."""
+    from oracle.make_golden_big import CASES, case_inputs
+    X, table = case_inputs(case)
+    lookup = {(k, it): seed for k, it, seed in table}
+    samples = {t: v for t, v in _big_samples().items() if t.startswith(case + "_")}
+    assert samples
+    ds = eng.dataset(X)
+    assert ds.f16                                     # the default path: exact counts -> 2 kind::f16 passes
+    for solver in ("mu", "cd"):
+        want = [(t, v) for t, v in samples.items() if t.endswith("_" + solver)]
+        if not want:
+            continue
+        jobs = [(int(v[2][2]), int(v[2][3])) for _, v in want]
+        # neighbours from the same job table: other K's / seeds share the batch (mixed-K packing, compaction)
+        extra = [(k, it) for (k, it, _) in table[1::max(1, len(table) // 6)] if (k, it) not in jobs][:5]
+        batch = jobs + extra
+        kw = dict(solver=solver, tol=1e-4, max_iter=1000, beta_loss=2.0 if solver == "mu" else "frobenius")
+        sp, _, n_iter, _ = ds.factorize([k for k, _ in batch], [lookup[j] for j in batch], kw)
+        for i, (t, (H, it_ref, meta)) in enumerate(want):
+            assert meta[0] == X.shape[0] and meta[1] == X.shape[1] and meta[4] == lookup[jobs[i]]
+            e = rel(sp[i], H)
+            assert int(n_iter[i]) == it_ref, (t, int(n_iter[i]), it_ref)
+            assert e < TOL_SPECTRA, (t, e)
+        # the same restarts alone: a restart's result does not depend on the batch it ran in
+        sp1, _, n1, _ = ds.factorize([k for k, _ in jobs[:1]], [lookup[jobs[0]]], kw)
+        assert int(n1[0]) == int(n_iter[0])
+        assert rel(sp1[0], sp[0].astype(np.float64)) < 1e-6, rel(sp1[0], sp[0].astype(np.float64))
 
 
 def test_factorize_batching_invariance(eng):
@@ -226,8 +284,7 @@ def test_factorize_kl_matches_reference_fixture(eng, precision):
         ref = g["merged_k%d" % k][it * k:(it + 1) * k]
         e = rel(sp[r], ref)
         errs.append(e)
-        limit = max(TOL_SPECTRA, 5.0 * float(g["fp32dev_k%d" % k][it]))
-        assert e < limit, (precision, k, it, e, limit)
+        assert e < TOL_SPECTRA, (precision, k, it, e)
         Wo, Ho, n_o = nmf_ref.nmf(g["X"], int(k), int(seed), solver="mu", beta=1)
         assert n_o == int(n_iter[r]), (precision, k, it, n_o, int(n_iter[r]))
         e_true = nmf_ref.frobenius_error(g["X"], us[r].astype(np.float64), sp[r].astype(np.float64))
@@ -378,7 +435,7 @@ def test_consensus_kernels_larger_random(eng):
 
 
 # ------------------------------------------------------------------------------------ end to end through the facade
-@pytest.mark.parametrize("tag", ["sim_mu", "sim_cd", "sim_kl"])
+@pytest.mark.parametrize("tag", ["sim_mu", "sim_cd", "sim_kl", "c1_mu", "c1_cd"])
 def test_pipeline_matches_reference_outputs(tmp_path, tag):
     """prepare -> factorize -> combine -> consensus through cnmf_b200.cNMF on the fixture's counts; every
     file the reference wrote is reproduced within tolerance (the reference test's own criterion is a sum of
@@ -416,7 +473,9 @@ def test_pipeline_matches_reference_outputs(tmp_path, tag):
                 got = load_df_from_npz(obj.paths[key] % (k, dts)).values
                 ref = g["%s_k%d" % (name, k)]
                 e = rel(got, ref)
-                assert e < 2e-4, (tag, k, key, e)
+                # the K=4 consensus of sim_mu contains the ill-conditioned restart named above (1 of its 8)
+                limit = 3e-4 if (tag, k) == ("sim_mu", 4) else TOL_SPECTRA
+                assert e < limit, (tag, k, key, e)
                 assert os.path.exists(obj.paths[key + "__txt"] % (k, dts))
 
 
@@ -441,10 +500,10 @@ def _prepared(tmp_path, g, name="run", n_iter=None):
 
 def test_worker_split_and_resume_give_identical_files(tmp_path):
     """factorize(worker_i, total_workers) over two workers, and a resumed run with skip_completed_runs, write
-    the files a single worker writes (cnmf.py:692-745, 729-733): same (k, iter) -> same seed -> same spectra.
-    Compared at 1e-3 rel-L2, not bitwise: the split-K partition of the GEMMs follows the number of live rows, so a
-    restart's last bits can move with the batch it ran in (a given batch is deterministic run to run); a wrong
-    seed or a misplaced file would differ at O(1)."""
+    the files a single worker writes (cnmf.py:692-745, 729-733): same (k, iter) -> same seed -> same spectra,
+    whatever batch the restart was solved in (the split-K partition is a function of the matrix shape only, the
+    operand pieces a function of the factor values only).  Held to 1e-6 rel-L2 rather than bitwise: the fp64
+    reduction order of the K x K Gram partials follows the launch geometry, which can move an fp32 rounding."""
     from cnmf_b200 import load_df_from_npz
     g = load_golden("sim_mu")
     a = _prepared(tmp_path / "a", g, n_iter=4)
@@ -465,7 +524,7 @@ def test_worker_split_and_resume_give_identical_files(tmp_path):
                 got = load_df_from_npz(other.paths["iter_spectra"] % (k, it))
                 assert got.shape == ref.shape and list(got.index) == list(range(1, k + 1))
                 rel = np.linalg.norm(got.values - ref.values) / np.linalg.norm(ref.values)
-                assert rel < 1e-3, (k, it, rel)
+                assert rel < 1e-6, (k, it, rel)
 
 
 def test_consensus_errors_and_density_cache(tmp_path):
@@ -577,3 +636,110 @@ def test_prepare_on_device_matches_reference_outputs(tmp_path, tag):
     ref = g["merged_k%d" % k]
     errs = [rel(merged[i * k:(i + 1) * k], ref[i * k:(i + 1) * k]) for i in range(ref.shape[0] // k)]
     assert np.median(errs) < 1e-5, errs
+
+
+# ------------------------------------------------------------------------------------ round-2 additions
+def test_density_filter_decision_near_tight_threshold(eng):
+    """BASELINE configs[3] runs consensus at density_threshold = 0.01: replicate spectra whose local densities
+    straddle the threshold (every cluster holds replicates with relative noise 1e-3 ... 3e-2, so the filter cuts
+    through each of them: ~2/3 kept, nearest margin 8e-4 relative).  The keep/drop decision of every
+    row must equal the oracle's (sklearn euclidean_distances + argpartition, float64); this is the regime the
+    direct-difference distance kernel exists for (a Gram-form fp32 distance has ~3e-4 absolute error here)."""
+    from cnmf_b200 import consensus as cs
+    from oracle import reference_path
+    rng = np.random.RandomState(11)
+    K, reps, G = 20, 60, 2000
+    cen = rng.gamma(0.3, 1.0, size=(K, G)) + 1e-3
+    spread = np.geomspace(1e-3, 3e-2, reps)            # per-replicate noise: local densities from 0.002 to 0.03
+    pts = np.vstack([cen[c] * (1.0 + spread[:, None] * rng.randn(reps, G)).clip(0.0) for c in range(K)])
+    pts = pts[rng.permutation(len(pts))]
+    dref, keep_ref, labels_ref, med_ref = reference_path.consensus_cluster(pts, K, density_threshold=0.01)
+    assert 0.5 < keep_ref.mean() < 0.8                 # the threshold cuts through every cluster
+    S = cs.SpectraMatrix(eng, pts).l2_normalize()
+    dens, _ = S.local_density(int(0.3 * len(pts) / K))
+    margin = np.abs(dref - 0.01) / 0.01
+    assert rel(dens, dref) < 2e-5
+    keep = dens < 0.01
+    assert np.array_equal(keep, keep_ref), (int((keep != keep_ref).sum()), float(margin.min()))
+    S2 = S.take_rows(np.where(keep)[0])
+    k_kept = len(set(labels_ref))
+    labels, labels_t, _, _ = cs.kmeans(S2, K)
+    assert np.array_equal(labels, labels_ref)
+    med = cs.cluster_medians(S2, labels_t, K)
+    assert rel(med, med_ref) < 1e-6 and k_kept == K
+
+
+def test_sparse_norm_counts_round_trip(tmp_path):
+    """The reference keeps X sparse (CSR) unless --densify (cnmf.py:399-405, 534-538).  prepare(densify=False)
+    stores CSR norm_counts / tpm, factorize and consensus consume them, and every output equals the dense run."""
+    import scipy.sparse as sp
+    from cnmf_b200 import cNMF, load_df_from_npz
+    from cnmf_b200 import io as cio
+    g = load_golden("sim_cd")
+    a = _prepared(tmp_path / "dense", g, n_iter=4)
+    import pandas as pd
+    from cnmf_b200 import save_df_to_npz
+    counts = g["counts"].astype(np.float64)
+    df = pd.DataFrame(counts, index=["c%d" % i for i in range(counts.shape[0])],
+                      columns=["g%d" % i for i in range(counts.shape[1])])
+    (tmp_path / "sparse").mkdir()
+    fn = str(tmp_path / "sparse" / "counts.df.npz")
+    save_df_to_npz(df, fn)
+    b = cNMF(output_dir=str(tmp_path / "sparse"), name="run")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b.prepare(fn, components=list(g["ks"]), n_iter=4, seed=int(g["seed"]), densify=False,
+                  beta_loss=g["beta_loss_arg"], num_highvar_genes=len(g["hvg_idx"]))
+    nb = cio.read_matrix(b.paths["normalized_counts"])
+    assert sp.issparse(nb.X) and sp.issparse(cio.read_matrix(b.paths["tpm"]).X)
+    na = cio.read_matrix(a.paths["normalized_counts"])
+    assert np.array_equal(nb.X.toarray(), na.X)
+    k = int(g["ks"][1])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for obj in (a, b):
+            obj.factorize()
+            obj.combine()
+            obj.consensus(k, density_threshold=2.0, show_clustering=False)
+    for key in ("consensus_spectra", "consensus_usages", "gene_spectra_tpm", "gene_spectra_score"):
+        ra = load_df_from_npz(a.paths[key] % (k, "2_0")).values
+        rb = load_df_from_npz(b.paths[key] % (k, "2_0")).values
+        assert rel(rb, ra) < 1e-6, key
+
+
+def test_clustergram_order_matches_reference_rule(tmp_path):
+    """cnmf.py:986-1010: clusters in label order, average-linkage leaf order inside a cluster, on the distances of
+    the density-filtered spectra.  Oracle: the same scipy calls on sklearn's float64 distances."""
+    from scipy.cluster.hierarchy import leaves_list, linkage
+    from scipy.spatial.distance import squareform
+    from sklearn.metrics.pairwise import euclidean_distances
+    from cnmf_b200 import load_df_from_npz
+    from oracle import consensus_ref as cr
+    g = load_golden("c1_mu")
+    obj = _prepared(tmp_path, g)
+    k = int(g["ks"][0])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        obj.factorize()
+        obj.combine()
+        obj.consensus(k, density_threshold=float(g["dt"]), show_clustering=True, close_clustergram_fig=True)
+    order = list(obj.last_clustergram_order)
+    merged = load_df_from_npz(obj.paths["merged_spectra"] % k).values
+    l2 = cr.l2_normalize_rows(merged)
+    D = euclidean_distances(l2)
+    n_nb = int(0.3 * merged.shape[0] / k)
+    dens = cr.local_density(D, n_nb)
+    keep = dens < float(g["dt"])
+    labels, _, _ = cr.kmeans(l2[keep], k)
+    Df = D[keep][:, keep]
+    ref = []
+    for cl in sorted(set(labels)):
+        f = labels == cl
+        if f.sum() > 1:
+            d = squareform(Df[f][:, f], checks=False)
+            d[d < 0] = 0
+            ref += list(np.where(f)[0][leaves_list(linkage(d, "average"))])
+        else:
+            ref += list(np.where(f)[0])
+    assert sorted(order) == list(range(int(keep.sum())))
+    assert order == ref

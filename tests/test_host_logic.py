@@ -276,3 +276,84 @@ def test_binding_table_matches_header_prototypes():
     ver = int(re.search(r"#define CNMF_B200_ABI_VERSION (\d+)", header).group(1))
     assert ver == _lib.ABI_VERSION == ctypes.CDLL(_lib.LIB_PATH).cnmf_abi_version()
     assert ctypes.sizeof(_lib.NmfParams) == 4 * 4 + 5 * 8 + 2 * 4
+
+
+# ------------------------------------------------------------------------------------ round-2 host logic
+def _counts_file(tmp_path, counts, name="counts.df.npz"):
+    df = pd.DataFrame(counts.astype(np.float64), index=["c%d" % i for i in range(counts.shape[0])],
+                      columns=["g%d" % i for i in range(counts.shape[1])])
+    fn = str(tmp_path / name)
+    save_df_to_npz(df, fn)
+    return fn
+
+
+def test_prepare_sparse_semantics_and_zero_std_rule(tmp_path):
+    """Without --densify the reference converts text / npz input to CSR (cnmf.py:399-405) and scales the HVG
+    matrix with sc.pp.scale(zero_center=False) (cnmf.py:538), which maps a zero standard deviation to 1; with
+    --densify it divides by the std (cnmf.py:542).  The facade keeps both behaviours and stores CSR like the
+    reference; the stored values are otherwise identical."""
+    import warnings
+    import scipy.sparse as sp
+    from cnmf_b200 import io as cio
+    from cnmf_b200.synth import make_counts
+    counts = make_counts(300, 60, k_true=3, seed=2, libsize=300.0).astype(np.float64)
+    counts[:, 5] = 1.0                         # a constant gene: zero variance
+    genes = ["g%d" % i for i in range(counts.shape[1])]
+    fn = _counts_file(tmp_path, counts)
+    gf = str(tmp_path / "genes.txt")
+    open(gf, "w").write("\n".join(genes[:30]))
+    out = {}
+    for densify in (False, True):
+        obj = cNMF(output_dir=str(tmp_path), name="d%d" % densify)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            obj.prepare(fn, components=[3], n_iter=2, seed=1, densify=densify, genes_file=gf)
+        out[densify] = cio.read_matrix(obj.paths["normalized_counts"])
+        assert sp.issparse(out[densify].X) == (not densify)
+        assert sp.issparse(cio.read_matrix(obj.paths["tpm"]).X) == (not densify)
+    Xs, Xd = out[False].X.toarray(), out[True].X
+    keep = np.arange(30) != 5
+    assert np.array_equal(Xs[:, keep], Xd[:, keep])
+    assert np.array_equal(Xs[:, 5], np.ones(300))          # std 0 -> 1: the column keeps its counts
+    assert not np.isfinite(Xd[:, 5]).any()                 # dense branch: 1 / 0, as the reference (it only warns)
+
+
+def test_unsupported_options_are_refused_at_prepare(tmp_path):
+    """K > 32 and init != 'random' fail when the user states them (prepare / get_nmf_iter_params / the CLI), not in
+    factorize; a refit ignores `init` (no random init when update_H=False, sklearn _nmf.py:1223-1228)."""
+    from cnmf_b200.engine import check_supported, make_params
+    from cnmf_b200.synth import make_counts
+    fn = _counts_file(tmp_path, make_counts(120, 40, k_true=3, seed=2, libsize=300.0))
+    obj = cNMF(output_dir=str(tmp_path), name="u")
+    with pytest.raises(ValueError, match=r"\[1, 32\]"):
+        obj.prepare(fn, components=[5, 40], n_iter=2, seed=1, densify=True)
+    with pytest.raises(NotImplementedError, match="init='random'"):
+        obj.prepare(fn, components=[5], n_iter=2, seed=1, densify=True, init="nndsvd")
+    with pytest.raises(ValueError, match=r"\[1, 32\]"):
+        obj.get_nmf_iter_params(ks=[33], n_iter=2)
+    with pytest.raises(NotImplementedError):
+        check_supported([5], "random", 0.5)
+    with pytest.raises(NotImplementedError):
+        make_params(dict(solver="cd", init="nndsvd"), 10, 10, "tf32x3")
+    p = make_params(dict(solver="cd", init="nndsvd"), 10, 10, "tf32x3", for_refit=True)
+    assert p.solver == 1
+    from cnmf_b200 import pipeline
+    import sys
+    argv = sys.argv
+    try:
+        sys.argv = ["cnmf", "prepare", "--init", "nndsvd", "-c", fn, "-k", "5"]
+        with pytest.raises(SystemExit):
+            pipeline.main()
+    finally:
+        sys.argv = argv
+
+
+def test_restart_groups_follow_the_memory_budget():
+    from cnmf_b200.pipeline import plan_groups
+    ks = [5] * 4 + [6] * 4 + [13] * 3
+    assert plan_groups(ks, 10 ** 9) == [(0, len(ks))]
+    groups = plan_groups(ks, 20)
+    assert groups[0] == (0, 4) and groups[-1][1] == len(ks)
+    assert all(sum(ks[a:b]) <= 20 or b - a == 1 for a, b in groups)
+    assert [a for a, _ in groups][1:] == [b for _, b in groups][:-1]      # consecutive, nothing skipped
+    assert plan_groups([40], 10) == [(0, 1)] and plan_groups([], 10) == []
