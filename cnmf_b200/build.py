@@ -66,7 +66,7 @@ def build(force=False, verbose=True):
                     print("compiled", os.path.relpath(src, ROOT))
     if jobs or not os.path.exists(LIB_PATH):
         cmd = [NVCC, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                          "-Xcompiler", "-fPIC", "-lpthread"]
+                                                          "-Xcompiler", "-fPIC", "-lpthread", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed\n" + r.stdout + r.stderr)

@@ -18,6 +18,11 @@ import numpy as np
 from ._lib import check, ptr
 
 
+# work counters of the last consensus_numerics call (bench.py's consensus roofline): Lloyd iterations summed over the
+# n_init runs, (rows, cols, n_iter) of every refit
+STATS = {}
+
+
 def _torch():
     import torch
     if not torch.cuda.is_available():
@@ -40,6 +45,16 @@ class SpectraMatrix:
         self.t = torch.zeros((self.R, self.ld), dtype=torch.float32, device="cuda:%d" % engine.device)
         if array is not None:
             self.t[:, :self.G].copy_(torch.from_numpy(array))     # H2D memcpy
+
+    @classmethod
+    def from_device_rows(cls, engine, src_ptr, ld_src, rows, n_cols):
+        """Rows `rows` of a device-resident slab (e.g. the all-gathered spectra of every restart) as a new matrix:
+        a device-side row gather, no trip through the host."""
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        out = cls(engine, shape=(len(rows), n_cols))
+        check(engine.lib.cnmf_gather_rows(engine._h, ctypes.c_void_p(int(src_ptr)), int(ld_src), ptr(rows), len(rows),
+                                          int(n_cols), out.p, out.ld, None))
+        return out
 
     @property
     def p(self):
@@ -187,6 +202,7 @@ def kmeans(S, k, n_init=10, random_state=1, max_iter=300, tol=1e-4):
                 break
             if shift_tot <= tol_abs:
                 break
+        STATS["lloyd_iters"] = STATS.get("lloyd_iters", 0) + n_it + 1
         centers = C64[cur].cpu().numpy()
         c32 = np.ascontiguousarray(centers, dtype=np.float32)
         # final E step (labels consistent with the final centres) + inertia
@@ -242,3 +258,72 @@ def ols_zscore(usages, tpm_ds):
     UtU = U.T @ U
     beta, *_ = np.linalg.lstsq(UtU, UtZ, rcond=None)
     return beta
+
+
+# ------------------------------------------------------------------------------ the consensus step as one function
+def consensus_numerics(eng, merged, k, norm_ds, kw, density_threshold=0.5, n_neighbors=None,
+                       local_neighborhood_size=0.30, stats_only=False, local_density=None, want_dist=False,
+                       tpm_ds=None, hvg_idx=None, tpm_std_hvg=None, refit_usage=True, tpm_sparse=False):
+    """Every numeric step of cNMF.consensus (cnmf.py:879-975) for one K, on the GPU, without files or labels:
+    the facade (pipeline.cNMF.consensus) wraps it in the reference's DataFrames / ledger, bench.py times it.
+
+    merged        R x G stacked spectra: numpy array or a SpectraMatrix already on the device (not yet normalised)
+    norm_ds       resident normalised counts (refit a, cnmf.py:919);  tpm_ds: resident TPM (refits b, c and the OLS)
+    local_density optional cached densities (cnmf.py:887-888); else computed (and returned)
+    Returns a dict: local_density, keep (indices), labels (0-based), median_spectra (K x G, rows sum to 1), rf_usages,
+    refit_err and, unless stats_only: order (program permutation, cnmf.py:939-946), norm_usages, spectra_tpm,
+    usage_coef, final rf_usages; with stats_only: silhouette, prediction_error (cnmf.py:922-936)."""
+    import pandas as pd
+    S = merged if isinstance(merged, SpectraMatrix) else SpectraMatrix(eng, merged)
+    S.l2_normalize()                                                            # cnmf.py:882
+    R = S.R
+    if n_neighbors is None:
+        n_neighbors = int(local_neighborhood_size * R / k)                      # cnmf.py:879
+    out = {"S_all": S, "topics_dist": None, "keep": np.arange(R)}
+    if not stats_only:
+        if local_density is None:
+            local_density, out["topics_dist"] = S.local_density(n_neighbors, return_dist=want_dist)   # cnmf.py:891-896
+        out["local_density"] = np.asarray(local_density, dtype=np.float64)
+        keep = np.where(out["local_density"] < density_threshold)[0]             # cnmf.py:903
+        if len(keep) == 0:
+            raise RuntimeError("Zero components remain after density filtering. Consider increasing density threshold")
+        if len(keep) < R:
+            S = S.take_rows(keep)
+        out["keep"] = keep
+    out["S"] = S
+    labels0, labels_t, _, _ = kmeans(S, k)                                        # cnmf.py:908-910
+    out["labels"] = labels0
+    med = cluster_medians(S, labels_t, k)                                         # cnmf.py:913-916
+    out["median_spectra"] = med
+    rf, it_a, err = norm_ds.refit(med, kw)                                        # cnmf.py:919
+    STATS.setdefault("refits", []).append((norm_ds.shape[0], norm_ds.shape[1], it_a))
+    rf = rf.astype(np.float64)
+    out["rf_usages"], out["refit_err"] = rf, err
+    if stats_only:                                                                # cnmf.py:922-936
+        out["silhouette"] = silhouette(S, labels0, labels_t, k)
+        out["prediction_error"] = err ** 2
+        return out
+    norm_usages = rf / rf.sum(axis=1, keepdims=True)                              # cnmf.py:939-946
+    order = pd.Series(norm_usages.sum(axis=0)).sort_values(ascending=False).index.values
+    rf, norm_usages, med = rf[:, order], norm_usages[:, order], med[order]
+    out.update(order=order, rf_usages=rf, norm_usages=norm_usages, median_spectra=med)
+    if tpm_ds is None:
+        return out
+    Ht, it_b, _ = tpm_ds.refit(np.ascontiguousarray(norm_usages.T), kw, transposed=True)   # cnmf.py:952 (refit_spectra)
+    STATS.setdefault("refits", []).append((tpm_ds.shape[1], tpm_ds.shape[0], it_b))
+    spectra_tpm = Ht.T.astype(np.float64)
+    out["spectra_tpm"] = spectra_tpm
+    out["usage_coef"] = ols_zscore(rf, tpm_ds)                                     # cnmf.py:958
+    if refit_usage and hvg_idx is not None:                                        # cnmf.py:961-975
+        _, var = tpm_ds.col_stats()
+        n = tpm_ds.shape[0]
+        std1 = np.sqrt(var[hvg_idx] * n / (n - 1.0))                              # std(ddof=1)
+        if tpm_sparse:
+            std1[std1 == 0] = 1.0                                                 # sc.pp.scale, cnmf.py:967
+        norm_tpm_ds = tpm_ds.from_columns(hvg_idx, 1.0 / std1)
+        sp_rf = spectra_tpm[:, hvg_idx] / np.asarray(tpm_std_hvg, dtype=np.float64)[None, :]
+        rf2, it_c, _ = norm_tpm_ds.refit(sp_rf, kw)
+        STATS.setdefault("refits", []).append((norm_tpm_ds.shape[0], norm_tpm_ds.shape[1], it_c))
+        norm_tpm_ds.close()
+        out["rf_usages"] = rf2.astype(np.float64)
+    return out

@@ -462,7 +462,7 @@ void parallel_for(int n, const std::function<void(int)>& fn) {
 // shared tail of cnmf_factorize / cnmf_factorize_init: factors already in fb.Fr / fb.Fc (full fp32)
 int run_and_download(cnmf_dataset_s* d, const std::vector<int>& ks, int SK, FactorBuffers& fb,
                      const cnmf_nmf_params& p, float* spectra_host, float* usages_host, int32_t* n_iter_host,
-                     double* err_host, cudaStream_t s) {
+                     double* err_host, cudaStream_t s, float* spectra_dev = nullptr, long long ld_dev = 0) {
   cnmf_handle_s* h = d->h;
   const bool tf32 = p.precision == CNMF_PRECISION_TF32X3;
   DataView v = make_view(d, false);
@@ -481,8 +481,12 @@ int run_and_download(cnmf_dataset_s* d, const std::vector<int>& ks, int SK, Fact
   CNMF_TRY(solve_batched(h, v, io, p, s));
   h->t_solve_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_solve).count();
   auto t_d2h = std::chrono::steady_clock::now();
-  CNMF_CUDA_CHECK(cudaMemcpy2DAsync(spectra_host, (size_t)d->n_cols * 4, fb.Fc, (size_t)d->ld_c * 4,
-                                    (size_t)d->n_cols * 4, SK, cudaMemcpyDeviceToHost, s));
+  if (spectra_dev)      // result stays in HBM (multi-GPU path: the slab goes straight into the NCCL all-gather)
+    CNMF_CUDA_CHECK(cudaMemcpy2DAsync(spectra_dev, (size_t)ld_dev * 4, fb.Fc, (size_t)d->ld_c * 4,
+                                      (size_t)d->n_cols * 4, SK, cudaMemcpyDeviceToDevice, s));
+  if (spectra_host)
+    CNMF_CUDA_CHECK(cudaMemcpy2DAsync(spectra_host, (size_t)d->n_cols * 4, fb.Fc, (size_t)d->ld_c * 4,
+                                      (size_t)d->n_cols * 4, SK, cudaMemcpyDeviceToHost, s));
   if (usages_host)
     CNMF_CUDA_CHECK(cudaMemcpy2DAsync(usages_host, (size_t)d->n_rows * 4, fb.Fr, (size_t)d->ld_r * 4,
                                       (size_t)d->n_rows * 4, SK, cudaMemcpyDeviceToHost, s));
@@ -505,11 +509,12 @@ int check_params(cnmf_dataset_s* d, const cnmf_nmf_params* p) {
 
 }  // namespace
 
-int cnmf_factorize(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, const uint32_t* seeds,
-                   const cnmf_nmf_params* p, float* spectra_host, float* usages_host, int32_t* n_iter_host,
-                   double* err_host, void* stream) {
+static int factorize_impl(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, const uint32_t* seeds,
+                          const cnmf_nmf_params* p, float* spectra_host, float* usages_host, int32_t* n_iter_host,
+                          double* err_host, void* stream, float* spectra_dev, long long ld_dev) {
   CNMF_TRY(check_params(d, p));
-  CNMF_REQUIRE(n_restarts > 0 && ks_in && seeds && spectra_host, "factorize: bad arguments");
+  CNMF_REQUIRE(n_restarts > 0 && ks_in && seeds && (spectra_host || spectra_dev), "factorize: bad arguments");
+  CNMF_REQUIRE(!spectra_dev || ld_dev >= d->n_cols, "factorize: device output row stride too small");
   cnmf_handle_s* h = d->h;
   cudaStream_t s = as_stream(stream);
   CNMF_CUDA_CHECK(cudaSetDevice(h->device));
@@ -538,7 +543,7 @@ int cnmf_factorize(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, const
                              fb.Fc, d->ld_c, h, s));
     CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
     h->t_rng_ms = ms_since(t_rng);
-    return run_and_download(d, ks, SK, fb, *p, spectra_host, usages_host, n_iter_host, err_host, s);
+    return run_and_download(d, ks, SK, fb, *p, spectra_host, usages_host, n_iter_host, err_host, s, spectra_dev, ld_dev);
   }
   // host RNG (bit-exact numpy legacy stream) in groups through a pinned staging buffer
   const double mean = d->sum / ((double)d->n_rows * (double)d->n_cols);
@@ -577,7 +582,21 @@ int cnmf_factorize(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, const
     h->t_h2d_ms += ms_since(t_h2d);
     r0 = r1;
   }
-  return run_and_download(d, ks, SK, fb, *p, spectra_host, usages_host, n_iter_host, err_host, s);
+  return run_and_download(d, ks, SK, fb, *p, spectra_host, usages_host, n_iter_host, err_host, s, spectra_dev, ld_dev);
+}
+
+int cnmf_factorize(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, const uint32_t* seeds,
+                   const cnmf_nmf_params* p, float* spectra_host, float* usages_host, int32_t* n_iter_host,
+                   double* err_host, void* stream) {
+  CNMF_REQUIRE(spectra_host, "factorize: spectra_host is NULL");
+  return factorize_impl(d, n_restarts, ks_in, seeds, p, spectra_host, usages_host, n_iter_host, err_host, stream, nullptr, 0);
+}
+
+int cnmf_factorize_seeds_dev(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, const uint32_t* seeds,
+                             const cnmf_nmf_params* p, float* spectra_dev, long long ld_out, int32_t* n_iter_host,
+                             double* err_host, void* stream) {
+  CNMF_REQUIRE(spectra_dev, "factorize_seeds_dev: spectra_dev is NULL");
+  return factorize_impl(d, n_restarts, ks_in, seeds, p, nullptr, nullptr, n_iter_host, err_host, stream, spectra_dev, ld_out);
 }
 
 int cnmf_last_timing(cnmf_handle_t h, double* rng_ms, double* h2d_ms, double* solve_ms, double* d2h_ms) {

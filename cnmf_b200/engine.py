@@ -213,6 +213,20 @@ class Dataset:
         check(self.lib.cnmf_random_init_dev(self._d, len(ks), ptr(ks), ptr(seeds), ctypes.c_void_p(Wt_ptr),
                                             ctypes.c_void_p(H_ptr), None))
 
+    def factorize_seeds_dev(self, ks, seeds, out_ptr, ld_out, nmf_kwargs):
+        """cnmf_factorize (same seeds, same device RNG) with the spectra left on the device: out_ptr is a
+        (sum ks) x ld_out fp32 device buffer.  Returns (n_iter, err)."""
+        ks = np.ascontiguousarray(ks, dtype=np.int32)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        R = len(ks)
+        p = self.params(nmf_kwargs)
+        self._check_loss(p)
+        n_iter = np.zeros(R, np.int32)
+        err = np.zeros(R, np.float64)
+        check(self.lib.cnmf_factorize_seeds_dev(self._d, R, ptr(ks), ptr(seeds), ctypes.byref(p), ctypes.c_void_p(out_ptr),
+                                                int(ld_out), ptr(n_iter), ptr(err), None))
+        return n_iter, err
+
     def factorize_dev(self, ks, Wt0_ptr, H0_ptr, out_ptr, nmf_kwargs):
         """Device-resident factorize: raw device pointers (e.g. torch.Tensor.data_ptr()) of the packed,
         padded initial factors and of the output spectra slab.  Returns (n_iter, err)."""

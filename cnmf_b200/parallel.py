@@ -82,10 +82,118 @@ def allgather_spectra(local_spectra, local_jobs, ks_all, n_genes, device=None):
     return out
 
 
+class SpectraComm:
+    """The library's own NCCL communicator (C ABI: cnmf_comm_unique_id / cnmf_comm_create), bootstrapped by shipping
+    the 128-byte id through torch.distributed's process group -- the only thing torch.distributed is used for on
+    the NCCL path.  A host that already owns an ncclComm_t passes it to cnmf_allgather_spectra directly."""
+
+    def __init__(self, engine):
+        import ctypes
+        import torch.distributed as dist
+        from ._lib import check
+        self.engine = engine
+        self.lib = engine.lib
+        rank, world, _ = dist_info()
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            check(self.lib.cnmf_comm_unique_id(buf))
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0)
+        self._comm = ctypes.c_void_p()
+        check(self.lib.cnmf_comm_create(engine._h, ctypes.create_string_buffer(box[0], 128), rank, world,
+                                        ctypes.byref(self._comm)))
+
+    def allgather(self, local_t, merged_t):
+        """merged_t (world x rows x ld) <- every rank's local_t (rows x ld); device tensors, asynchronous."""
+        import ctypes
+        from ._lib import check
+        rows, ld = int(local_t.shape[0]), int(local_t.shape[1])
+        check(self.lib.cnmf_allgather_spectra(self._comm, ctypes.c_void_p(local_t.data_ptr()), rows, ld,
+                                              ctypes.c_void_p(merged_t.data_ptr()), None))
+
+    def close(self):
+        if self._comm:
+            self.lib.cnmf_comm_destroy(self._comm)
+            import ctypes
+            self._comm = ctypes.c_void_p()
+
+
+class ShardedSpectra:
+    """Result of factorize_sharded: every restart's spectra in ONE device slab (world x max_rows x ld), identical on
+    all ranks after the all-gather, plus the map job -> slab row."""
+
+    def __init__(self, gathered, ks_all, n_genes, world):
+        self.t = gathered                       # torch tensor (world, max_rows, ld) on the device
+        self.ks_all = list(ks_all)
+        self.n_genes = int(n_genes)
+        self.world = int(world)
+        self.max_rows = int(gathered.shape[1])
+        self.ld = int(gathered.shape[2])
+        self.first_row = [0] * len(ks_all)
+        for r in range(world):
+            o = 0
+            for j in shard_jobs(len(ks_all), r, world):
+                self.first_row[j] = r * self.max_rows + o
+                o += ks_all[j]
+
+    def rows_of_jobs(self, jobs):
+        """Slab rows (flattened world*max_rows index) of the given jobs, job by job, component by component."""
+        out = []
+        for j in jobs:
+            out.extend(range(self.first_row[j], self.first_row[j] + self.ks_all[j]))
+        return np.asarray(out, dtype=np.int32)
+
+    def matrix(self, engine, jobs):
+        """The stacked spectra of `jobs` (what `combine` would have merged, cnmf.py:748-773) as a device matrix."""
+        from .consensus import SpectraMatrix
+        return SpectraMatrix.from_device_rows(engine, self.t.data_ptr(), self.ld, self.rows_of_jobs(jobs), self.n_genes)
+
+    def host(self):
+        """All spectra on the host, list indexed by job."""
+        flat = self.t.reshape(self.world * self.max_rows, self.ld)[:, :self.n_genes].cpu().numpy()
+        return [flat[self.first_row[j]:self.first_row[j] + k].copy() for j, k in enumerate(self.ks_all)]
+
+
+def factorize_sharded(ds, ks_all, seeds_all, nmf_kwargs, comm=None):
+    """The multi-GPU factorize: this rank's jobs (idx % world == rank, cnmf.py:52-53) in one batched solve whose
+    spectra stay in HBM, then ONE NCCL all-gather of the per-rank slabs (cnmf_allgather_spectra).  No host staging.
+    Returns (ShardedSpectra, n_iter of the local jobs, local job indices)."""
+    import torch
+    rank, world, _ = dist_info()
+    n_jobs = len(ks_all)
+    jobs = shard_jobs(n_jobs, rank, world)
+    rows_per_rank = [sum(ks_all[j] for j in shard_jobs(n_jobs, r, world)) for r in range(world)]
+    max_rows = max(max(rows_per_rank), 1)
+    _, ld = ds.ld()
+    dev = torch.device("cuda:%d" % ds.engine.device)
+    gathered = torch.zeros((world, max_rows, ld), dtype=torch.float32, device=dev)
+    slab = gathered[rank] if world == 1 else torch.zeros((max_rows, ld), dtype=torch.float32, device=dev)
+    n_iter = np.zeros(0, np.int32)
+    if jobs:
+        n_iter, _ = ds.factorize_seeds_dev([ks_all[j] for j in jobs], [seeds_all[j] for j in jobs], slab.data_ptr(), ld,
+                                           nmf_kwargs)
+    if world > 1:
+        own = comm is None
+        if own:
+            comm = SpectraComm(ds.engine)
+        comm.allgather(slab, gathered)
+        torch.cuda.synchronize(dev)
+        if own:
+            comm.close()
+    return ShardedSpectra(gathered, ks_all, ds.shape[1], world), n_iter, jobs
+
+
+def consensus_ks_of_rank(ks_sorted, rank, world):
+    """K -> GPU assignment of the consensus sweep (`cnmf consensus` / k_selection_plot loop over K,
+    cnmf.py:1119-1135, 1278-1291): consensus for one K is a chain of small dependent kernels, so the Ks -- not the
+    rows -- are what shards; every rank holds all spectra after the all-gather."""
+    return [k for i, k in enumerate(ks_sorted) if i % world == rank]
+
+
 def factorize_distributed(cnmf_obj, write_files=True):
     """Sharded cNMF.factorize + in-memory combine.  Every rank factorizes its jobs on its own GPU; the
-    spectra are all-gathered; rank 0 writes the per-restart and merged files (so `combine` / `consensus`
-    find exactly what the reference would have written).  Returns {k: merged R x G float64 array}."""
+    spectra slabs are all-gathered on the device; rank 0 writes the per-restart and merged files (so `combine` /
+    `consensus` find exactly what the reference would have written).  Returns {k: merged R x G float64 DataFrame}."""
     import pandas as pd
     import yaml
     from . import io as cio
@@ -97,9 +205,10 @@ def factorize_distributed(cnmf_obj, write_files=True):
     kw = yaml.load(open(cnmf_obj.paths["nmf_run_parameters"]), Loader=yaml.FullLoader)
     ks_all = [int(k) for k in run_params["n_components"]]
     seeds_all = [int(s) for s in run_params["nmf_seed"]]
-    jobs = shard_jobs(len(ks_all), rank, world)
-    spectra, _, _ = cnmf_obj._nmf_batched(norm.X, [ks_all[j] for j in jobs], [seeds_all[j] for j in jobs], kw)
-    full = allgather_spectra([s.astype(np.float32) for s in spectra], jobs, ks_all, norm.shape[1], device=local)
+    ds = cnmf_obj._dataset(norm.X)
+    sharded, _, _ = factorize_sharded(ds, ks_all, seeds_all, kw)
+    cnmf_obj.last_sharded_spectra = sharded          # consensus can take its matrices from the device slab
+    full = sharded.host()
     merged = {}
     for k in sorted(set(ks_all)):
         rows = run_params[run_params.n_components == k].sort_values("iter")

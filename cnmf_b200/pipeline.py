@@ -399,78 +399,46 @@ class cNMF:
 
         dt_str = "2" if skip_density_and_return_after_stats else str(density_threshold)
         dt_repl = dt_str.replace(".", "_")
-        n_neighbors = int(local_neighborhood_size * merged.shape[0] / k)
-
-        S = cs.SpectraMatrix(eng, merged.values).l2_normalize()                    # cnmf.py:882
-        l2_index = merged.index
-        topics_dist = None
-        density_filter = None
-        if not skip_density_and_return_after_stats:
-            cache = self.paths["local_density_cache"] % k
-            if os.path.isfile(cache):                                              # cnmf.py:887-888 (keyed by k only)
-                local_density = load_df_from_npz(cache)
-            else:
-                dens, topics_dist = S.local_density(n_neighbors, return_dist=show_clustering)
-                local_density = pd.DataFrame(dens, columns=["local_density"], index=l2_index)
-                save_df_to_npz(local_density, cache)
-            density_filter = local_density.iloc[:, 0] < density_threshold           # cnmf.py:903
-            keep = np.where(density_filter.values)[0]
-            if len(keep) == 0:
-                raise RuntimeError("Zero components remain after density filtering. Consider increasing density threshold")
-            if len(keep) < S.R:
-                S = S.take_rows(keep)
-            l2_index = l2_index[keep]
-
-        labels0, labels_t, _, _ = cs.kmeans(S, k)                                   # cnmf.py:908-910
-        cluster_labels = pd.Series(labels0 + 1, index=l2_index)
-        med = cs.cluster_medians(S, labels_t, k)                                    # cnmf.py:913-916
-        median_spectra = pd.DataFrame(med, index=np.arange(1, k + 1), columns=merged.columns)
-        median_spectra.index.name = None
-
-        rf, _, err = norm_ds.refit(median_spectra.values, kw)                       # cnmf.py:919
-        rf_usages = pd.DataFrame(rf.astype(np.float64), index=norm_counts.obs_names, columns=median_spectra.index)
-
-        if skip_density_and_return_after_stats:                                     # cnmf.py:922-936
-            silhouette = cs.silhouette(S, labels0, labels_t, k)
-            prediction_error = err ** 2
-            return pd.DataFrame([k, density_threshold, silhouette, prediction_error],
+        stats_only = bool(skip_density_and_return_after_stats)
+        cached = None
+        cache = self.paths["local_density_cache"] % k
+        if not stats_only and os.path.isfile(cache):                                # cnmf.py:887-888 (keyed by k only)
+            local_density = load_df_from_npz(cache)
+            cached = local_density.iloc[:, 0].values
+        tpm = tpm_ds = hv_idx = tpm_std_hvg = None
+        if not stats_only:
+            tpm = cio.read_matrix(self.paths["tpm"])                                # cnmf.py:950-953
+            tpm_stats = load_df_from_npz(self.paths["tpm_stats"])
+            tpm_ds = self._dataset(tpm.X)
+            if refit_usage:
+                hvgs = open(self.paths["nmf_genes_list"]).read().split("\n")
+                hv_idx = tpm.var_names.get_indexer(hvgs)
+                tpm_std_hvg = tpm_stats.loc[hvgs, "__std"].values
+        res = cs.consensus_numerics(eng, merged.values, k, norm_ds, kw, density_threshold=density_threshold,
+                                    local_neighborhood_size=local_neighborhood_size, stats_only=stats_only,
+                                    local_density=cached, want_dist=show_clustering, tpm_ds=tpm_ds, hvg_idx=hv_idx,
+                                    tpm_std_hvg=tpm_std_hvg, refit_usage=refit_usage,
+                                    tpm_sparse=bool(tpm is not None and tpm.is_sparse))
+        if tpm_ds is not None:
+            tpm_ds.close()
+        if stats_only:                                                              # cnmf.py:922-936
+            return pd.DataFrame([k, density_threshold, res["silhouette"], res["prediction_error"]],
                                 index=["k", "local_density_threshold", "silhouette", "prediction_error"],
                                 columns=["stats"])
-
-        norm_usages = rf_usages.div(rf_usages.sum(axis=1), axis=0)                  # cnmf.py:939-946
-        reorder = norm_usages.sum(axis=0).sort_values(ascending=False)
-        rf_usages = rf_usages.loc[:, reorder.index]
-        norm_usages = norm_usages.loc[:, reorder.index]
-        median_spectra = median_spectra.loc[reorder.index, :]
-        rf_usages.columns = np.arange(1, rf_usages.shape[1] + 1)
-        norm_usages.columns = rf_usages.columns
-        median_spectra.index = rf_usages.columns
-
-        tpm = cio.read_matrix(self.paths["tpm"])                                    # cnmf.py:950-953
-        tpm_stats = load_df_from_npz(self.paths["tpm_stats"])
-        tpm_ds = self._dataset(tpm.X)
-        spectra_tpm = self.refit_spectra(tpm_ds, norm_usages.values)
-        spectra_tpm = pd.DataFrame(spectra_tpm, index=rf_usages.columns, columns=tpm.var_names)
+        if cached is None:
+            local_density = pd.DataFrame(res["local_density"], columns=["local_density"], index=merged.index)
+            save_df_to_npz(local_density, cache)
+        density_filter = local_density.iloc[:, 0] < density_threshold               # cnmf.py:903
+        l2_index = merged.index[res["keep"]]
+        cluster_labels = pd.Series(res["labels"] + 1, index=l2_index)
+        programs = np.arange(1, k + 1)                                              # relabelled 1..K in usage order
+        median_spectra = pd.DataFrame(res["median_spectra"], index=programs, columns=merged.columns)
+        rf_usages = pd.DataFrame(res["rf_usages"], index=norm_counts.obs_names, columns=programs)
+        spectra_tpm = pd.DataFrame(res["spectra_tpm"], index=programs, columns=tpm.var_names)
         if normalize_tpm_spectra:
             spectra_tpm = spectra_tpm.div(spectra_tpm.sum(axis=1), axis=0) * 1e6
-
-        usage_coef = cs.ols_zscore(rf_usages.values, tpm_ds)                        # cnmf.py:958
-        usage_coef = pd.DataFrame(usage_coef, index=rf_usages.columns, columns=tpm.var_names)
-
-        if refit_usage:                                                             # cnmf.py:961-975
-            hvgs = open(self.paths["nmf_genes_list"]).read().split("\n")
-            hv_idx = tpm.var_names.get_indexer(hvgs)
-            _, var = tpm_ds.col_stats()
-            n = tpm.shape[0]
-            std1 = np.sqrt(var[hv_idx] * n / (n - 1.0))                             # std(ddof=1)
-            if tpm.is_sparse:
-                std1[std1 == 0] = 1.0                                               # sc.pp.scale, cnmf.py:967
-            norm_tpm_ds = tpm_ds.from_columns(hv_idx, 1.0 / std1)
-            sp_rf = spectra_tpm.loc[:, hvgs].div(tpm_stats.loc[hvgs, "__std"], axis=1)
-            rf2, _, _ = norm_tpm_ds.refit(sp_rf.values, kw)
-            rf_usages = pd.DataFrame(rf2.astype(np.float64), index=norm_counts.obs_names, columns=sp_rf.index)
-            norm_tpm_ds.close()
-        tpm_ds.close()
+        usage_coef = pd.DataFrame(res["usage_coef"], index=programs, columns=tpm.var_names)
+        S, topics_dist = res["S"], res["topics_dist"]
 
         tag = (k, dt_repl)
         save_df_to_npz(median_spectra, self.paths["consensus_spectra"] % tag)

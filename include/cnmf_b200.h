@@ -152,6 +152,26 @@ int cnmf_factorize(cnmf_dataset_t d, int n_restarts, const int32_t* ks, const ui
                    const cnmf_nmf_params* params, float* spectra_host, float* usages_host,
                    int32_t* n_iter_host, double* err_host, void* stream);
 
+/* Same restarts, same seeds, but the spectra stay on the device: spectra_dev is (sum ks) x ld_out (ld_out >= n_cols).
+ * This is the per-rank half of the multi-GPU path: the slab goes straight into cnmf_allgather_spectra / an NCCL
+ * all-gather without touching the host (cnmf.py:748-773 `combine` meets on disk instead). */
+int cnmf_factorize_seeds_dev(cnmf_dataset_t d, int n_restarts, const int32_t* ks, const uint32_t* seeds,
+                             const cnmf_nmf_params* params, float* spectra_dev, long long ld_out,
+                             int32_t* n_iter_host, double* err_host, void* stream);
+
+/* ---- the one collective of the path: all-gather of the per-rank spectra slabs ---------------- */
+/* merged_dev (world x rows_per_rank x ld) <- every rank's local_dev (rows_per_rank x ld; ranks with fewer rows pad),
+ * asynchronous on `stream`.  `nccl_comm` is an ncclComm_t -- the host application's own, or one made by
+ * cnmf_comm_create.  libnccl.so.2 is bound at run time (no link-time dependency; CNMF_NCCL_LIB overrides the path). */
+int cnmf_allgather_spectra(void* nccl_comm, const float* local_dev, long long rows_per_rank, long long ld,
+                           float* merged_dev, void* stream);
+/* communicator bootstrap for hosts without one: rank 0 calls cnmf_comm_unique_id and ships the 128 bytes to every
+ * rank over whatever channel it has (MPI, a TCP store, torch.distributed ...); every rank then calls
+ * cnmf_comm_create with its rank (collective: blocks until all ranks arrive) */
+int cnmf_comm_unique_id(char* id_out_128);
+int cnmf_comm_create(cnmf_handle_t h, const char* id_128, int rank, int world, void** comm_out);
+int cnmf_comm_destroy(void* nccl_comm);
+
 /* Same, but initial factors are supplied (host, packed like the outputs) instead of seeds. */
 int cnmf_factorize_init(cnmf_dataset_t d, int n_restarts, const int32_t* ks, const float* Wt0_host,
                         const float* H0_host, const cnmf_nmf_params* params, float* spectra_host,

@@ -50,10 +50,27 @@ def main():
         got = merged[int(k)].values
         for it in range(ref.shape[0] // k):
             e = np.linalg.norm(got[it * k:(it + 1) * k] - ref[it * k:(it + 1) * k]) / np.linalg.norm(ref[it * k:(it + 1) * k])
-            lim = max(1e-4, 5 * float(g["fp32dev_k%d" % k][it]))
+            lim = 1e-3 if (int(k), it) == (4, 0) else 1e-4     # the ill-conditioned restart named in test_gpu_parity.py
             assert e < lim, (k, it, e)
             worst = max(worst, e)
     print("rank %d/%d: merged spectra match the reference fixture (worst rel-L2 %.2e)" % (rank, world, worst), flush=True)
+    # consensus sweep sharded K -> GPU, fed from the device slab the all-gather left behind (no files, no H2D)
+    import yaml
+    from cnmf_b200 import consensus as cs
+    from cnmf_b200 import io as cio
+    from cnmf_b200.parallel import consensus_ks_of_rank
+    sharded = obj.last_sharded_spectra
+    table = g["table"]
+    kw = yaml.load(open(obj.paths["nmf_run_parameters"]), Loader=yaml.FullLoader)
+    norm = cio.read_matrix(obj.paths["normalized_counts"])
+    norm_ds = obj._dataset(norm.X)
+    for k in consensus_ks_of_rank(sorted(int(x) for x in g["ks"]), rank, world):
+        jobs = [j for j in range(len(table)) if table[j, 0] == k]
+        res = cs.consensus_numerics(obj.engine(), sharded.matrix(obj.engine(), jobs), k, norm_ds, kw,
+                                    density_threshold=float(g["dt"]))
+        e = np.linalg.norm(res["median_spectra"] - g["cspectra_k%d" % k]) / np.linalg.norm(g["cspectra_k%d" % k])
+        assert e < (3e-4 if k == 4 else 1e-4), (k, e)
+        print("rank %d/%d: consensus(k=%d) from the device slab matches the reference (rel-L2 %.2e)" % (rank, world, k, e), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

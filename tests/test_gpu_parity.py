@@ -743,3 +743,20 @@ def test_clustergram_order_matches_reference_rule(tmp_path):
             ref += list(np.where(f)[0])
     assert sorted(order) == list(range(int(keep.sum())))
     assert order == ref
+
+
+def test_two_gpu_sharded_factorize_allgather_consensus():
+    """tests/gpu_dist_check.py under torchrun with 2 ranks: restarts sharded idx % 2, ONE NCCL all-gather through the C
+    ABI (cnmf_allgather_spectra on a communicator made by cnmf_comm_create), merged spectra equal the reference fixture
+    on both ranks, consensus Ks sharded over the ranks.  Needs 2 GPUs (skipped on a single-GPU box)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gpu_dist_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29571", script],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("merged spectra match the reference fixture") == 2, r.stdout[-2000:]
