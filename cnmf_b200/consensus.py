@@ -263,17 +263,28 @@ def ols_zscore(usages, tpm_ds):
 # ------------------------------------------------------------------------------ the consensus step as one function
 def consensus_numerics(eng, merged, k, norm_ds, kw, density_threshold=0.5, n_neighbors=None,
                        local_neighborhood_size=0.30, stats_only=False, local_density=None, want_dist=False,
-                       tpm_ds=None, hvg_idx=None, tpm_std_hvg=None, refit_usage=True, tpm_sparse=False):
+                       tpm_ds=None, hvg_idx=None, tpm_std_hvg=None, refit_usage=True, tpm_sparse=False,
+                       on_density=None):
     """Every numeric step of cNMF.consensus (cnmf.py:879-975) for one K, on the GPU, without files or labels:
     the facade (pipeline.cNMF.consensus) wraps it in the reference's DataFrames / ledger, bench.py times it.
 
     merged        R x G stacked spectra: numpy array or a SpectraMatrix already on the device (not yet normalised)
     norm_ds       resident normalised counts (refit a, cnmf.py:919);  tpm_ds: resident TPM (refits b, c and the OLS)
-    local_density optional cached densities (cnmf.py:887-888); else computed (and returned)
+    local_density optional cached densities (cnmf.py:887-888); else computed (and returned); on_density(array) is
+                  called as soon as they exist -- the reference writes its cache before the filter can raise
     Returns a dict: local_density, keep (indices), labels (0-based), median_spectra (K x G, rows sum to 1), rf_usages,
     refit_err and, unless stats_only: order (program permutation, cnmf.py:939-946), norm_usages, spectra_tpm,
     usage_coef, final rf_usages; with stats_only: silhouette, prediction_error (cnmf.py:922-936)."""
     import pandas as pd
+    import time
+    phases = STATS.setdefault("phases_ms", {})
+    t_last = [time.perf_counter()]
+
+    def mark(name):          # host wall clock per phase (every phase ends in a host-visible result, i.e. synchronised)
+        now = time.perf_counter()
+        phases[name] = phases.get(name, 0.0) + 1e3 * (now - t_last[0])
+        t_last[0] = now
+
     S = merged if isinstance(merged, SpectraMatrix) else SpectraMatrix(eng, merged)
     S.l2_normalize()                                                            # cnmf.py:882
     R = S.R
@@ -284,24 +295,31 @@ def consensus_numerics(eng, merged, k, norm_ds, kw, density_threshold=0.5, n_nei
         if local_density is None:
             local_density, out["topics_dist"] = S.local_density(n_neighbors, return_dist=want_dist)   # cnmf.py:891-896
         out["local_density"] = np.asarray(local_density, dtype=np.float64)
+        if on_density is not None:
+            on_density(out["local_density"])
         keep = np.where(out["local_density"] < density_threshold)[0]             # cnmf.py:903
         if len(keep) == 0:
             raise RuntimeError("Zero components remain after density filtering. Consider increasing density threshold")
         if len(keep) < R:
             S = S.take_rows(keep)
         out["keep"] = keep
+        mark("l2_dist_density_filter")
     out["S"] = S
     labels0, labels_t, _, _ = kmeans(S, k)                                        # cnmf.py:908-910
     out["labels"] = labels0
+    mark("kmeans")
     med = cluster_medians(S, labels_t, k)                                         # cnmf.py:913-916
     out["median_spectra"] = med
+    mark("median")
     rf, it_a, err = norm_ds.refit(med, kw)                                        # cnmf.py:919
     STATS.setdefault("refits", []).append((norm_ds.shape[0], norm_ds.shape[1], it_a))
     rf = rf.astype(np.float64)
     out["rf_usages"], out["refit_err"] = rf, err
+    mark("refit_usage_norm_counts")
     if stats_only:                                                                # cnmf.py:922-936
         out["silhouette"] = silhouette(S, labels0, labels_t, k)
         out["prediction_error"] = err ** 2
+        mark("silhouette")
         return out
     norm_usages = rf / rf.sum(axis=1, keepdims=True)                              # cnmf.py:939-946
     order = pd.Series(norm_usages.sum(axis=0)).sort_values(ascending=False).index.values
@@ -313,7 +331,9 @@ def consensus_numerics(eng, merged, k, norm_ds, kw, density_threshold=0.5, n_nei
     STATS.setdefault("refits", []).append((tpm_ds.shape[1], tpm_ds.shape[0], it_b))
     spectra_tpm = Ht.T.astype(np.float64)
     out["spectra_tpm"] = spectra_tpm
+    mark("refit_spectra_tpm")
     out["usage_coef"] = ols_zscore(rf, tpm_ds)                                     # cnmf.py:958
+    mark("ols")
     if refit_usage and hvg_idx is not None:                                        # cnmf.py:961-975
         _, var = tpm_ds.col_stats()
         n = tpm_ds.shape[0]
@@ -326,4 +346,5 @@ def consensus_numerics(eng, merged, k, norm_ds, kw, density_threshold=0.5, n_nei
         STATS.setdefault("refits", []).append((norm_tpm_ds.shape[0], norm_tpm_ds.shape[1], it_c))
         norm_tpm_ds.close()
         out["rf_usages"] = rf2.astype(np.float64)
+        mark("refit_usage_tpm_hvg")
     return out

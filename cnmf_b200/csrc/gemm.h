@@ -38,7 +38,9 @@ int gemm_fixed_splits(int Kd, int f16 = 0);
 
 // Choice of the split-K factor (gemm_fixed_splits) and the tile width for the tcgen05 kernel: minimises
 // (waves of the persistent grid) x (tile cost) x (k-blocks per item + pipeline fill) over the tile widths.
-void gemm_plan(int M, int N, int Kd, int sm_count, int* splits, int* bn, int f16 = 0);
+void gemm_plan(int M, int N, int Kd, int sm_count, int* splits, int* bn, int f16 = 0, int b_exact = 0);
+// whether gemm_tf32x3 runs the CTA-pair (cta_group::2, 256-row tiles) kernel for this problem
+bool gemm_uses_pair(int M, int b_exact);
 
 // tcgen05 / TMEM / TMA path (gemm_tf32x3.cu)
 int gemm_tf32x3(const GemmArgs& g, cudaStream_t stream);

@@ -52,10 +52,13 @@ constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;   // ~2 s: a dead pipeli
 
 // BEXACT: the B operand is exactly representable in tf32 (e.g. integer counts), so it needs no "lo" piece:
 // 2 MMAs per k-step instead of 3, 64 KB stages (3 of them) instead of 96 KB (2).
-template <int BN, int STAGES, bool BEXACT>
+// CTA2: a pair of CTAs (one cluster, two SMs of a TPC) works on a 256 x BN tile with tcgen05.mma.cta_group::2: each CTA
+// stages its own 128 rows of A and HALF of the B tile, so the operand bytes every SM pulls from L2 per MMA cycle drop
+// from 64 KB to 48 KB per k-block -- the feed the 1-CTA kernel is bound by (profiles/r1i_ncu_f16_summary.txt).
+template <int BN, int STAGES, bool BEXACT, bool CTA2 = false>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 4;              // 16 KB
-  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int B_BYTES = (CTA2 ? BN / 2 : BN) * BK * 4;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + (BEXACT ? 1 : 2) * B_BYTES;
   static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFFSET = TILE_BYTES;            // full[STAGES], empty[STAGES], tfull[2], tempty[2]
@@ -103,6 +106,54 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- CTA-pair (cluster of 2) variants
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// both CTAs of a pair load into their OWN shared memory; the transaction bytes are signalled on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -139,11 +190,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 
 template <bool F16>
-__device__ __forceinline__ uint32_t make_idesc(int bn) {
+__device__ __forceinline__ uint32_t make_idesc(int bn, int m = BM) {
   // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a/b format @7/@10 (TF32 = 2, F16 = 0), K-major A and B, N>>3 @17, M>>4 @24
+  // (M = 256 for cta_group::2: 128 rows in each CTA of the pair)
   const uint32_t fmt = F16 ? 0u : 2u;
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(bn >> 3) << 17) |
-         (static_cast<uint32_t>(BM >> 4) << 24);
+         (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -163,18 +215,24 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ------------------------------------------------------------------ the kernel
 // F16 (with BEXACT): operands are fp16 (two pieces of A, one exact B); a k-block is still 128 B per row = 64 elements,
 // a k-step still 32 B = 16 elements (UMMA_K of kind::f16), so the smem / TMA / descriptor byte geometry is unchanged.
-template <int BN, int STAGES, bool BEXACT, bool F16>
-// 320 threads = 10 warps, allocated as 12 (granularity 4): at most 65536 / (12 * 32) = 170 registers per thread --
-// __launch_bounds__ makes ptxas pick 168; a higher __maxnreg__ compiles but cannot launch
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                   float* __restrict__ C, int M, int N, int ldc, long long c_split_stride,
-                   int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split, int chain_kb, int bn,
-                   const float* __restrict__ out_scale, const float* __restrict__ a_tile_scale, int a_tiles) {
+//
+// CTA2: the grid is made of clusters of two CTAs (ranks 0 / 1 = the two SMs of a TPC).  A work item is a 256 x bn tile:
+// rank r stages rows [256 i + 128 r, +128) of both A pieces and rows [r bn/2, +bn/2) of the B tile; rank 0's MMA thread
+// issues tcgen05.mma.cta_group::2 (M = 256) which reads A from each CTA's own shared memory, the two B halves from both,
+// and leaves rows 0-127 of the product in rank 0's TMEM and rows 128-255 in rank 1's.  Barrier protocol (the one of
+// CUTLASS / DeepGEMM 2-SM kernels): `full` lives in rank 0 (both producers arrive on it, both CTAs' TMA bytes are
+// signalled on it), `empty` and `tfull` exist in both CTAs and are arrived by multicast commits, `tempty` lives in
+// rank 0 and is arrived by the accumulate warps of both CTAs.
+template <int BN, int STAGES, bool BEXACT, bool F16, bool CTA2>
+__device__ __forceinline__ void
+gemm_body(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi, const CUtensorMap& tmB_lo,
+          float* __restrict__ C, int M, int N, int ldc, long long c_split_stride,
+          int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split, int chain_kb, int bn,
+          const float* __restrict__ out_scale, const float* __restrict__ a_tile_scale, int a_tiles) {
   static_assert(!F16 || BEXACT, "the fp16 path exists for exact integer B operands only");
+  static_assert(!CTA2 || BEXACT, "the CTA-pair kernel is built for the exact-B (2-pass) forms");
   constexpr int BKE = F16 ? 2 * BK : BK;                        // elements per k-block
-  using L = SmemLayout<BN, STAGES, BEXACT>;
+  using L = SmemLayout<BN, STAGES, BEXACT, CTA2>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024 B alignment
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -189,37 +247,51 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = 2 * BN;                      // two accumulators (power of two: 256 or 512)
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;       // 0 = leader of the pair
+  const int worker = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_workers = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // CTA2: m_tiles counts 256-row tile PAIRS; this CTA's 128-row tile is 2 * (pair) + rank
+
+  if constexpr (CTA2) cluster_sync_all();                     // both CTAs are running before either touches the pair state
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), CTA2 ? 2 : 1);                   // CTA2 (used in rank 0): one arrival per producer
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 32 * NUM_EPI_WARPS);
+      mbar_init(tempty_bar(a), (CTA2 ? 2 : 1) * NUM_EPI_WARPS);   // one arrival per accumulate warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_base + L::TMEM_PTR_OFFSET), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_base + L::TMEM_PTR_OFFSET), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_base + L::TMEM_PTR_OFFSET), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();                     // the peer's barriers are initialised before anyone arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int items = m_tiles * n_tiles * splits;
+  const int bnl = CTA2 ? bn >> 1 : bn;                        // B rows this CTA stages
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < items; w += gridDim.x) {
-        const int mt = w % m_tiles;
+      for (int w = worker; w < items; w += n_workers) {
+        const int mt = (w % m_tiles) * (CTA2 ? 2 : 1) + static_cast<int>(rank);
         const int nt = (w / m_tiles) % n_tiles;
         const int z = w / (m_tiles * n_tiles);
         const int kb0 = z * kb_per_split;
@@ -227,25 +299,42 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 0);
           const uint32_t st = smem_base + stage * L::STAGE_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage),
-                                2u * L::A_BYTES + (BEXACT ? 1u : 2u) * static_cast<uint32_t>(bn) * BK * 4u);
-          tma_load_2d(st, &tmA_hi, full_bar(stage), kb * BKE, mt * BM);
-          tma_load_2d(st + L::A_BYTES, &tmA_lo, full_bar(stage), kb * BKE, mt * BM);
-          tma_load_2d(st + 2 * L::A_BYTES, &tmB_hi, full_bar(stage), kb * BKE, nt * bn);
-          if constexpr (!BEXACT) tma_load_2d(st + 2 * L::A_BYTES + L::B_BYTES, &tmB_lo, full_bar(stage), kb * BKE, nt * bn);
+          const uint32_t stage_tx = 2u * L::A_BYTES + (BEXACT ? 1u : 2u) * static_cast<uint32_t>(bnl) * BK * 4u;
+          if constexpr (CTA2) {
+            const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2u * stage_tx);      // both CTAs' bytes
+            tma_load_2d_pair(st, &tmA_hi, lead_full, kb * BKE, mt * BM);
+            tma_load_2d_pair(st + L::A_BYTES, &tmA_lo, lead_full, kb * BKE, mt * BM);
+            tma_load_2d_pair(st + 2 * L::A_BYTES, &tmB_hi, lead_full, kb * BKE, nt * bn + static_cast<int>(rank) * bnl);
+            if (rank != 0) mbar_arrive_cluster(lead_full);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), stage_tx);
+            tma_load_2d(st, &tmA_hi, full_bar(stage), kb * BKE, mt * BM);
+            tma_load_2d(st + L::A_BYTES, &tmA_lo, full_bar(stage), kb * BKE, mt * BM);
+            tma_load_2d(st + 2 * L::A_BYTES, &tmB_hi, full_bar(stage), kb * BKE, nt * bn);
+            if constexpr (!BEXACT) tma_load_2d(st + 2 * L::A_BYTES + L::B_BYTES, &tmB_lo, full_bar(stage), kb * BKE, nt * bn);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if constexpr (CTA2) {
+        // the MMA thread's last commits arrive on this CTA's `empty` barriers from the other SM: see every slot
+        // released before this CTA may retire its shared memory
+        for (int i = 0; i < STAGES; ++i) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc<F16>(bn);          // UMMA N = bn (multiple of 16, <= BN)
+    // ===================== MMA issuer (one thread; the leader CTA of a pair) =====================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc<F16>(bn, CTA2 ? 2 * BM : BM);   // UMMA N = bn (multiple of 16, <= BN)
       int stage = 0;
       uint32_t phase = 0;
       int buf = 0;
       uint32_t buf_phase = 0;
-      for (int w = blockIdx.x; w < items; w += gridDim.x) {
+      for (int w = worker; w < items; w += n_workers) {
         const int z = w / (m_tiles * n_tiles);
         const int kb0 = z * kb_per_split;
         const int kb1 = min(total_kb, kb0 + kb_per_split);
@@ -265,19 +354,37 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 4) >> 4);   // +32 B per k-step inside the swizzle row
-              if constexpr (F16) {
-                umma_f16(tmem_d, a_lo + koff, b_hi + koff, idesc, (kb > c0 || k > 0) ? 1u : 0u);    // small terms first
+              const uint32_t acc0 = (kb > c0 || k > 0) ? 1u : 0u;
+              if constexpr (CTA2) {
+                if constexpr (F16) {
+                  umma_f16_pair(tmem_d, a_lo + koff, b_hi + koff, idesc, acc0);     // small terms first
+                  umma_f16_pair(tmem_d, a_hi + koff, b_hi + koff, idesc, 1u);
+                } else {
+                  umma_tf32_pair(tmem_d, a_lo + koff, b_hi + koff, idesc, acc0);
+                  umma_tf32_pair(tmem_d, a_hi + koff, b_hi + koff, idesc, 1u);
+                }
+              } else if constexpr (F16) {
+                umma_f16(tmem_d, a_lo + koff, b_hi + koff, idesc, acc0);    // small terms first
                 umma_f16(tmem_d, a_hi + koff, b_hi + koff, idesc, 1u);
               } else {
-                umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, (kb > c0 || k > 0) ? 1u : 0u);   // small terms first
+                umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, acc0);   // small terms first
                 if constexpr (!BEXACT) umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1u);
                 umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, 1u);
               }
             }
-            umma_commit(empty_bar(stage));         // smem slot is free once these MMAs have read it
+            // smem slot is free once these MMAs have read it (CTA2: in both CTAs)
+            if constexpr (CTA2) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(tfull_bar(buf));             // chain complete -> accumulate warps
+          // chain complete -> accumulate warps (CTA2: of both CTAs)
+          if constexpr (CTA2) umma_commit_pair(tfull_bar(buf)); else umma_commit(tfull_bar(buf));
+          if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
+        }
+      }
+      if constexpr (CTA2) {
+        // every chain has been drained by both CTAs before the leader lets go of its barriers
+        for (int i = 0; i < 2; ++i) {
+          mbar_wait(tempty_bar(buf), buf_phase ^ 1u, 1);
           if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
         }
       }
@@ -291,8 +398,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const int half = (warp - 2) >> 2;
     int buf = 0;
     uint32_t buf_phase = 0;
-    for (int w = blockIdx.x; w < items; w += gridDim.x) {
-      const int mt = w % m_tiles;
+    for (int w = worker; w < items; w += n_workers) {
+      const int mt = (w % m_tiles) * (CTA2 ? 2 : 1) + static_cast<int>(rank);
       const int nt = (w / m_tiles) % n_tiles;
       const int z = w / (m_tiles * n_tiles);
       const int kb0 = z * kb_per_split;
@@ -324,7 +431,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           }
         }
         tc_fence_before();
-        mbar_arrive(tempty_bar(buf));
+        __syncwarp();
+        if (lane == 0) {                                // one arrival per warp, on the leader's barrier
+          if constexpr (CTA2) mbar_arrive_cluster(mapa_shared(tempty_bar(buf), 0));
+          else mbar_arrive(tempty_bar(buf));
+        }
         if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
       }
       // Epilogue.  A thread owns one output row, so a direct store touches 32 rows x 16 B per instruction (32 cache
@@ -366,10 +477,39 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();       // neither CTA retires while the other may still signal it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (CTA2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+}
+
+// 320 threads = 10 warps, allocated as 12 (granularity 4): at most 65536 / (12 * 32) = 170 registers per thread --
+// __launch_bounds__ makes ptxas pick 168; a higher __maxnreg__ compiles but cannot launch
+template <int BN, int STAGES, bool BEXACT, bool F16>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                   float* __restrict__ C, int M, int N, int ldc, long long c_split_stride,
+                   int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split, int chain_kb, int bn,
+                   const float* __restrict__ out_scale, const float* __restrict__ a_tile_scale, int a_tiles) {
+  gemm_body<BN, STAGES, BEXACT, F16, false>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, C, M, N, ldc, c_split_stride, m_tiles, n_tiles,
+                                            splits, total_kb, kb_per_split, chain_kb, bn, out_scale, a_tile_scale, a_tiles);
+}
+
+// the CTA-pair form: clusters of two CTAs, m_tiles = number of 256-row tile pairs
+template <int BN, int STAGES, bool F16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmB_hi,
+                 float* __restrict__ C, int M, int N, int ldc, long long c_split_stride,
+                 int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split, int chain_kb, int bn,
+                 const float* __restrict__ out_scale, const float* __restrict__ a_tile_scale, int a_tiles) {
+  gemm_body<BN, STAGES, true, F16, true>(tmA_hi, tmA_lo, tmB_hi, tmB_hi, C, M, N, ldc, c_split_stride, m_tiles, n_tiles,
+                                         splits, total_kb, kb_per_split, chain_kb, bn, out_scale, a_tile_scale, a_tiles);
 }
 
 // ------------------------------------------------------------------ host side
@@ -429,6 +569,24 @@ int make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int
   return 0;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+
+// k-blocks per TMEM accumulation chain: at most 16 MMAs between drains (general: 1 k-block = 12 MMAs,
+// exact-B: 2 k-blocks = 16 MMAs; with 8 MMAs per chain the drain, not the tensor pipe, paced the kernel)
+template <bool BEXACT, bool F16>
+static int pick_chain_kb(const GemmArgs& g) {
+  int chain_kb = g.chain_kb;
+  if (chain_kb <= 0) {
+    static const int env_chain = [] { const int v = env_int("CNMF_CHAIN_KB", 0); return v >= 1 ? v : 0; }();   // tuning knob
+    chain_kb = env_chain > 0 ? env_chain : (BEXACT ? 2 : 1);
+  }
+  if (F16) chain_kb = 2;     // scale groups of 512 elements = 8 k-blocks: chains of 2 never straddle one
+  return chain_kb;
+}
+
 template <int BN, int STAGES, bool BEXACT, bool F16>
 int launch(const GemmArgs& g, cudaStream_t stream) {
   using L = SmemLayout<BN, STAGES, BEXACT>;
@@ -458,7 +616,7 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
     }
   }
   {
-    static const int env_bn = [] { const char* e = std::getenv("CNMF_GEMM_BN"); return e ? std::atoi(e) : 0; }();
+    static const int env_bn = env_int("CNMF_GEMM_BN", 0);
     if (env_bn >= 16 && env_bn <= BN && env_bn % 16 == 0) bn = env_bn;
   }
   if ((rc = make_map(&mBh, g.B_hi, g.N, g.Kd, g.ldb, bn, F16))) return rc;
@@ -481,21 +639,74 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   }
   const int items = m_tiles * n_tiles * splits;
   const int grid = items < sms ? items : sms;
-  // k-blocks per TMEM accumulation chain: at most 16 MMAs between drains (general: 1 k-block = 12 MMAs,
-  // exact-B: 2 k-blocks = 16 MMAs; with 8 MMAs per chain the drain, not the tensor pipe, paced the kernel)
-  int chain_kb = g.chain_kb;
-  if (chain_kb <= 0) {
-    static const int env_chain = [] {
-      const char* e = std::getenv("CNMF_CHAIN_KB");      // tuning knob
-      const int v = e ? std::atoi(e) : 0;
-      return v >= 1 ? v : 0;
-    }();
-    chain_kb = env_chain > 0 ? env_chain : (BEXACT ? 2 : 1);
-  }
-  if (F16) chain_kb = 2;     // scale groups of 512 elements = 8 k-blocks: chains of 2 never straddle one
+  const int chain_kb = pick_chain_kb<BEXACT, F16>(g);
   kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(mAh, mAl, mBh, mBl, g.C, g.M, g.N, g.ldc, g.c_split_stride,
                                                     m_tiles, n_tiles, splits, total_kb, kb_per_split,
                                                     chain_kb, bn, g.out_col_scale, g.a_tile_scale, g.a_tiles);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// CTA-pair launch (exact-B forms): 256 x bn tiles, one cluster of two CTAs per tile, 4 stages of 48 KB
+template <int BN, int STAGES, bool F16>
+int launch_pair(const GemmArgs& g, cudaStream_t stream) {
+  using L = SmemLayout<BN, STAGES, true, true>;
+  static_assert(L::DYN_BYTES <= 227 * 1024, "CTA-pair stages do not fit the shared memory of an SM");
+  constexpr int BKE = F16 ? 2 * BK : BK;
+  CUtensorMap mAh, mAl, mBh;
+  int rc;
+  if ((rc = make_map(&mAh, g.A_hi, g.M, g.Kd, g.lda, BM, F16))) return rc;
+  if ((rc = make_map(&mAl, g.A_lo, g.M, g.Kd, g.lda, BM, F16))) return rc;
+  int dev = 0, sms = 0;
+  CNMF_CUDA_CHECK(cudaGetDevice(&dev));
+  CNMF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int m_pairs = (g.M + 2 * BM - 1) / (2 * BM);
+  int bn = g.bn;
+  if (bn <= 0 || bn > BN || bn % 16 != 0) bn = g.N <= BN ? ((g.N + 15) / 16) * 16 : BN;
+  {
+    static const int env_bn = env_int("CNMF_GEMM_BN", 0);
+    if (env_bn >= 16 && env_bn <= BN && env_bn % 16 == 0) bn = env_bn;
+  }
+  if ((rc = make_map(&mBh, g.B_hi, g.N, g.Kd, g.ldb, bn / 2, F16))) return rc;    // each CTA stages half of the B tile
+
+  const int n_tiles = (g.N + bn - 1) / bn;
+  const int total_kb = (g.Kd + BKE - 1) / BKE;
+  int splits = g.splits < 1 ? 1 : g.splits;
+  if (splits > total_kb) splits = total_kb;
+  int kb_per_split = (total_kb + splits - 1) / splits;
+  if (F16 && (kb_per_split & 1)) ++kb_per_split;
+  splits = (total_kb + kb_per_split - 1) / kb_per_split;
+  if (splits != g.splits_effective) { set_last_error("gemm: splits_effective mismatch (use gemm_effective_splits)"); return -1; }
+
+  auto kern = gemm_pair_kernel<BN, STAGES, F16>;
+  static bool attr_set[64] = {};
+  static int max_clusters[64] = {};
+  const int di = (dev >= 0 && dev < 64) ? dev : 0;
+  if (!attr_set[di]) {
+    CNMF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sms & ~1);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = L::DYN_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = sms / 2;
+    }
+    max_clusters[di] = n;
+    attr_set[di] = true;
+  }
+  const int items = m_pairs * n_tiles * splits;
+  const int clusters = items < max_clusters[di] ? items : max_clusters[di];
+  const int chain_kb = pick_chain_kb<true, F16>(g);
+  kern<<<2 * clusters, NUM_THREADS, L::DYN_BYTES, stream>>>(mAh, mAl, mBh, g.C, g.M, g.N, g.ldc, g.c_split_stride,
+                                                            m_pairs, n_tiles, splits, total_kb, kb_per_split,
+                                                            chain_kb, bn, g.out_col_scale, g.a_tile_scale, g.a_tiles);
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -514,8 +725,17 @@ int gemm_fixed_splits(int Kd, int f16) {
   return gemm_effective_splits(Kd, s, f16);
 }
 
-void gemm_plan(int M, int N, int Kd, int sm_count, int* splits_out, int* bn_out, int f16) {
-  const int m_tiles = (M + BM - 1) / BM;
+// CTA pairs (cta_group::2) pay off as soon as there are two 128-row tiles to pair: each SM then pulls 48 KB instead of
+// 64 KB of operands per k-block from L2.  CNMF_GEMM_PAIR=0 keeps the 1-CTA kernel (A/B comparison).
+bool gemm_uses_pair(int M, int b_exact) {
+  static const int env_pair = env_int("CNMF_GEMM_PAIR", 1);
+  return env_pair != 0 && b_exact && M > BM;
+}
+
+void gemm_plan(int M, int N, int Kd, int sm_count, int* splits_out, int* bn_out, int f16, int b_exact) {
+  const bool pair = gemm_uses_pair(M, b_exact || f16);
+  const int m_tiles = pair ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM;
+  if (pair) sm_count /= 2;                                   // workers are CTA pairs
   const int bke = f16 ? 2 * BK : BK;
   const int total_kb = (Kd + bke - 1) / bke;
   const int s = gemm_fixed_splits(Kd, f16);
@@ -556,14 +776,19 @@ int gemm_tf32x3(const GemmArgs& g, cudaStream_t stream) {
                 reinterpret_cast<uintptr_t>(g.B_hi) | reinterpret_cast<uintptr_t>(g.B_lo) |
                 reinterpret_cast<uintptr_t>(g.C) | reinterpret_cast<uintptr_t>(g.out_col_scale)) % 16 == 0,
                "gemm: pointers must be 16-byte aligned");
+  const bool pair = gemm_uses_pair(g.M, g.b_exact);
   if (g.f16) {
     CNMF_REQUIRE(g.b_exact, "gemm: the fp16 path needs an exact B operand");
     CNMF_REQUIRE(g.lda % 8 == 0 && g.ldb % 8 == 0, "gemm: fp16 leading dimensions must be multiples of 8 halves");
     CNMF_REQUIRE(!g.a_tile_scale || g.a_tiles * 512 >= g.Kd, "gemm: a_tiles does not cover the reduction length");
     CNMF_REQUIRE(g.chain_kb == 0 || g.chain_kb == 2, "gemm: the fp16 path drains chains of 2 k-blocks");
+    if (pair) return launch_pair<256, 4, true>(g, stream);
     return launch<256, 3, true, true>(g, stream);
   }
-  if (g.b_exact) return launch<256, 3, true, false>(g, stream);
+  if (g.b_exact) {
+    if (pair) return launch_pair<256, 4, false>(g, stream);
+    return launch<256, 3, true, false>(g, stream);
+  }
   return launch<256, 2, false, false>(g, stream);
 }
 

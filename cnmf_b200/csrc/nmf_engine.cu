@@ -151,7 +151,7 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   float *NUMr = nullptr, *NUMc = nullptr;
   auto plan_one = [&](int sk, int n, int kd, GemmPlan* pl) {
     if (tf32) {
-      gemm_plan(sk, n, kd, h->sm_count, &pl->splits, &pl->bn, f16 ? 1 : 0);
+      gemm_plan(sk, n, kd, h->sm_count, &pl->splits, &pl->bn, f16 ? 1 : 0, v.exact ? 1 : 0);
     } else {
       pl->splits = gemm_fixed_splits(kd, 0);
       pl->bn = 0;

@@ -414,11 +414,15 @@ class cNMF:
                 hvgs = open(self.paths["nmf_genes_list"]).read().split("\n")
                 hv_idx = tpm.var_names.get_indexer(hvgs)
                 tpm_std_hvg = tpm_stats.loc[hvgs, "__std"].values
+        def save_density(dens):                                                     # cnmf.py:897-899
+            if cached is None:
+                save_df_to_npz(pd.DataFrame(dens, columns=["local_density"], index=merged.index), cache)
+
         res = cs.consensus_numerics(eng, merged.values, k, norm_ds, kw, density_threshold=density_threshold,
                                     local_neighborhood_size=local_neighborhood_size, stats_only=stats_only,
                                     local_density=cached, want_dist=show_clustering, tpm_ds=tpm_ds, hvg_idx=hv_idx,
                                     tpm_std_hvg=tpm_std_hvg, refit_usage=refit_usage,
-                                    tpm_sparse=bool(tpm is not None and tpm.is_sparse))
+                                    tpm_sparse=bool(tpm is not None and tpm.is_sparse), on_density=save_density)
         if tpm_ds is not None:
             tpm_ds.close()
         if stats_only:                                                              # cnmf.py:922-936
@@ -427,7 +431,6 @@ class cNMF:
                                 columns=["stats"])
         if cached is None:
             local_density = pd.DataFrame(res["local_density"], columns=["local_density"], index=merged.index)
-            save_df_to_npz(local_density, cache)
         density_filter = local_density.iloc[:, 0] < density_threshold               # cnmf.py:903
         l2_index = merged.index[res["keep"]]
         cluster_labels = pd.Series(res["labels"] + 1, index=l2_index)
