@@ -725,10 +725,14 @@ int gemm_fixed_splits(int Kd, int f16) {
   return gemm_effective_splits(Kd, s, f16);
 }
 
-// CTA pairs (cta_group::2) pay off as soon as there are two 128-row tiles to pair: each SM then pulls 48 KB instead of
-// 64 KB of operands per k-block from L2.  CNMF_GEMM_PAIR=0 keeps the 1-CTA kernel (A/B comparison).
+// CTA pairs (cta_group::2): each SM pulls 48 KB instead of 64 KB of operands per k-block from L2.  MEASURED (run r2b,
+// profiles/r2b_gemm_pair_vs_1cta.log): correct (same bits as the 1-CTA kernel) but 0.65x its speed -- 387 vs 608 TFLOP/s on
+// the c2 W half, 487 vs 740 on 4096 x 16384 x 2000.  The 1-CTA kernel already runs at ~0.9 of the MMA rate its two passes
+// allow when timed alone, so the operand feed was not the limiter; what the pair adds is a cross-SM round trip (remote
+// mbarrier arrive + multicast commit) on EVERY 16-MMA accumulation chain, and with chains that short (the TMEM
+// truncation fix) the handshake, not the tensor pipe, paces the pair.  Kept as an opt-in (CNMF_GEMM_PAIR=1).
 bool gemm_uses_pair(int M, int b_exact) {
-  static const int env_pair = env_int("CNMF_GEMM_PAIR", 1);
+  static const int env_pair = env_int("CNMF_GEMM_PAIR", 0);
   return env_pair != 0 && b_exact && M > BM;
 }
 
