@@ -27,6 +27,7 @@
 // finished chain into round-to-nearest fp32 register accumulators (128 per thread) while the next
 // chain is being issued.  Result: ~4e-7 relative, the same class as an FFMA fp32 GEMM.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -212,6 +213,224 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------ fused W-half epilogue
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// The multiplicative update of the row factor, applied to the product tile while it is still in registers (struct
+// FuseW in gemm.h).  Thread = packed row (o + c) of a restart x the 128 items of one scale group; acc[] holds the
+// numerators on entry and the new factor values on exit.  The 128 threads that share a column half exchange rows
+// through their four transpose patches (a 128 x 20-float staging area): per 16-item chunk every thread publishes the
+// OLD values of its row, reads the K rows of its restart (den = sum_i Gram[c, i] F[o + i, item]), publishes the NEW
+// values, accumulates its row of the restart's K x K Gram of the new values (fp32 over the chunk's 16 items, fp64
+// across chunks -- the same summation granularity as the stand-alone update kernel) and the warp stores its 32 rows of
+// the chunk coalesced.  Restarts never straddle a 128-row tile (the engine packs them that way), so every row a thread
+// needs is in the staging area.  Afterwards the thread emits the two fp16 operand pieces of its 128 values with the
+// power-of-two scale of the group: the same bits emit_f16_kernel would produce from F_out.
+template <int HALF>
+__device__ __forceinline__ void fused_w_epilogue(float (&acc)[HALF], const FuseW& fz, int M, int mt, int nt, int n_tiles,
+                                                 int q, int half, int lane, const float* __restrict__ out_scale,
+                                                 float* epi) {
+  static_assert(HALF == 128, "one thread owns one 128-item scale group");
+  constexpr float EPS32 = 1.1920928955078125e-07f;     // np.finfo(np.float32).eps, sklearn _nmf.py:32
+  constexpr float FMIN = 1.17549435e-38f;
+  const int r = q * 32 + lane;                          // row inside the 128-row tile
+  const int grow = mt * BM + r;
+  const int col0 = nt * 256 + half * HALF;              // first item of this thread's group (tile width 256)
+  float* S = epi + half * (128 * 20);                   // staging of this column half
+  float* Sr = S + r * 20;
+  const int bar_id = 1 + half;
+  const int ld = fz.ld;
+
+  int slot = -1;
+  if (grow < M) slot = __ldg(fz.row_slot + grow);
+  int K = 0, o = grow, rid = 0;
+  bool upd = false, cpy = false;
+  if (slot >= 0) {
+    rid = __ldg(fz.rid + slot);
+    K = __ldg(fz.k + slot);
+    o = __ldg(fz.off + slot);
+    if (__ldg(fz.done + rid)) cpy = true; else upd = true;
+  }
+  const int c = grow - o;
+  const int lr0 = o - mt * BM;                          // tile-local row of the restart's first component
+  const int Kl = upd ? K : 0;
+  float g[16];                                          // row c of the other factor's Gram (dynamic index: local memory)
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    g[i] = (i < Kl) ? static_cast<float>(fz.gram_in[static_cast<long long>(rid) * (KMAX * KMAX) + c * KMAX + i]) : 0.f;
+  double gd[16];                                        // row c of the Gram of the new values
+  const bool want_gram = fz.gram_part != nullptr;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) gd[i] = 0.0;
+
+  if (out_scale) {                                      // per-item scale of the product (exact-count datasets)
+#pragma unroll
+    for (int j = 0; j < HALF; j += 4) {
+      if (col0 + j + 3 < ld) {
+        const float4 sc = *reinterpret_cast<const float4*>(out_scale + col0 + j);
+        acc[j] *= sc.x; acc[j + 1] *= sc.y; acc[j + 2] *= sc.z; acc[j + 3] *= sc.w;
+      }
+    }
+  }
+
+  const bool row_ok = grow < M;
+  const float* pin = fz.F_in + static_cast<long long>(row_ok ? grow : 0) * ld + col0;
+  float* pout = fz.F_out;
+  const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;
+  float4 wn[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+    wn[t] = (row_ok && col0 + 4 * t + 3 < ld) ? *reinterpret_cast<const float4*>(pin + 4 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    float4 wc[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      wc[t] = wn[t];
+      *reinterpret_cast<float4*>(Sr + 4 * t) = wc[t];
+    }
+    if (ch < 7) {                                       // next chunk of the own row (in flight under this chunk's math)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int cc = (ch + 1) * 16 + 4 * t;
+        wn[t] = (row_ok && col0 + cc + 3 < ld) ? *reinterpret_cast<const float4*>(pin + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    named_bar(bar_id, 128);                             // old rows of the chunk are published
+    float2 den[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) den[t] = make_float2(0.f, 0.f);
+#pragma unroll 2
+    for (int i = 0; i < Kl; ++i) {                      // summed in component order, like the reference's W @ HHt row
+      const float2 gi = bcast2(g[i]);
+      const float4* sp = reinterpret_cast<const float4*>(S + (lr0 + i) * 20);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float4 w = sp[t];
+        den[2 * t] = fma2(gi, make_float2(w.x, w.y), den[2 * t]);
+        den[2 * t + 1] = fma2(gi, make_float2(w.z, w.w), den[2 * t + 1]);
+      }
+    }
+    float4 outv[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 own0 = make_float2(wc[t].x, wc[t].y), own1 = make_float2(wc[t].z, wc[t].w);
+      const float2 num0 = make_float2(acc[ch * 16 + 4 * t], acc[ch * 16 + 4 * t + 1]);
+      const float2 num1 = make_float2(acc[ch * 16 + 4 * t + 2], acc[ch * 16 + 4 * t + 3]);
+      // regularisation terms unconditionally (adding 0 is exact); zero denominators -> eps (sklearn _nmf.py:615)
+      float2 d0 = fma2(bcast2(fz.l2), own0, add2(den[2 * t], bcast2(fz.l1)));
+      float2 d1 = fma2(bcast2(fz.l2), own1, add2(den[2 * t + 1], bcast2(fz.l1)));
+      d0.x = (d0.x < FMIN) ? EPS32 : d0.x; d0.y = (d0.y < FMIN) ? EPS32 : d0.y;
+      d1.x = (d1.x < FMIN) ? EPS32 : d1.x; d1.y = (d1.y < FMIN) ? EPS32 : d1.y;
+      float2 o0 = mul2(own0, div_nr2(num0, d0));
+      float2 o1 = mul2(own1, div_nr2(num1, d1));
+      if (!upd) {                                       // converged restart: carried over unchanged; padding row: zero
+        o0 = cpy ? own0 : make_float2(0.f, 0.f);
+        o1 = cpy ? own1 : make_float2(0.f, 0.f);
+      }
+      outv[t] = make_float4(o0.x, o0.y, o1.x, o1.y);
+      acc[ch * 16 + 4 * t] = o0.x; acc[ch * 16 + 4 * t + 1] = o0.y;
+      acc[ch * 16 + 4 * t + 2] = o1.x; acc[ch * 16 + 4 * t + 3] = o1.y;
+    }
+    named_bar(bar_id, 128);                             // everybody has read the old rows
+#pragma unroll
+    for (int t = 0; t < 4; ++t) *reinterpret_cast<float4*>(Sr + 4 * t) = outv[t];
+    named_bar(bar_id, 128);                             // new rows of the chunk are published
+    if (want_gram) {
+#pragma unroll 2
+      for (int i = 0; i < Kl; ++i) {
+        const float4* sp = reinterpret_cast<const float4*>(S + (lr0 + i) * 20);
+        float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float4 w = sp[t];
+          s2 = fma2(make_float2(outv[t].x, outv[t].y), make_float2(w.x, w.y), s2);
+          s2 = fma2(make_float2(outv[t].z, outv[t].w), make_float2(w.z, w.w), s2);
+        }
+        gd[i] += static_cast<double>(s2.x + s2.y);
+      }
+    }
+    {                                                   // this warp's 32 rows x 16 items, 8 rows x 64 B per instruction
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = q * 32 + sub_r + 8 * j;
+        const float4 v = *reinterpret_cast<const float4*>(S + rr * 20 + sub_c);
+        const int grow2 = mt * BM + rr, gcol = col0 + ch * 16 + sub_c;
+        if (grow2 < M && gcol + 3 < ld) *reinterpret_cast<float4*>(pout + static_cast<long long>(grow2) * ld + gcol) = v;
+      }
+    }
+    named_bar(bar_id, 128);                             // staging free for the next chunk
+  }
+
+  if (want_gram) {                                      // the two column halves of a row meet in shared memory
+    named_bar(3, 256);
+    double* SD = reinterpret_cast<double*>(epi);        // 128 rows x 16 doubles (16 KB of the 20 KB patch area)
+    if (half == 1) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) SD[r * 16 + i] = gd[i];
+    }
+    named_bar(3, 256);
+    if (half == 0 && upd) {
+      const int KP = (K + 3) & ~3;                      // layout finalize_kernel reads: [c * KP + i]
+      double* dst = fz.gram_part + (static_cast<long long>(rid) * n_tiles + nt) * 256 + c * KP;
+      for (int i = 0; i < KP; ++i) dst[i] = (i < K) ? gd[i] + SD[r * 16 + i] : 0.0;
+    }
+    named_bar(3, 256);
+  }
+
+  // ---- fp16 operand pieces of the new values, group scale = power of two from the group maximum
+  float m = 0.f;
+  if (fz.piece_scale) {
+#pragma unroll
+    for (int j = 0; j < HALF; j += 4) {
+      float4 ps = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (col0 + j + 3 < ld) ps = *reinterpret_cast<const float4*>(fz.piece_scale + col0 + j);
+      acc[j] *= ps.x; acc[j + 1] *= ps.y; acc[j + 2] *= ps.z; acc[j + 3] *= ps.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < HALF; ++j) m = fmaxf(m, acc[j]);
+  const float sc = f16_group_scale(m);
+  const float inv = 1.f / sc;                           // power of two: exact
+  if (row_ok && col0 < ld) fz.tile_scale[static_cast<long long>(grow) * fz.n_groups + (col0 >> 7)] = sc;
+  __half* ph = static_cast<__half*>(fz.P_hi);
+  __half* pm = static_cast<__half*>(fz.P_mid);
+  uint32_t* Su = reinterpret_cast<uint32_t*>(Sr);
+  const int sub_q = lane & 3;
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {                      // 32 items = 64 B of halves per row and piece
+    uint32_t hi2[16], mid2[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const float x0 = acc[cc * 32 + 2 * e] * inv, x1 = acc[cc * 32 + 2 * e + 1] * inv;
+      const __half2 h = __floats2half2_rn(x0, x1);
+      const float2 hf = __half22float2(h);
+      const __half2 md = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+      hi2[e] = *reinterpret_cast<const uint32_t*>(&h);
+      mid2[e] = *reinterpret_cast<const uint32_t*>(&md);
+    }
+#pragma unroll
+    for (int pc = 0; pc < 2; ++pc) {
+      __syncwarp();
+#pragma unroll
+      for (int e = 0; e < 16; e += 4)
+        *reinterpret_cast<uint4*>(Su + e) = pc == 0 ? make_uint4(hi2[e], hi2[e + 1], hi2[e + 2], hi2[e + 3])
+                                                    : make_uint4(mid2[e], mid2[e + 1], mid2[e + 2], mid2[e + 3]);
+      __syncwarp();
+      __half* dstp = pc == 0 ? ph : pm;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = q * 32 + sub_r + 8 * j;
+        const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(S + rr * 20) + sub_q * 4);
+        const int grow2 = mt * BM + rr, gcol = col0 + cc * 32 + sub_q * 8;
+        if (grow2 < M && gcol + 7 < ld) *reinterpret_cast<uint4*>(dstp + static_cast<long long>(grow2) * ld + gcol) = v;
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------ the kernel
 // F16 (with BEXACT): operands are fp16 (two pieces of A, one exact B); a k-block is still 128 B per row = 64 elements,
 // a k-step still 32 B = 16 elements (UMMA_K of kind::f16), so the smem / TMA / descriptor byte geometry is unchanged.
@@ -223,13 +442,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // CUTLASS / DeepGEMM 2-SM kernels): `full` lives in rank 0 (both producers arrive on it, both CTAs' TMA bytes are
 // signalled on it), `empty` and `tfull` exist in both CTAs and are arrived by multicast commits, `tempty` lives in
 // rank 0 and is arrived by the accumulate warps of both CTAs.
-template <int BN, int STAGES, bool BEXACT, bool F16, bool CTA2>
+template <int BN, int STAGES, bool BEXACT, bool F16, bool CTA2, bool FUSE = false>
 __device__ __forceinline__ void
 gemm_body(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi, const CUtensorMap& tmB_lo,
           float* __restrict__ C, int M, int N, int ldc, long long c_split_stride,
           int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split, int chain_kb, int bn,
-          const float* __restrict__ out_scale, const float* __restrict__ a_tile_scale, int a_tiles) {
+          const float* __restrict__ out_scale, const float* __restrict__ a_tile_scale, int a_tiles, int a_gshift,
+          const FuseW* __restrict__ fz = nullptr) {
   static_assert(!F16 || BEXACT, "the fp16 path exists for exact integer B operands only");
+  static_assert(!FUSE || (F16 && !CTA2 && BN == 256), "the fused W-half epilogue is built for the kind::f16 1-CTA kernel");
   static_assert(!CTA2 || BEXACT, "the CTA-pair kernel is built for the exact-B (2-pass) forms");
   constexpr int BKE = F16 ? 2 * BK : BK;                        // elements per k-block
   using L = SmemLayout<BN, STAGES, BEXACT, CTA2>;
@@ -412,7 +633,7 @@ gemm_body(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMa
       const float* sc_row = (F16 && a_tile_scale && arow < M) ? a_tile_scale + static_cast<long long>(arow) * a_tiles : nullptr;
       for (int c0 = kb0; c0 < kb1; c0 += chain_kb) {
         float sc = 1.f;
-        if (F16 && sc_row) sc = sc_row[c0 >> 3];
+        if (F16 && sc_row) sc = sc_row[c0 >> a_gshift];
         mbar_wait(tfull_bar(buf), buf_phase, 3);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
@@ -437,6 +658,12 @@ gemm_body(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMa
           else mbar_arrive(tempty_bar(buf));
         }
         if (++buf == 2) { buf = 0; buf_phase ^= 1u; }
+      }
+      if constexpr (FUSE) {
+        // W-half update applied to the tile in registers; the product itself is never stored (gemm.h, struct FuseW)
+        fused_w_epilogue<HALF>(acc, *fz, M, mt, nt, n_tiles, q, half, lane, out_scale,
+                               reinterpret_cast<float*>(smem_gen + L::EPI_OFFSET));
+        continue;
       }
       // Epilogue.  A thread owns one output row, so a direct store touches 32 rows x 16 B per instruction (32 cache
       // lines: the LSU, not the tensor pipe, then paces short tiles -- the 720-tile W half ran at 0.76 of the MMA rate
@@ -495,9 +722,20 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    float* __restrict__ C, int M, int N, int ldc, long long c_split_stride,
                    int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split, int chain_kb, int bn,
-                   const float* __restrict__ out_scale, const float* __restrict__ a_tile_scale, int a_tiles) {
+                   const float* __restrict__ out_scale, const float* __restrict__ a_tile_scale, int a_tiles, int a_gshift) {
   gemm_body<BN, STAGES, BEXACT, F16, false>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, C, M, N, ldc, c_split_stride, m_tiles, n_tiles,
-                                            splits, total_kb, kb_per_split, chain_kb, bn, out_scale, a_tile_scale, a_tiles);
+                                            splits, total_kb, kb_per_split, chain_kb, bn, out_scale, a_tile_scale, a_tiles,
+                                            a_gshift);
+}
+
+// NUM = F_other * X^T with the multiplicative update of the row factor in the epilogue (kind::f16, 256-wide tiles, no split-K)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_fused_w_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, int M, int N,
+                    int m_tiles, int n_tiles, int total_kb, const float* __restrict__ out_scale,
+                    const float* __restrict__ a_tile_scale, int a_tiles, int a_gshift, const __grid_constant__ FuseW fz) {
+  gemm_body<256, 3, true, true, false, true>(tmA_hi, tmA_lo, tmB_hi, tmB_hi, nullptr, M, N, 0, 0, m_tiles, n_tiles, 1, total_kb,
+                                             total_kb + (total_kb & 1), 2, 256, out_scale, a_tile_scale, a_tiles, a_gshift, &fz);
 }
 
 // the CTA-pair form: clusters of two CTAs, m_tiles = number of 256-row tile pairs
@@ -507,9 +745,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                  const __grid_constant__ CUtensorMap tmB_hi,
                  float* __restrict__ C, int M, int N, int ldc, long long c_split_stride,
                  int m_tiles, int n_tiles, int splits, int total_kb, int kb_per_split, int chain_kb, int bn,
-                 const float* __restrict__ out_scale, const float* __restrict__ a_tile_scale, int a_tiles) {
+                 const float* __restrict__ out_scale, const float* __restrict__ a_tile_scale, int a_tiles, int a_gshift) {
   gemm_body<BN, STAGES, true, F16, true>(tmA_hi, tmA_lo, tmB_hi, tmB_hi, C, M, N, ldc, c_split_stride, m_tiles, n_tiles,
-                                         splits, total_kb, kb_per_split, chain_kb, bn, out_scale, a_tile_scale, a_tiles);
+                                         splits, total_kb, kb_per_split, chain_kb, bn, out_scale, a_tile_scale, a_tiles,
+                                         a_gshift);
 }
 
 // ------------------------------------------------------------------ host side
@@ -642,7 +881,35 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
   const int chain_kb = pick_chain_kb<BEXACT, F16>(g);
   kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(mAh, mAl, mBh, mBl, g.C, g.M, g.N, g.ldc, g.c_split_stride,
                                                     m_tiles, n_tiles, splits, total_kb, kb_per_split,
-                                                    chain_kb, bn, g.out_col_scale, g.a_tile_scale, g.a_tiles);
+                                                    chain_kb, bn, g.out_col_scale, g.a_tile_scale, g.a_tiles,
+                                                    g.a_group_kb_shift > 0 ? g.a_group_kb_shift : 3);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// fused W-half launch: 128 x 256 tiles, the whole reduction in one item (no split-K), kind::f16
+int launch_fused_w(const GemmArgs& g, cudaStream_t stream) {
+  using L = SmemLayout<256, 3, true>;
+  CUtensorMap mAh, mAl, mBh;
+  int rc;
+  if ((rc = make_map(&mAh, g.A_hi, g.M, g.Kd, g.lda, BM, true))) return rc;
+  if ((rc = make_map(&mAl, g.A_lo, g.M, g.Kd, g.lda, BM, true))) return rc;
+  if ((rc = make_map(&mBh, g.B_hi, g.N, g.Kd, g.ldb, 256, true))) return rc;
+  int dev = 0, sms = 0;
+  CNMF_CUDA_CHECK(cudaGetDevice(&dev));
+  CNMF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + 255) / 256;
+  const int total_kb = (g.Kd + 2 * BK - 1) / (2 * BK);
+  static bool attr_set[64] = {};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    CNMF_CUDA_CHECK(cudaFuncSetAttribute(gemm_fused_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const int items = m_tiles * n_tiles;
+  const int grid = items < sms ? items : sms;
+  gemm_fused_w_kernel<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(mAh, mAl, mBh, g.M, g.N, m_tiles, n_tiles, total_kb,
+                                                                   g.out_col_scale, g.a_tile_scale, g.a_tiles,
+                                                                   g.a_group_kb_shift > 0 ? g.a_group_kb_shift : 3, g.fuse);
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -706,7 +973,8 @@ int launch_pair(const GemmArgs& g, cudaStream_t stream) {
   const int chain_kb = pick_chain_kb<true, F16>(g);
   kern<<<2 * clusters, NUM_THREADS, L::DYN_BYTES, stream>>>(mAh, mAl, mBh, g.C, g.M, g.N, g.ldc, g.c_split_stride,
                                                             m_pairs, n_tiles, splits, total_kb, kb_per_split,
-                                                            chain_kb, bn, g.out_col_scale, g.a_tile_scale, g.a_tiles);
+                                                            chain_kb, bn, g.out_col_scale, g.a_tile_scale, g.a_tiles,
+                                                            g.a_group_kb_shift > 0 ? g.a_group_kb_shift : 3);
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -786,6 +1054,12 @@ int gemm_tf32x3(const GemmArgs& g, cudaStream_t stream) {
     CNMF_REQUIRE(g.lda % 8 == 0 && g.ldb % 8 == 0, "gemm: fp16 leading dimensions must be multiples of 8 halves");
     CNMF_REQUIRE(!g.a_tile_scale || g.a_tiles * 512 >= g.Kd, "gemm: a_tiles does not cover the reduction length");
     CNMF_REQUIRE(g.chain_kb == 0 || g.chain_kb == 2, "gemm: the fp16 path drains chains of 2 k-blocks");
+    if (g.fuse.active) {
+      CNMF_REQUIRE(g.fuse.F_in && g.fuse.F_out && g.fuse.F_in != g.fuse.F_out && g.fuse.P_hi && g.fuse.P_mid &&
+                       g.fuse.tile_scale && g.fuse.gram_in && g.fuse.row_slot && g.fuse.ld % 32 == 0,
+                   "gemm: incomplete fused-update arguments");
+      return launch_fused_w(g, stream);
+    }
     if (pair) return launch_pair<256, 4, true>(g, stream);
     return launch<256, 3, true, true>(g, stream);
   }

@@ -183,18 +183,9 @@ __global__ void sums_final_kernel(const double* __restrict__ part, int nblocks, 
 // The pieces are a pure function of the factor values: this stand-alone kernel (initial factors, re-packing after a
 // compaction, K > 16 batches) and the in-update emission (emit_tile_f16) produce the same bits, so a restart's
 // operands do not depend on when the batch around it was compacted.
-// One block per row, one warp per 512-column group, a lane owns four 16-byte quads of the group.
-__device__ __forceinline__ float f16_group_scale(float m) {
-  float sc = 1.f;
-  if (m > 0.f && m < 3.0e38f) {
-    int e;
-    frexpf(m, &e);                       // m = f * 2^e, f in [0.5, 1)
-    sc = ldexpf(1.f, max(e - 15, -126)); // m / sc in [2^14, 2^15); groups that decayed below 2^-111 (dead components
-                                         // of an over-specified K) keep a normal scale so that 1 / sc stays finite
-  }
-  return sc;
-}
-
+// One block per row, one warp per group of 128 * QUADS columns (512: what the update kernels' tiles emit; 128: what the
+// fused GEMM epilogue emits, one group per thread), a lane owns QUADS 16-byte quads of the group.
+template <int QUADS>
 __global__ void __launch_bounds__(256)
 emit_f16_kernel(const float* __restrict__ F, int n, int ld, const float* __restrict__ pscale, __half* __restrict__ hi,
                 __half* __restrict__ mid, float* __restrict__ tile_scale, int n_ktiles) {
@@ -202,11 +193,11 @@ emit_f16_kernel(const float* __restrict__ F, int n, int ld, const float* __restr
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* src = F + row * ld;
   for (int g = warp; g < n_ktiles; g += blockDim.x >> 5) {
-    const int t0 = g * 512;
-    float4 v[4];
+    const int t0 = g * (128 * QUADS);
+    float4 v[QUADS];
     float m = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < QUADS; ++j) {
       const int col = t0 + 4 * lane + 128 * j;
       v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (col < ld) {
@@ -224,7 +215,7 @@ emit_f16_kernel(const float* __restrict__ F, int n, int ld, const float* __restr
     const float inv = 1.f / sc;          // power of two: exact
     if (lane == 0) tile_scale[row * n_ktiles + g] = sc;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < QUADS; ++j) {
       const int col = t0 + 4 * lane + 128 * j;
       if (col < ld) {
         const float x0 = v[j].x * inv, x1 = v[j].y * inv, x2 = v[j].z * inv, x3 = v[j].w * inv;
@@ -1036,11 +1027,16 @@ int launch_split_scaled(const float* src, float* hi, float* lo, int rows, int ld
 }
 
 int launch_emit_f16(const float* F, int rows, int n, int ld, const float* pscale, void* hi, void* mid, float* tile_scale,
-                    int n_ktiles, cudaStream_t s) {
-  CNMF_REQUIRE(ld % 8 == 0 && n_ktiles * 512 >= ld, "emit_f16: bad ld / n_ktiles");
+                    int n_ktiles, cudaStream_t s, int group) {
+  CNMF_REQUIRE(group == 512 || group == 128, "emit_f16: scale groups hold 512 or 128 elements");
+  CNMF_REQUIRE(ld % 8 == 0 && (long long)n_ktiles * group >= ld, "emit_f16: bad ld / n_ktiles");
   if (rows <= 0) return 0;
-  emit_f16_kernel<<<rows, 256, 0, s>>>(F, n, ld, pscale, static_cast<__half*>(hi), static_cast<__half*>(mid), tile_scale,
-                                       n_ktiles);
+  if (group == 512)
+    emit_f16_kernel<4><<<rows, 256, 0, s>>>(F, n, ld, pscale, static_cast<__half*>(hi), static_cast<__half*>(mid), tile_scale,
+                                            n_ktiles);
+  else
+    emit_f16_kernel<1><<<rows, 256, 0, s>>>(F, n, ld, pscale, static_cast<__half*>(hi), static_cast<__half*>(mid), tile_scale,
+                                            n_ktiles);
   CNMF_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
