@@ -79,6 +79,7 @@ SIGNATURES = {
     "cnmf_gather_rows": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _i, _vp]),
     "cnmf_sq_dists_to_rows": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "cnmf_kmeans_step": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _pp(_c.c_int32), _pp(_c.c_int32), _pp(_d), _vp]),
+    "cnmf_kmeans_fit": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _d, _vp, _vp, _i, _vp, _vp, _vp, _pp(_c.c_int32), _vp]),
     "cnmf_kmeans_assign": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cnmf_cluster_dist_sums": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "cnmf_cluster_median": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp]),

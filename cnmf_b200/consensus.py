@@ -125,23 +125,63 @@ def _same_clustering(l1, l2, k):
     return True
 
 
+def _kmeans_draws(rng, n, k, n_init):
+    """The random numbers k-means++ consumes, in sklearn's order (SK/cluster/_kmeans.py:231, 249-251): per run one
+    rng.choice(n, p=uniform) for the first centre, then rng.uniform(size=n_local_trials) per further centre.  They do not
+    depend on the data, so the whole fit can run on the device without handing control back for a draw."""
+    n_trials = 2 + int(np.log(k))
+    w = np.ones(n)
+    first = np.empty(n_init, np.int32)
+    unif = np.empty((n_init, max(k - 1, 1), n_trials), np.float64)
+    for t in range(n_init):
+        first[t] = rng.choice(n, p=w / w.sum())
+        for c in range(k - 1):
+            unif[t, c] = rng.uniform(size=n_trials)
+    return first, unif, n_trials
+
+
 def kmeans(S, k, n_init=10, random_state=1, max_iter=300, tol=1e-4):
     """KMeans(n_clusters=k, n_init=10, random_state=1).fit(l2_spectra).labels_ (cnmf.py:908-910).
-    Returns (labels int32 numpy, labels device tensor, inertia, centers)."""
+    Returns (labels int32 numpy, labels device tensor, inertia, centers or None).
+
+    Default path: ONE library call (cnmf_kmeans_fit) -- k-means++ and Lloyd for all n_init runs resident on the device,
+    the host only pre-draws the random numbers and applies sklearn's best-run rule.  When a cluster comes out empty
+    (sklearn's relocation rule) the per-run host-assisted path below is used instead."""
+    torch = _torch()
+    lib, h = S.lib, S.engine._h
+    G, R = S.G, S.R
+    # tolerance: mean of the per-feature variances * tol (sklearn _kmeans.py:285-293)
+    mean = np.empty(G)
+    var = np.empty(G)
+    check(lib.cnmf_col_stats_dev(h, S.p, R, G, S.ld, ptr(mean), ptr(var), None))
+    tol_abs = float(var.mean()) * tol
+    if k <= 32 and n_init <= 32 and R * 8 <= 200 * 1024:
+        rng = np.random.RandomState(random_state)
+        first, unif, n_trials = _kmeans_draws(rng, R, k, n_init)
+        labels_all = np.empty((n_init, R), np.int32)
+        inertia = np.empty(n_init, np.float64)
+        n_it = np.zeros(n_init, np.int32)
+        fallback = ctypes.c_int32(0)
+        check(lib.cnmf_kmeans_fit(h, S.p, R, G, S.ld, int(k), int(n_init), int(max_iter), tol_abs, ptr(first), ptr(unif),
+                                  int(n_trials), ptr(labels_all), ptr(inertia), ptr(n_it), ctypes.byref(fallback), None))
+        if not fallback.value:
+            STATS["lloyd_iters"] = STATS.get("lloyd_iters", 0) + int(n_it.sum())
+            best = None
+            for t in range(n_init):            # sklearn _kmeans.py:1534-1541
+                if best is None or (inertia[t] < best[1] and not _same_clustering(labels_all[t], best[0], k)):
+                    best = (labels_all[t], float(inertia[t]))
+            labels_t = torch.from_numpy(np.ascontiguousarray(best[0])).to(S.t.device)
+            return best[0].copy(), labels_t, best[1], None
+    return _kmeans_per_run(S, k, n_init, random_state, max_iter, tol_abs)
+
+
+def _kmeans_per_run(S, k, n_init, random_state, max_iter, tol_abs):
+    """One run at a time, k-means++ draws and the empty-cluster relocation rule on the host (sklearn
+    _k_means_common.pyx:167-211), distances and Lloyd steps on the device."""
     torch = _torch()
     lib, h = S.lib, S.engine._h
     rng = np.random.RandomState(random_state)
     G, R = S.G, S.R
-    # tolerance: mean of the per-feature variances * tol (sklearn _kmeans.py:285-293)
-    host = S.numpy().astype(np.float64) if R * G <= (1 << 22) else None
-    if host is not None:
-        var_mean = float(np.mean(np.var(host, axis=0)))
-    else:
-        mean = np.empty(G)
-        var = np.empty(G)
-        check(lib.cnmf_col_stats_dev(h, S.p, R, G, S.ld, ptr(mean), ptr(var), None))
-        var_mean = float(var.mean())
-    tol_abs = var_mean * tol
 
     dev = S.t.device
     labels_t = torch.empty(R, dtype=torch.int32, device=dev)

@@ -56,7 +56,7 @@ constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;   // ~2 s: a dead pipeli
 // CTA2: a pair of CTAs (one cluster, two SMs of a TPC) works on a 256 x BN tile with tcgen05.mma.cta_group::2: each CTA
 // stages its own 128 rows of A and HALF of the B tile, so the operand bytes every SM pulls from L2 per MMA cycle drop
 // from 64 KB to 48 KB per k-block -- the feed the 1-CTA kernel is bound by (profiles/r1i_ncu_f16_summary.txt).
-template <int BN, int STAGES, bool BEXACT, bool CTA2 = false>
+template <int BN, int STAGES, bool BEXACT, bool CTA2 = false, int EPI_BYTES_OVERRIDE = 0>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 4;              // 16 KB
   static constexpr int B_BYTES = (CTA2 ? BN / 2 : BN) * BK * 4;
@@ -65,7 +65,7 @@ struct SmemLayout {
   static constexpr int BAR_OFFSET = TILE_BYTES;            // full[STAGES], empty[STAGES], tfull[2], tempty[2]
   static constexpr int TMEM_PTR_OFFSET = BAR_OFFSET + (2 * STAGES + 4) * 8;
   static constexpr int EPI_OFFSET = TMEM_PTR_OFFSET + 16;   // per accumulate warp: 32 x 20-float transpose patch
-  static constexpr int EPI_BYTES = NUM_EPI_WARPS * 32 * 20 * 4;
+  static constexpr int EPI_BYTES = EPI_BYTES_OVERRIDE > 0 ? EPI_BYTES_OVERRIDE : NUM_EPI_WARPS * 32 * 20 * 4;
   static constexpr int TOTAL = EPI_OFFSET + EPI_BYTES;
   static constexpr int DYN_BYTES = TOTAL + 1024;           // slack for manual 1024 B alignment
 };
@@ -215,29 +215,48 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ------------------------------------------------------------------ fused W-half epilogue
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;                       // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// shared memory of the fused epilogue (after the pipeline stages and barriers): a staging area of 128 rows x 36 floats per
+// column half, and per accumulate thread its row of the other factor's Gram (16 floats) and of the new Gram (16 doubles)
+constexpr int FUSE_SROW = 36;                                        // floats per staging row (32 items + pad: conflict-free)
+constexpr int FUSE_STAGING_BYTES = 2 * 128 * FUSE_SROW * 4;          // 36 864
+constexpr int FUSE_G_BYTES = 16 * 256 * 4;                           // 16 384
+constexpr int FUSE_GD_BYTES = 16 * 256 * 8;                          // 32 768
+constexpr int FUSE_EPI_BYTES = FUSE_STAGING_BYTES + FUSE_G_BYTES + FUSE_GD_BYTES;
 
 // The multiplicative update of the row factor, applied to the product tile while it is still in registers (struct
 // FuseW in gemm.h).  Thread = packed row (o + c) of a restart x the 128 items of one scale group; acc[] holds the
 // numerators on entry and the new factor values on exit.  The 128 threads that share a column half exchange rows
-// through their four transpose patches (a 128 x 20-float staging area): per 16-item chunk every thread publishes the
-// OLD values of its row, reads the K rows of its restart (den = sum_i Gram[c, i] F[o + i, item]), publishes the NEW
-// values, accumulates its row of the restart's K x K Gram of the new values (fp32 over the chunk's 16 items, fp64
-// across chunks -- the same summation granularity as the stand-alone update kernel) and the warp stores its 32 rows of
-// the chunk coalesced.  Restarts never straddle a 128-row tile (the engine packs them that way), so every row a thread
-// needs is in the staging area.  Afterwards the thread emits the two fp16 operand pieces of its 128 values with the
-// power-of-two scale of the group: the same bits emit_f16_kernel would produce from F_out.
+// through a shared-memory staging area: per 32-item chunk every thread publishes the OLD values of its row (cp.async
+// straight from global memory), reads the K rows of its restart (den = sum_i Gram[c, i] F[o + i, item]), publishes the
+// NEW values, accumulates its row of the restart's K x K Gram of the new values (fp32 over 16 items, fp64 beyond: the
+// summation granularity of the stand-alone update kernel) and the warp stores its 32 rows of the chunk coalesced.
+// Restarts never straddle a 128-row tile (the engine packs them that way), so every row a thread needs is in the
+// staging area.  All per-thread state that is indexed by the component lives in shared memory, the component loops are
+// rolled (small code, no local memory: with ~200 KB of shared memory per CTA the L1 is too small to hold spills).
+// Afterwards the thread emits the two fp16 operand pieces of its 128 values with the power-of-two scale of the group:
+// the same bits emit_f16_kernel would produce from F_out.
 template <int HALF>
 __device__ __forceinline__ void fused_w_epilogue(float (&acc)[HALF], const FuseW& fz, int M, int mt, int nt, int n_tiles,
                                                  int q, int half, int lane, const float* __restrict__ out_scale,
-                                                 float* epi) {
+                                                 uint8_t* epi) {
   static_assert(HALF == 128, "one thread owns one 128-item scale group");
   constexpr float EPS32 = 1.1920928955078125e-07f;     // np.finfo(np.float32).eps, sklearn _nmf.py:32
   constexpr float FMIN = 1.17549435e-38f;
+  constexpr int SR = FUSE_SROW;
   const int r = q * 32 + lane;                          // row inside the 128-row tile
+  const int tid = half * 128 + r;                       // accumulate-thread index 0..255
   const int grow = mt * BM + r;
   const int col0 = nt * 256 + half * HALF;              // first item of this thread's group (tile width 256)
-  float* S = epi + half * (128 * 20);                   // staging of this column half
-  float* Sr = S + r * 20;
+  float* S = reinterpret_cast<float*>(epi) + half * (128 * SR);     // staging of this column half
+  float* Sr = S + r * SR;
+  float* gs = reinterpret_cast<float*>(epi + FUSE_STAGING_BYTES) + tid;                       // gs[i * 256]
+  double* gd = reinterpret_cast<double*>(epi + FUSE_STAGING_BYTES + FUSE_G_BYTES) + tid;      // gd[i * 256]
   const int bar_id = 1 + half;
   const int ld = fz.ld;
 
@@ -254,15 +273,18 @@ __device__ __forceinline__ void fused_w_epilogue(float (&acc)[HALF], const FuseW
   const int c = grow - o;
   const int lr0 = o - mt * BM;                          // tile-local row of the restart's first component
   const int Kl = upd ? K : 0;
-  float g[16];                                          // row c of the other factor's Gram (dynamic index: local memory)
-#pragma unroll
-  for (int i = 0; i < 16; ++i)
-    g[i] = (i < Kl) ? static_cast<float>(fz.gram_in[static_cast<long long>(rid) * (KMAX * KMAX) + c * KMAX + i]) : 0.f;
-  double gd[16];                                        // row c of the Gram of the new values
   const bool want_gram = fz.gram_part != nullptr;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) gd[i] = 0.0;
+  const bool row_ok = grow < M;
+  const float* pin = fz.F_in + static_cast<long long>(row_ok ? grow : 0) * ld + col0;
+  const uint32_t sr_addr = smem_u32(Sr);
 
+  // old values of the first chunk on their way while the per-thread state is set up
+#pragma unroll
+  for (int t = 0; t < 8; ++t) cp_async16(sr_addr + 16 * t, pin + 4 * t, row_ok && col0 + 4 * t + 3 < ld);
+  for (int i = 0; i < 16; ++i) {
+    gs[i * 256] = (i < Kl) ? static_cast<float>(fz.gram_in[static_cast<long long>(rid) * (KMAX * KMAX) + c * KMAX + i]) : 0.f;
+    gd[i * 256] = 0.0;
+  }
   if (out_scale) {                                      // per-item scale of the product (exact-count datasets)
 #pragma unroll
     for (int j = 0; j < HALF; j += 4) {
@@ -272,109 +294,97 @@ __device__ __forceinline__ void fused_w_epilogue(float (&acc)[HALF], const FuseW
       }
     }
   }
-
-  const bool row_ok = grow < M;
-  const float* pin = fz.F_in + static_cast<long long>(row_ok ? grow : 0) * ld + col0;
   float* pout = fz.F_out;
-  const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;
-  float4 wn[4];
-#pragma unroll
-  for (int t = 0; t < 4; ++t)
-    wn[t] = (row_ok && col0 + 4 * t + 3 < ld) ? *reinterpret_cast<const float4*>(pin + 4 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;  // coalesced store: 4 rows x 128 B per instruction
 
 #pragma unroll
-  for (int ch = 0; ch < 8; ++ch) {
-    float4 wc[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      wc[t] = wn[t];
-      *reinterpret_cast<float4*>(Sr + 4 * t) = wc[t];
-    }
-    if (ch < 7) {                                       // next chunk of the own row (in flight under this chunk's math)
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int cc = (ch + 1) * 16 + 4 * t;
-        wn[t] = (row_ok && col0 + cc + 3 < ld) ? *reinterpret_cast<const float4*>(pin + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
+  for (int ch = 0; ch < 4; ++ch) {                      // 32 items per chunk
+    cp_async_wait_all();
     named_bar(bar_id, 128);                             // old rows of the chunk are published
-    float2 den[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) den[t] = make_float2(0.f, 0.f);
+    for (int hh = 0; hh < 2; ++hh) {                    // 16 items at a time (register budget)
+      float2 den[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) den[t] = make_float2(0.f, 0.f);
 #pragma unroll 2
-    for (int i = 0; i < Kl; ++i) {                      // summed in component order, like the reference's W @ HHt row
-      const float2 gi = bcast2(g[i]);
-      const float4* sp = reinterpret_cast<const float4*>(S + (lr0 + i) * 20);
+      for (int i = 0; i < Kl; ++i) {                    // summed in component order, like the reference's W @ HHt row
+        const float2 gi = bcast2(gs[i * 256]);
+        const float4* sp = reinterpret_cast<const float4*>(S + (lr0 + i) * SR + hh * 16);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float4 w = sp[t];
+          den[2 * t] = fma2(gi, make_float2(w.x, w.y), den[2 * t]);
+          den[2 * t + 1] = fma2(gi, make_float2(w.z, w.w), den[2 * t + 1]);
+        }
+      }
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float4 w = sp[t];
-        den[2 * t] = fma2(gi, make_float2(w.x, w.y), den[2 * t]);
-        den[2 * t + 1] = fma2(gi, make_float2(w.z, w.w), den[2 * t + 1]);
+        const float4 own = *reinterpret_cast<const float4*>(Sr + hh * 16 + 4 * t);
+        const int j = ch * 32 + hh * 16 + 4 * t;
+        const float2 own0 = make_float2(own.x, own.y), own1 = make_float2(own.z, own.w);
+        const float2 num0 = make_float2(acc[j], acc[j + 1]), num1 = make_float2(acc[j + 2], acc[j + 3]);
+        // regularisation terms unconditionally (adding 0 is exact); zero denominators -> eps (sklearn _nmf.py:615)
+        float2 d0 = fma2(bcast2(fz.l2), own0, add2(den[2 * t], bcast2(fz.l1)));
+        float2 d1 = fma2(bcast2(fz.l2), own1, add2(den[2 * t + 1], bcast2(fz.l1)));
+        d0.x = (d0.x < FMIN) ? EPS32 : d0.x; d0.y = (d0.y < FMIN) ? EPS32 : d0.y;
+        d1.x = (d1.x < FMIN) ? EPS32 : d1.x; d1.y = (d1.y < FMIN) ? EPS32 : d1.y;
+        float2 o0 = mul2(own0, div_nr2(num0, d0));
+        float2 o1 = mul2(own1, div_nr2(num1, d1));
+        if (!upd) {                                     // converged restart: carried over unchanged; padding row: zero
+          o0 = cpy ? own0 : make_float2(0.f, 0.f);
+          o1 = cpy ? own1 : make_float2(0.f, 0.f);
+        }
+        acc[j] = o0.x; acc[j + 1] = o0.y; acc[j + 2] = o1.x; acc[j + 3] = o1.y;
       }
-    }
-    float4 outv[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float2 own0 = make_float2(wc[t].x, wc[t].y), own1 = make_float2(wc[t].z, wc[t].w);
-      const float2 num0 = make_float2(acc[ch * 16 + 4 * t], acc[ch * 16 + 4 * t + 1]);
-      const float2 num1 = make_float2(acc[ch * 16 + 4 * t + 2], acc[ch * 16 + 4 * t + 3]);
-      // regularisation terms unconditionally (adding 0 is exact); zero denominators -> eps (sklearn _nmf.py:615)
-      float2 d0 = fma2(bcast2(fz.l2), own0, add2(den[2 * t], bcast2(fz.l1)));
-      float2 d1 = fma2(bcast2(fz.l2), own1, add2(den[2 * t + 1], bcast2(fz.l1)));
-      d0.x = (d0.x < FMIN) ? EPS32 : d0.x; d0.y = (d0.y < FMIN) ? EPS32 : d0.y;
-      d1.x = (d1.x < FMIN) ? EPS32 : d1.x; d1.y = (d1.y < FMIN) ? EPS32 : d1.y;
-      float2 o0 = mul2(own0, div_nr2(num0, d0));
-      float2 o1 = mul2(own1, div_nr2(num1, d1));
-      if (!upd) {                                       // converged restart: carried over unchanged; padding row: zero
-        o0 = cpy ? own0 : make_float2(0.f, 0.f);
-        o1 = cpy ? own1 : make_float2(0.f, 0.f);
-      }
-      outv[t] = make_float4(o0.x, o0.y, o1.x, o1.y);
-      acc[ch * 16 + 4 * t] = o0.x; acc[ch * 16 + 4 * t + 1] = o0.y;
-      acc[ch * 16 + 4 * t + 2] = o1.x; acc[ch * 16 + 4 * t + 3] = o1.y;
     }
     named_bar(bar_id, 128);                             // everybody has read the old rows
 #pragma unroll
-    for (int t = 0; t < 4; ++t) *reinterpret_cast<float4*>(Sr + 4 * t) = outv[t];
+    for (int t = 0; t < 8; ++t)
+      *reinterpret_cast<float4*>(Sr + 4 * t) = make_float4(acc[ch * 32 + 4 * t], acc[ch * 32 + 4 * t + 1],
+                                                           acc[ch * 32 + 4 * t + 2], acc[ch * 32 + 4 * t + 3]);
     named_bar(bar_id, 128);                             // new rows of the chunk are published
     if (want_gram) {
 #pragma unroll 2
       for (int i = 0; i < Kl; ++i) {
-        const float4* sp = reinterpret_cast<const float4*>(S + (lr0 + i) * 20);
-        float2 s2 = make_float2(0.f, 0.f);
+        const float4* sp = reinterpret_cast<const float4*>(S + (lr0 + i) * SR);
+        float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);   // two 16-item partial sums
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const float4 w = sp[t];
-          s2 = fma2(make_float2(outv[t].x, outv[t].y), make_float2(w.x, w.y), s2);
-          s2 = fma2(make_float2(outv[t].z, outv[t].w), make_float2(w.z, w.w), s2);
+          const float4 w = sp[t], w2 = sp[t + 4];
+          const int j = ch * 32 + 4 * t;
+          sa = fma2(make_float2(acc[j], acc[j + 1]), make_float2(w.x, w.y), sa);
+          sa = fma2(make_float2(acc[j + 2], acc[j + 3]), make_float2(w.z, w.w), sa);
+          sb = fma2(make_float2(acc[j + 16], acc[j + 17]), make_float2(w2.x, w2.y), sb);
+          sb = fma2(make_float2(acc[j + 18], acc[j + 19]), make_float2(w2.z, w2.w), sb);
         }
-        gd[i] += static_cast<double>(s2.x + s2.y);
+        gd[i * 256] += static_cast<double>(sa.x + sa.y) + static_cast<double>(sb.x + sb.y);
       }
     }
-    {                                                   // this warp's 32 rows x 16 items, 8 rows x 64 B per instruction
+    {                                                   // this warp's 32 rows x 32 items, 4 rows x 128 B per instruction
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int rr = q * 32 + sub_r + 8 * j;
-        const float4 v = *reinterpret_cast<const float4*>(S + rr * 20 + sub_c);
-        const int grow2 = mt * BM + rr, gcol = col0 + ch * 16 + sub_c;
+      for (int j = 0; j < 8; ++j) {
+        const int rr = q * 32 + sub_r + 4 * j;
+        const float4 v = *reinterpret_cast<const float4*>(S + rr * SR + sub_c);
+        const int grow2 = mt * BM + rr, gcol = col0 + ch * 32 + sub_c;
         if (grow2 < M && gcol + 3 < ld) *reinterpret_cast<float4*>(pout + static_cast<long long>(grow2) * ld + gcol) = v;
       }
     }
     named_bar(bar_id, 128);                             // staging free for the next chunk
+    if (ch < 3) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int cc = (ch + 1) * 32 + 4 * t;
+        cp_async16(sr_addr + 16 * t, pin + cc, row_ok && col0 + cc + 3 < ld);
+      }
+    }
   }
 
   if (want_gram) {                                      // the two column halves of a row meet in shared memory
     named_bar(3, 256);
-    double* SD = reinterpret_cast<double*>(epi);        // 128 rows x 16 doubles (16 KB of the 20 KB patch area)
-    if (half == 1) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) SD[r * 16 + i] = gd[i];
-    }
-    named_bar(3, 256);
     if (half == 0 && upd) {
       const int KP = (K + 3) & ~3;                      // layout finalize_kernel reads: [c * KP + i]
       double* dst = fz.gram_part + (static_cast<long long>(rid) * n_tiles + nt) * 256 + c * KP;
-      for (int i = 0; i < KP; ++i) dst[i] = (i < K) ? gd[i] + SD[r * 16 + i] : 0.0;
+      for (int i = 0; i < KP; ++i) dst[i] = (i < K) ? gd[i * 256] + gd[i * 256 + 128] : 0.0;
     }
     named_bar(3, 256);
   }
@@ -397,32 +407,35 @@ __device__ __forceinline__ void fused_w_epilogue(float (&acc)[HALF], const FuseW
   __half* ph = static_cast<__half*>(fz.P_hi);
   __half* pm = static_cast<__half*>(fz.P_mid);
   uint32_t* Su = reinterpret_cast<uint32_t*>(Sr);
-  const int sub_q = lane & 3;
+  const int sub_r8 = lane >> 2, sub_q = lane & 3;       // 8 rows x 64 B per instruction
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) {                      // 32 items = 64 B of halves per row and piece
-    uint32_t hi2[16], mid2[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const float x0 = acc[cc * 32 + 2 * e] * inv, x1 = acc[cc * 32 + 2 * e + 1] * inv;
-      const __half2 h = __floats2half2_rn(x0, x1);
-      const float2 hf = __half22float2(h);
-      const __half2 md = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-      hi2[e] = *reinterpret_cast<const uint32_t*>(&h);
-      mid2[e] = *reinterpret_cast<const uint32_t*>(&md);
-    }
 #pragma unroll
     for (int pc = 0; pc < 2; ++pc) {
       __syncwarp();
 #pragma unroll
-      for (int e = 0; e < 16; e += 4)
-        *reinterpret_cast<uint4*>(Su + e) = pc == 0 ? make_uint4(hi2[e], hi2[e + 1], hi2[e + 2], hi2[e + 3])
-                                                    : make_uint4(mid2[e], mid2[e + 1], mid2[e + 2], mid2[e + 3]);
+      for (int e = 0; e < 16; e += 4) {
+        uint32_t u[4];
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const float x0 = acc[cc * 32 + 2 * (e + k2)] * inv, x1 = acc[cc * 32 + 2 * (e + k2) + 1] * inv;
+          const __half2 h = __floats2half2_rn(x0, x1);
+          if (pc == 0) {
+            u[k2] = *reinterpret_cast<const uint32_t*>(&h);
+          } else {
+            const float2 hf = __half22float2(h);
+            const __half2 md = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+            u[k2] = *reinterpret_cast<const uint32_t*>(&md);
+          }
+        }
+        *reinterpret_cast<uint4*>(Su + e) = make_uint4(u[0], u[1], u[2], u[3]);
+      }
       __syncwarp();
       __half* dstp = pc == 0 ? ph : pm;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int rr = q * 32 + sub_r + 8 * j;
-        const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(S + rr * 20) + sub_q * 4);
+        const int rr = q * 32 + sub_r8 + 8 * j;
+        const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(S + rr * SR) + sub_q * 4);
         const int grow2 = mt * BM + rr, gcol = col0 + cc * 32 + sub_q * 8;
         if (grow2 < M && gcol + 7 < ld) *reinterpret_cast<uint4*>(dstp + static_cast<long long>(grow2) * ld + gcol) = v;
       }
@@ -453,7 +466,7 @@ gemm_body(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMa
   static_assert(!FUSE || (F16 && !CTA2 && BN == 256), "the fused W-half epilogue is built for the kind::f16 1-CTA kernel");
   static_assert(!CTA2 || BEXACT, "the CTA-pair kernel is built for the exact-B (2-pass) forms");
   constexpr int BKE = F16 ? 2 * BK : BK;                        // elements per k-block
-  using L = SmemLayout<BN, STAGES, BEXACT, CTA2>;
+  using L = SmemLayout<BN, STAGES, BEXACT, CTA2, FUSE ? FUSE_EPI_BYTES : 0>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024 B alignment
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -661,8 +674,7 @@ gemm_body(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMa
       }
       if constexpr (FUSE) {
         // W-half update applied to the tile in registers; the product itself is never stored (gemm.h, struct FuseW)
-        fused_w_epilogue<HALF>(acc, *fz, M, mt, nt, n_tiles, q, half, lane, out_scale,
-                               reinterpret_cast<float*>(smem_gen + L::EPI_OFFSET));
+        fused_w_epilogue<HALF>(acc, *fz, M, mt, nt, n_tiles, q, half, lane, out_scale, smem_gen + L::EPI_OFFSET);
         continue;
       }
       // Epilogue.  A thread owns one output row, so a direct store touches 32 rows x 16 B per instruction (32 cache
@@ -734,7 +746,7 @@ gemm_fused_w_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     const __grid_constant__ CUtensorMap tmB_hi, int M, int N,
                     int m_tiles, int n_tiles, int total_kb, const float* __restrict__ out_scale,
                     const float* __restrict__ a_tile_scale, int a_tiles, int a_gshift, const __grid_constant__ FuseW fz) {
-  gemm_body<256, 3, true, true, false, true>(tmA_hi, tmA_lo, tmB_hi, tmB_hi, nullptr, M, N, 0, 0, m_tiles, n_tiles, 1, total_kb,
+  gemm_body<256, 2, true, true, false, true>(tmA_hi, tmA_lo, tmB_hi, tmB_hi, nullptr, M, N, 0, 0, m_tiles, n_tiles, 1, total_kb,
                                              total_kb + (total_kb & 1), 2, 256, out_scale, a_tile_scale, a_tiles, a_gshift, &fz);
 }
 
@@ -889,7 +901,8 @@ int launch(const GemmArgs& g, cudaStream_t stream) {
 
 // fused W-half launch: 128 x 256 tiles, the whole reduction in one item (no split-K), kind::f16
 int launch_fused_w(const GemmArgs& g, cudaStream_t stream) {
-  using L = SmemLayout<256, 3, true>;
+  using L = SmemLayout<256, 2, true, false, FUSE_EPI_BYTES>;     // 2 stages of 64 KB leave room for the epilogue's state
+  static_assert(L::DYN_BYTES <= 227 * 1024, "fused epilogue state does not fit the shared memory of an SM");
   CUtensorMap mAh, mAl, mBh;
   int rc;
   if ((rc = make_map(&mAh, g.A_hi, g.M, g.Kd, g.lda, BM, true))) return rc;

@@ -114,10 +114,13 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
   }
   int R = R0, SK = SK0;     // live slots / live packed rows
   const int kp = kmax <= 16 ? 16 : 32;
-  // MU, f16x2, K <= 16, both factors iterated, whole gene reduction in one slice: the W-half update runs in the epilogue
-  // of its own GEMM (gemm.h, struct FuseW) and the product NUM_r is never materialised.  CNMF_FUSE_W=0 keeps the
-  // separate update kernel (A/B comparison).
-  static const bool env_fuse_w = [] { const char* e = std::getenv("CNMF_FUSE_W"); return !(e && e[0] == '0'); }();
+  // MU, f16x2, K <= 16, both factors iterated, whole gene reduction in one slice: the W-half update can run in the
+  // epilogue of its own GEMM (gemm.h, struct FuseW) so that the product NUM_r is never materialised.  Parity-green
+  // (same n_iter, same accuracy class) but MEASURED SLOWER than GEMM + separate update kernel (c3: 715 vs 870
+  // restarts/s, run r2f): the epilogue's ~50 k warp-instructions per tile run on the 8 accumulate warps only (2 per
+  // scheduler, 168 registers of which 128 hold the tile) and do not overlap the tensor pipe beyond the two TMEM chain
+  // buffers.  Opt-in with CNMF_FUSE_W=1 until the update runs as a third warp role under the next tile's main loop.
+  static const bool env_fuse_w = [] { const char* e = std::getenv("CNMF_FUSE_W"); return e && e[0] == '1'; }();
   const bool fuse_w = env_fuse_w && f16 && mu && kp == 16 && io.update_cols && gemm_fixed_splits(v.n_c, 1) == 1;
   // packing rule of the fused path: a restart never straddles a 128-row GEMM tile (its K rows meet in one CTA's
   // epilogue); padding rows hold zeros.  The caller's buffers stay in the unpadded layout (off0).
@@ -187,18 +190,14 @@ int solve_batched(cnmf_handle_s* h, const DataView& v, SolveIO& io, const cnmf_n
     return 0;
   };
   plan_gemms();
-  // size the product buffers for the worst case over all compaction states (splits <= 32 but bounded by SK0 rows)
+  // size the product buffers: the split-K factor depends on the reduction length only, the rows never exceed SKcap
+  // (padded packing of the fused path included)
   {
-    size_t need_r = 0, need_c = 0;
-    for (int sk = SK0; sk >= 1; sk -= (io.update_cols ? 1 : SK0)) {   // every SK a compaction can produce
-      GemmPlan a, b2;
-      plan_one(sk, v.n_r, v.n_c, &a);
-      plan_one(sk, v.n_c, v.n_r, &b2);
-      need_r = std::max(need_r, (size_t)a.splits * (size_t)sk * v.ld_r);
-      need_c = std::max(need_c, (size_t)b2.splits * (size_t)sk * v.ld_c);
-    }
-    need_r = std::max(need_r, (size_t)plan_r.splits * (size_t)plan_r.split_stride);
-    need_c = std::max(need_c, (size_t)plan_c.splits * (size_t)plan_c.split_stride);
+    GemmPlan a, b2;
+    plan_one(SKcap, v.n_r, v.n_c, &a);
+    plan_one(SKcap, v.n_c, v.n_r, &b2);
+    const size_t need_r = (size_t)a.splits * (size_t)SKcap * v.ld_r;
+    const size_t need_c = (size_t)b2.splits * (size_t)SKcap * v.ld_c;
     NUMr = fuse_w ? nullptr : static_cast<float*>(h->dev_buf("solve.NUMr", sizeof(float) * need_r));
     NUMc = io.update_cols ? static_cast<float*>(h->dev_buf("solve.NUMc", sizeof(float) * need_c)) : nullptr;
     if ((!fuse_w && !NUMr) || (io.update_cols && !NUMc)) return -2;

@@ -235,6 +235,20 @@ int cnmf_kmeans_step(cnmf_handle_t h, const float* S_dev, int R, int G, int ld, 
                      const double* C64_cur_dev, double* C64_new_dev, float* C32_new_dev, int32_t* labels_dev,
                      float* mind_dev, double* sums_dev, int32_t* counts_dev, int32_t* n_changed_host,
                      int32_t* any_empty_host, double* shift_host, void* stream);
+/* The whole KMeans(n_clusters=K, n_init, random_state) fit of the consensus step (cnmf.py:908-910) with every
+ * initialisation resident and advancing together on the device: k-means++ for all runs (2 launches per centre, no
+ * host round trip), Lloyd for all runs (one small flag read per iteration), final E step + inertia.  The random
+ * draws are data-independent in count and order, so the caller draws them from numpy's legacy RandomState exactly
+ * as sklearn would and passes them in: first_idx_host[n_init] (rng.choice per run) and uniforms_host
+ * [n_init][K-1][n_trials] (rng.uniform(size=n_trials) per further centre, n_trials = 2 + int(log(K))), in sklearn's
+ * order of consumption (run by run).  tol_abs = mean feature variance * tol (sklearn _kmeans.py:285-293).
+ * Outputs per run: labels (n_init x R), inertia, iterations; the caller applies sklearn's best-run rule
+ * (_kmeans.py:1534-1541).  *needs_host_path = 1 when a cluster came out empty (sklearn's relocation rule,
+ * _k_means_common.pyx:167-211): outputs are then undefined and the caller falls back to cnmf_kmeans_step. */
+int cnmf_kmeans_fit(cnmf_handle_t h, const float* S_dev, int R, int G, int ld, int K, int n_init, int max_iter,
+                    double tol_abs, const int32_t* first_idx_host, const double* uniforms_host, int n_trials,
+                    int32_t* labels_host, double* inertia_host, int32_t* n_iter_host, int32_t* needs_host_path,
+                    void* stream);
 /* sums_host[i*K + c] = sum over rows j with label c of ||S_i - S_j||_2 : the per-sample cluster distance sums
  * from which sklearn.metrics.silhouette_score(metric='euclidean') is formed (cnmf.py:923, k_selection) */
 int cnmf_cluster_dist_sums(cnmf_handle_t h, const float* S_dev, int R, int G, int ld, const int32_t* labels_dev,

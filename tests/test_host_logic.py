@@ -357,3 +357,32 @@ def test_restart_groups_follow_the_memory_budget():
     assert all(sum(ks[a:b]) <= 20 or b - a == 1 for a, b in groups)
     assert [a for a, _ in groups][1:] == [b for _, b in groups][:-1]      # consecutive, nothing skipped
     assert plan_groups([40], 10) == [(0, 1)] and plan_groups([], 10) == []
+
+
+def test_kmeans_draws_are_data_independent_and_in_sklearn_order():
+    """cnmf_kmeans_fit receives every random number k-means++ will use up front.  That is only legitimate if the count
+    and order of the draws do not depend on the data: consume the pre-drawn numbers in a numpy restatement of
+    sklearn's k-means++ (SK/cluster/_kmeans.py:180-278) and check the chosen centres against sklearn's own
+    kmeans_plusplus for the same RandomState, run after run."""
+    from sklearn.cluster import kmeans_plusplus
+    from cnmf_b200.consensus import _kmeans_draws
+    rng0 = np.random.RandomState(3)
+    X = np.abs(rng0.randn(240, 30)) + np.repeat(np.eye(6, 30) * 4, 40, axis=0)
+    k, n_init = 6, 4
+    first, unif, n_trials = _kmeans_draws(np.random.RandomState(1), X.shape[0], k, n_init)
+    assert n_trials == 2 + int(np.log(k))
+    ref_rng = np.random.RandomState(1)
+    x_sq = (X * X).sum(axis=1)
+    for t in range(n_init):
+        _, ref_idx = kmeans_plusplus(X, k, random_state=ref_rng, x_squared_norms=x_sq)
+        idx = [int(first[t])]
+        closest = ((X - X[idx[0]]) ** 2).sum(axis=1)
+        pot = closest.sum()
+        for c in range(1, k):
+            cand = np.searchsorted(np.cumsum(closest), unif[t, c - 1] * pot)
+            np.clip(cand, None, len(closest) - 1, out=cand)
+            d = np.minimum(closest, ((X[None, :, :] - X[cand][:, None, :]) ** 2).sum(axis=2))
+            best = int(np.argmin(d.sum(axis=1)))
+            pot, closest = d[best].sum(), d[best]
+            idx.append(int(cand[best]))
+        assert idx == list(ref_idx), (t, idx, list(ref_idx))
