@@ -304,6 +304,10 @@ static int dataset_finish(cnmf_dataset_s* d, cudaStream_t s) {
         CNMF_TRY(launch_to_half(d->Xt_hi, d->Xt_h16, (long long)nxt, s));
         h->launches += 2;
         d->f16 = true;
+        // every product of an f16 dataset reads the fp16 count matrices: the fp32 copies of C / C^T were scaffolding.
+        // Resident forms are then X (fp32, column operations and derived datasets) + C and C^T as fp16: 2 x the
+        // bytes of X instead of 4 x.  (Released after the stream has drained, below.)
+        d->drop_tf32 = true;
       }
     } else {
     CNMF_TRY(dataset_alloc(d, &d->X_hi, nx));
@@ -332,6 +336,18 @@ static int dataset_finish(cnmf_dataset_s* d, cudaStream_t s) {
   CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
   d->sum = out2[0];
   d->sum_sq = out2[1];
+  if (d->drop_tf32) {          // the conversions above have completed: hand the fp32 count matrices back
+    for (float** pp : {&d->X_hi, &d->Xt_hi}) {
+      for (auto it = d->owned.begin(); it != d->owned.end(); ++it)
+        if (it->first == *pp) {
+          h->pool_give(it->first, it->second);
+          d->owned.erase(it);
+          break;
+        }
+      *pp = nullptr;
+    }
+    d->drop_tf32 = false;
+  }
   return 0;
 }
 

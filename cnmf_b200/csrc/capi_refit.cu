@@ -2,6 +2,7 @@
 // (cnmf.py:926-930), left projections for the OLS step (cnmf.py:98-119), column statistics,
 // column-subset datasets (cnmf.py:965-969) and a raw GEMM hook used by tests / micro-benchmarks.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -259,6 +260,7 @@ int cnmf_refit(cnmf_dataset_t d, int transposed, int k, const float* fixed_host,
   CNMF_REQUIRE(d && fixed_host && p && out_host, "refit: NULL argument");
   CNMF_REQUIRE(p->precision == d->precision, "params.precision must match the precision the dataset was created with");
   CNMF_REQUIRE(k >= 1 && k <= KMAX, "refit: n_components must be in [1, 32] on the CUDA path");
+  const auto t_enter = std::chrono::steady_clock::now();
   cnmf_handle_s* h = d->h;
   cudaStream_t s = as_stream(stream);
   CNMF_CUDA_CHECK(cudaSetDevice(h->device));
@@ -300,7 +302,14 @@ int cnmf_refit(cnmf_dataset_t d, int transposed, int k, const float* fixed_host,
   io.Fr = Fr; io.Fr_hi = Fr_hi; io.Fr_lo = Fr_lo;
   io.Fc = Fc; io.Fc_hi = Fc_hi; io.Fc_lo = Fc_lo;
   io.update_cols = false;
+  auto t_solve = std::chrono::steady_clock::now();
+  if (h->profile) {
+    CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+    h->t_h2d_ms = std::chrono::duration<double, std::milli>(t_solve - t_enter).count();
+    t_solve = std::chrono::steady_clock::now();
+  }
   CNMF_TRY(solve_batched(h, v, io, *p, s));
+  if (h->profile) h->t_solve_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_solve).count();
 
   // Fr is k x n_r; the caller wants n_r x k (row-major)
   const int ldt = pad_ld(k);
@@ -331,11 +340,19 @@ int cnmf_project_rows(cnmf_dataset_t d, int k, const float* Ut_host, float* out_
   CNMF_CUDA_CHECK(cudaMemsetAsync(A, 0, nr * 4, s));
   CNMF_CUDA_CHECK(cudaMemcpy2DAsync(A, (size_t)d->ld_r * 4, Ut_host, (size_t)d->n_rows * 4, (size_t)d->n_rows * 4, k,
                                     cudaMemcpyHostToDevice, s));
+  float* A_rs = nullptr;
+  const int a_tiles = (d->ld_r + 511) / 512;
   if (tf32) {
     A_hi = static_cast<float*>(h->dev_buf("proj.A_hi", nr * 4));
     A_lo = static_cast<float*>(h->dev_buf("proj.A_lo", nr * 4));
     if (!A_hi || !A_lo) return -2;
-    CNMF_TRY(launch_split_scaled(A, A_hi, A_lo, k, d->ld_r, d->exact ? d->row_scale : nullptr, s));
+    if (d->f16) {            // f16 datasets keep C^T as fp16 only: two fp16 pieces of the (signed) rows, group scales
+      A_rs = static_cast<float*>(h->dev_buf("proj.A_rs", sizeof(float) * (size_t)k * a_tiles));
+      if (!A_rs) return -2;
+      CNMF_TRY(launch_emit_f16(A, k, d->n_rows, d->ld_r, d->exact ? d->row_scale : nullptr, A_hi, A_lo, A_rs, a_tiles, s));
+    } else {
+      CNMF_TRY(launch_split_scaled(A, A_hi, A_lo, k, d->ld_r, d->exact ? d->row_scale : nullptr, s));
+    }
     h->launches += 1;
   }
   GemmArgs g{};
@@ -347,7 +364,7 @@ int cnmf_project_rows(cnmf_dataset_t d, int k, const float* Ut_host, float* out_
     if (tiles < 2 * h->sm_count) splits = (2 * h->sm_count + tiles - 1) / tiles;
     splits = std::min(splits, std::max(1, ((d->n_rows + 31) / 32) / 8));
     splits = std::min(splits, 32);
-    splits = gemm_effective_splits(d->n_rows, splits);
+    splits = gemm_effective_splits(d->n_rows, splits, d->f16 ? 1 : 0);
   }
   g.splits = g.splits_effective = splits;
   g.c_split_stride = (long long)k * d->ld_c;
@@ -358,6 +375,12 @@ int cnmf_project_rows(cnmf_dataset_t d, int k, const float* Ut_host, float* out_
     g.A_hi = A_hi; g.A_lo = A_lo; g.B_hi = d->Xt_hi; g.B_lo = d->Xt_lo;
     g.b_exact = d->exact ? 1 : 0;
     g.out_col_scale = d->exact ? d->col_scale : nullptr;
+    if (d->f16) {
+      g.f16 = 1;
+      g.B_hi = static_cast<const float*>(d->Xt_h16);
+      g.a_tile_scale = A_rs;
+      g.a_tiles = a_tiles;
+    }
     CNMF_TRY(gemm_tf32x3(g, s));
   } else {
     g.A_hi = A; g.B_hi = d->Xt;

@@ -66,6 +66,7 @@ struct cnmf_dataset_s {
   // f16x2 precision: requested at creation (want_f16); active (f16) once the dataset turned out exact.  X_h16 / Xt_h16
   // hold the integer matrices C / C^T as fp16 (same shapes and element strides as X_hi / Xt_hi)
   bool want_f16 = false, f16 = false;
+  bool drop_tf32 = false;       // f16 datasets: X_hi / Xt_hi are released once the fp16 matrices exist
   void *X_h16 = nullptr, *Xt_h16 = nullptr;
   float *row_scale = nullptr, *col_scale = nullptr;    // lengths ld_r / ld_c, zero padded
   double sum = 0.0, sum_sq = 0.0;

@@ -16,6 +16,7 @@
 // Numerics are those of the per-run path this replaces (same kernels' arithmetic, same summation orders), so labels and
 // inertia are bit-identical to it -- and labels equal scikit-learn's on the parity fixtures.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <vector>
 
@@ -168,21 +169,25 @@ kpp_select_kernel(KmState st, int step /* centre being committed: 0 = the first 
   const double* u = st.unif + ((long long)t * (st.K - 1) + step) * st.n_trials;
   double rv[8];
   int found[8];
-  for (int j = 0; j < st.n_trials; ++j) {
-    rv[j] = u[j] * pot;
-    found[j] = -1;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {                 // fixed trip count: rv / found stay in registers
+    rv[j] = j < st.n_trials ? u[j] * pot : 0.0;
+    found[j] = j < st.n_trials ? -1 : 0;
   }
   double c = 0.0;
   int left = st.n_trials;
   for (int i = 0; i < st.R && left > 0; ++i) {
     c += cl_s[i];                               // np.cumsum: strictly sequential
-    for (int j = 0; j < st.n_trials; ++j)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
       if (found[j] < 0 && c >= rv[j]) {         // searchsorted side='left': first index with cumsum >= value
         found[j] = i;
         --left;
       }
   }
-  for (int j = 0; j < st.n_trials; ++j) st.cand[t * 8 + j] = found[j] < 0 ? st.R - 1 : found[j];   // np.clip
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < st.n_trials) st.cand[t * 8 + j] = found[j] < 0 ? st.R - 1 : found[j];   // np.clip
 }
 
 __global__ void __launch_bounds__(256)
@@ -403,6 +408,9 @@ extern "C" int cnmf_kmeans_fit(cnmf_handle_t h, const float* S_dev, int R, int G
   HostBlock* hb = static_cast<HostBlock*>(h->host_buf("kmb.host", sizeof(HostBlock)));
   if (!hb) return -2;
 
+  using clk = std::chrono::steady_clock;
+  auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
+  auto t_phase = clk::now();
   // ---- k-means++ seeding, all runs together
   {
     std::vector<int> cidx((size_t)n_init * K, 0);
@@ -430,6 +438,11 @@ extern "C" int cnmf_kmeans_fit(cnmf_handle_t h, const float* S_dev, int R, int G
   kpp_gather_centres_kernel<<<dim3(K, n_init), 256, 0, s>>>(st, C64, C32);
   h->launches += 2 * K + 1;
 
+  if (h->profile) {                 // phase timing for bench / probes (cnmf_last_timing: rng = seeding, solve = Lloyd)
+    CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+    h->t_rng_ms = ms_since(t_phase);
+    t_phase = clk::now();
+  }
   // ---- Lloyd, all runs together
   CNMF_CUDA_CHECK(cudaMemsetAsync(ls.labels, 0xff, nR * 4, s));          // -1: every label "changes" in iteration 1
   CNMF_CUDA_CHECK(cudaMemsetAsync(ls.flags, 0, (size_t)n_init * 16, s));
@@ -461,6 +474,11 @@ extern "C" int cnmf_kmeans_fit(cnmf_handle_t h, const float* S_dev, int R, int G
     return 0;
   }
   *needs_host_path = 0;
+  if (h->profile) {
+    h->t_solve_ms = ms_since(t_phase);
+    h->t_h2d_ms = (double)it;      // Lloyd iterations of the slowest run
+    t_phase = clk::now();
+  }
   // ---- final E step against every run's final centres + inertia (sklearn _kmeans.py:736-744)
   kmb_assign_kernel<<<assign_grid, 256, 0, s>>>(ls, C32, C32 + nKG, 0, 1);
   kmb_inertia_kernel<<<n_init, 256, 0, s>>>(ls);
@@ -469,6 +487,7 @@ extern "C" int cnmf_kmeans_fit(cnmf_handle_t h, const float* S_dev, int R, int G
   CNMF_CUDA_CHECK(cudaMemcpyAsync(hb->inertia, ls.inertia, (size_t)n_init * 8, cudaMemcpyDeviceToHost, s));
   CNMF_CUDA_CHECK(cudaMemcpyAsync(labels_host, ls.labels, nR * 4, cudaMemcpyDeviceToHost, s));
   CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (h->profile) h->t_d2h_ms = ms_since(t_phase);
   for (int t = 0; t < n_init; ++t) {
     inertia_host[t] = hb->inertia[t];
     if (n_iter_host) n_iter_host[t] = hb->flags[t * 4 + 3];

@@ -207,7 +207,8 @@ emit_f16_kernel(const float* __restrict__ F, int n, int ld, const float* __restr
           v[j].x *= p.x; v[j].y *= p.y; v[j].z *= p.z; v[j].w *= p.w;
         }
       }
-      m = fmaxf(fmaxf(m, fmaxf(v[j].x, v[j].y)), fmaxf(v[j].z, v[j].w));
+      // |.|: factors are non-negative, but the OLS projection sends signed (centred) rows through the same pieces
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v[j].x), fabsf(v[j].y))), fmaxf(fabsf(v[j].z), fabsf(v[j].w)));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));

@@ -28,7 +28,22 @@ def run(name, ks, n_iter, eng, reps=2, n_cells=None):
             res = cs.consensus_numerics(eng, merged, k, ds, bench.NMF_KW, tpm_ds=tds, hvg_idx=np.arange(X.shape[1]), tpm_std_hvg=tpm_std)
             torch.cuda.synchronize()
             tot = 1e3 * (time.perf_counter() - t0)
-        print(json.dumps({"case": name, "N": X.shape[0], "k": k, "R": merged.shape[0], "factorize_s": round(tf, 3), "consensus_ms": round(tot, 1),
+        # phase detail: KMeans (seeding / Lloyd / final) and the three refits (setup / solve), library-side timers
+        eng.profile(True)
+        S = cs.SpectraMatrix(eng, merged).l2_normalize()
+        t0 = time.perf_counter(); cs.kmeans(S, k); km_ms = 1e3 * (time.perf_counter() - t0)
+        km = eng.last_timing()
+        detail = {"kmeans_ms": round(km_ms, 2), "km_seed_ms": round(km["rng_ms"], 2), "km_lloyd_ms": round(km["solve_ms"], 2),
+                  "km_lloyd_iters_max": km["h2d_ms"], "km_final_ms": round(km["d2h_ms"], 2)}
+        t0 = time.perf_counter(); W, it_a, _ = ds.refit(res["median_spectra"], bench.NMF_KW); ra = 1e3 * (time.perf_counter() - t0)
+        ta = eng.last_timing()
+        U = res["norm_usages"]
+        t0 = time.perf_counter(); Ht, it_b, _ = tds.refit(np.ascontiguousarray(U.T), bench.NMF_KW, transposed=True); rb = 1e3 * (time.perf_counter() - t0)
+        tb = eng.last_timing()
+        detail.update(refit_a_ms=round(ra, 2), refit_a_setup=round(ta["h2d_ms"], 2), refit_a_solve=round(ta["solve_ms"], 2), refit_a_it=it_a,
+                      refit_b_ms=round(rb, 2), refit_b_setup=round(tb["h2d_ms"], 2), refit_b_solve=round(tb["solve_ms"], 2), refit_b_it=it_b)
+        eng.profile(False)
+        print(json.dumps({"case": name, "detail": detail, "N": X.shape[0], "k": k, "R": merged.shape[0], "factorize_s": round(tf, 3), "consensus_ms": round(tot, 1),
                           "phases_ms": {a: round(b, 1) for a, b in cs.STATS["phases_ms"].items()},
                           "lloyd_iters": cs.STATS.get("lloyd_iters"), "refits": [list(map(int, r)) for r in cs.STATS.get("refits", [])]}), flush=True)
     ds.close(); tds.close()
