@@ -233,6 +233,12 @@ def run_ours(args, rank, world, local):
     n_jobs = len(ks_all)
     eng = Engine(local)
     comm = SpectraComm(eng) if world > 1 else None
+    # Python's cyclic collector walks every object of every imported package (torch, pandas, sklearn: ~10^6) when a
+    # generation-2 collection fires -- 60-90 ms at a random point of a timed region (seen in tools/probe_stalls.py).
+    # Everything alive now is set-up state: move it out of the collector's reach.
+    import gc
+    gc.collect()
+    gc.freeze()
 
     def sync_all():
         torch.cuda.synchronize(dev)

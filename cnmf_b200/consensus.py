@@ -23,6 +23,26 @@ from ._lib import check, ptr
 STATS = {}
 
 
+class _few_blas_threads:
+    """The host-side linear algebra of this stage is tiny (K x K solves, N x K Gram products).  On a 128-core host a
+    BLAS pool of 128 threads wakes up for each of them and the wake-up, not the arithmetic, becomes the cost (tens of ms
+    at random points of a stage whose GPU work takes milliseconds).  Four threads for the duration of the stage."""
+
+    def __enter__(self):
+        try:
+            from threadpoolctl import threadpool_limits
+            self._ctx = threadpool_limits(limits=4)
+            self._ctx.__enter__()
+        except Exception:
+            self._ctx = None
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+        return False
+
+
 def _torch():
     import torch
     if not torch.cuda.is_available():
@@ -301,7 +321,13 @@ def ols_zscore(usages, tpm_ds):
 
 
 # ------------------------------------------------------------------------------ the consensus step as one function
-def consensus_numerics(eng, merged, k, norm_ds, kw, density_threshold=0.5, n_neighbors=None,
+def consensus_numerics(eng, merged, k, norm_ds, kw, **kwargs):
+    """See _consensus_numerics; runs it with a small host BLAS pool."""
+    with _few_blas_threads():
+        return _consensus_numerics(eng, merged, k, norm_ds, kw, **kwargs)
+
+
+def _consensus_numerics(eng, merged, k, norm_ds, kw, density_threshold=0.5, n_neighbors=None,
                        local_neighborhood_size=0.30, stats_only=False, local_density=None, want_dist=False,
                        tpm_ds=None, hvg_idx=None, tpm_std_hvg=None, refit_usage=True, tpm_sparse=False,
                        on_density=None):

@@ -311,15 +311,17 @@ int cnmf_refit(cnmf_dataset_t d, int transposed, int k, const float* fixed_host,
   CNMF_TRY(solve_batched(h, v, io, *p, s));
   if (h->profile) h->t_solve_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_solve).count();
 
-  // Fr is k x n_r; the caller wants n_r x k (row-major)
-  const int ldt = pad_ld(k);
-  float* T = static_cast<float*>(h->dev_buf("refit.T", (size_t)v.n_r * ldt * 4));
-  if (!T) return -2;
-  CNMF_TRY(launch_transpose(Fr, k, v.n_r, v.ld_r, T, nullptr, nullptr, ldt, s));
+  // Fr is k x n_r; the caller wants n_r x k (row-major).  Transposed on the device into a COMPACT n_r x k array and
+  // copied back in one contiguous transfer through pinned memory: a pitched 2-D copy of 50 000 rows of ~40 bytes to
+  // pageable memory took 10 ms on a good day and 80 ms on a bad one -- ten times the solve itself.
+  float* T = static_cast<float*>(h->dev_buf("refit.T", (size_t)v.n_r * k * 4));
+  float* T_host = static_cast<float*>(h->host_buf("refit.T_host", (size_t)v.n_r * k * 4));
+  if (!T || !T_host) return -2;
+  CNMF_TRY(launch_transpose(Fr, k, v.n_r, v.ld_r, T, nullptr, nullptr, k, s));
   h->launches += 1;
-  CNMF_CUDA_CHECK(cudaMemcpy2DAsync(out_host, (size_t)k * 4, T, (size_t)ldt * 4, (size_t)k * 4, v.n_r,
-                                    cudaMemcpyDeviceToHost, s));
+  CNMF_CUDA_CHECK(cudaMemcpyAsync(T_host, T, (size_t)v.n_r * k * 4, cudaMemcpyDeviceToHost, s));
   CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+  std::memcpy(out_host, T_host, (size_t)v.n_r * k * 4);
   if (n_iter_host) *n_iter_host = io.n_iter[0];
   if (err_host) *err_host = io.err[0];
   return 0;
