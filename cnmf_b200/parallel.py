@@ -118,6 +118,9 @@ class SpectraComm:
             self._comm = ctypes.c_void_p()
 
 
+_PINNED = {}      # pinned staging buffer of ShardedSpectra.host(), keyed by slab shape
+
+
 class ShardedSpectra:
     """Result of factorize_sharded: every restart's spectra in ONE device slab (world x max_rows x ld), identical on
     all ranks after the all-gather, plus the map job -> slab row."""
@@ -149,9 +152,19 @@ class ShardedSpectra:
         return SpectraMatrix.from_device_rows(engine, self.t.data_ptr(), self.ld, self.rows_of_jobs(jobs), self.n_genes)
 
     def host(self):
-        """All spectra on the host, list indexed by job."""
-        flat = self.t.reshape(self.world * self.max_rows, self.ld)[:, :self.n_genes].cpu().numpy()
-        return [flat[self.first_row[j]:self.first_row[j] + k].copy() for j, k in enumerate(self.ks_all)]
+        """All spectra on the host, list indexed by job: ONE contiguous copy of the slab into pinned memory (cached per
+        size), then per-job views -- a pitched, pageable copy of the same 65 MB took 45 ms instead of 3."""
+        import torch
+        n = self.world * self.max_rows
+        key = (n, self.ld)
+        buf = _PINNED.get(key)
+        if buf is None:
+            _PINNED.clear()
+            buf = _PINNED[key] = torch.empty((n, self.ld), dtype=torch.float32, pin_memory=True)
+        buf.copy_(self.t.reshape(n, self.ld), non_blocking=True)
+        torch.cuda.synchronize(self.t.device)
+        flat = buf.numpy()
+        return [flat[self.first_row[j]:self.first_row[j] + k, :self.n_genes] for j, k in enumerate(self.ks_all)]
 
 
 def factorize_sharded(ds, ks_all, seeds_all, nmf_kwargs, comm=None):
