@@ -483,7 +483,7 @@ int run_and_download(cnmf_dataset_s* d, const std::vector<int>& ks, int SK, Fact
   cnmf_handle_s* h = d->h;
   const bool tf32 = p.precision == CNMF_PRECISION_TF32X3;
   DataView v = make_view(d, false);
-  if (tf32) {
+  if (tf32 && !v.f16) {      // f16 datasets: the solver emits fp16 pieces itself; tf32 pieces would be dead work
     CNMF_TRY(launch_split_scaled(fb.Fr, fb.Fr_hi, fb.Fr_lo, SK, d->ld_r, v.exact ? v.scale_r : nullptr, s));
     CNMF_TRY(launch_split_scaled(fb.Fc, fb.Fc_hi, fb.Fc_lo, SK, d->ld_c, v.exact ? v.scale_c : nullptr, s));
     h->launches += 2;
@@ -670,7 +670,7 @@ int cnmf_factorize_dev(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in, c
   CNMF_CUDA_CHECK(cudaMemcpyAsync(fb.Fr, Wt0_dev, (size_t)SK * d->ld_r * 4, cudaMemcpyDeviceToDevice, s));
   CNMF_CUDA_CHECK(cudaMemcpyAsync(fb.Fc, H0_dev, (size_t)SK * d->ld_c * 4, cudaMemcpyDeviceToDevice, s));
   DataView v = make_view(d, false);
-  if (tf32) {
+  if (tf32 && !v.f16) {      // f16 datasets: the solver emits fp16 pieces itself; tf32 pieces would be dead work
     CNMF_TRY(launch_split_scaled(fb.Fr, fb.Fr_hi, fb.Fr_lo, SK, d->ld_r, v.exact ? v.scale_r : nullptr, s));
     CNMF_TRY(launch_split_scaled(fb.Fc, fb.Fc_hi, fb.Fc_lo, SK, d->ld_c, v.exact ? v.scale_c : nullptr, s));
     h->launches += 2;

@@ -291,7 +291,7 @@ int cnmf_refit(cnmf_dataset_t d, int transposed, int k, const float* fixed_host,
     CNMF_CUDA_CHECK(cudaGetLastError());
     h->launches += 1;
   }  // 'cd': zeros (sklearn _nmf.py:1227-1228)
-  if (tf32) {
+  if (tf32 && !v.f16) {
     CNMF_TRY(launch_split_scaled(Fr, Fr_hi, Fr_lo, k, v.ld_r, v.exact ? v.scale_r : nullptr, s));
     CNMF_TRY(launch_split_scaled(Fc, Fc_hi, Fc_lo, k, v.ld_c, v.exact ? v.scale_c : nullptr, s));
     h->launches += 2;

@@ -176,14 +176,26 @@ kpp_select_kernel(KmState st, int step /* centre being committed: 0 = the first 
   }
   double c = 0.0;
   int left = st.n_trials;
+  double next_rv = rv[0];                       // smallest pending value: one comparison per element in the common case
+#pragma unroll
+  for (int j = 1; j < 8; ++j)
+    if (j < st.n_trials) next_rv = fmin(next_rv, rv[j]);
   for (int i = 0; i < st.R && left > 0; ++i) {
     c += cl_s[i];                               // np.cumsum: strictly sequential
+    if (c >= next_rv) {                         // searchsorted side='left': first index with cumsum >= value
+      next_rv = 1.0e308;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (found[j] < 0 && c >= rv[j]) {         // searchsorted side='left': first index with cumsum >= value
-        found[j] = i;
-        --left;
+      for (int j = 0; j < 8; ++j) {
+        if (found[j] < 0) {
+          if (c >= rv[j]) {
+            found[j] = i;
+            --left;
+          } else {
+            next_rv = fmin(next_rv, rv[j]);
+          }
+        }
       }
+    }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j)
