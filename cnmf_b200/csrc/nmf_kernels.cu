@@ -491,7 +491,7 @@ __device__ __forceinline__ void emit_tile_f16(const FactorView& f, const float* 
 // body (~80 instructions) instead of K unrolled copies: no per-component predicates for K < KP, and the code
 // stays resident in the instruction cache (the unrolled version stalled on instruction fetch, profiles/r1g_*).
 // Returns <NUM, F_new> over the thread's items (fp32 within a tile, fp64 across tiles).
-template <int KP, int VEC, bool GRAM>
+template <int KP, int VEC, bool GRAM, bool STREAMN>
 __device__ __forceinline__ double mu_body(const FactorView& f, const float* __restrict__ NUM, int nsplit,
                                           long long sstride, const float* G, int K, int o, float l1, float l2,
                                           int col_begin, int col_end, float* tileF, float* tileN, double* gsum) {
@@ -511,9 +511,34 @@ __device__ __forceinline__ double mu_body(const FactorView& f, const float* __re
       float* const pH = f.F_hi ? f.F_hi + e0 : nullptr;
       float* const pL = f.F_hi ? f.F_lo + e0 : nullptr;
       float2 fv[KP][NP];
-      {
+      const float* const pN = NUM + e0;
+      const int n_left = f.n - col;
+      float2 nvn[NP];                                // STREAMN: the products of component c + 1, in flight
+      if constexpr (STREAMN) {
+#pragma unroll
+        for (int i = 0; i < KP; ++i) {
+          if (i < K) {
+            VecIO<VEC>::ld(pF + (unsigned)i * ld, fv[i]);
+          } else {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) fv[i][p] = make_float2(0.f, 0.f);
+          }
+        }
+        VecIO<VEC>::ld(pN, nvn);
+        if (n_left < VEC) {                          // ragged tail: columns >= n of the factor count as zeros
+#pragma unroll
+          for (int i = 0; i < KP; ++i)
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              if (2 * p >= n_left) fv[i][p].x = 0.f;
+              if (2 * p + 1 >= n_left) fv[i][p].y = 0.f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < KP; ++i) VecIO<VEC>::st(myF + i * TILE, fv[i]);
+      } else {
         float2 nv[KP][NP];
-        load_items<KP, VEC>(pF, NUM + e0, nsplit, sstride, K, ld, f.n - col, fv, nv);
+        load_items<KP, VEC>(pF, pN, nsplit, sstride, K, ld, n_left, fv, nv);
 #pragma unroll
         for (int i = 0; i < KP; ++i) {               // rows >= K hold zeros (load_items): the Gram tile needs them
           VecIO<VEC>::st(myF + i * TILE, fv[i]);
@@ -542,7 +567,28 @@ __device__ __forceinline__ double mu_body(const FactorView& f, const float* __re
         }
         float2 fvc[NP], nvc[NP], out[NP];
         VecIO<VEC>::ld(myF + c * TILE, fvc);
-        VecIO<VEC>::ld(myN + c * TILE, nvc);
+        if constexpr (STREAMN) {
+          // the products are read once, straight from global memory, one component ahead of their use (the
+          // component loop body is ~100 instructions: enough lead for an L2 / HBM access at 4 blocks per SM)
+#pragma unroll
+          for (int p = 0; p < NP; ++p) nvc[p] = nvn[p];
+          if (c + 1 < K) VecIO<VEC>::ld(pN + off + ld, nvn);
+          for (int s = 1; s < nsplit; ++s) {         // split-K slices, added in slice order
+            float2 t[NP];
+            VecIO<VEC>::ld(pN + s * sstride + off, t);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) nvc[p] = add2(nvc[p], t[p]);
+          }
+          if (n_left < VEC) {                        // product columns >= n are not defined
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              if (2 * p >= n_left) nvc[p].x = 0.f;
+              if (2 * p + 1 >= n_left) nvc[p].y = 0.f;
+            }
+          }
+        } else {
+          VecIO<VEC>::ld(myN + c * TILE, nvc);
+        }
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
           // regularisation terms unconditionally: adding l1 = 0 and l2 * F = 0 is exact, a uniform branch costs more
@@ -707,8 +753,8 @@ __device__ __forceinline__ double update_body(const FactorView& f, const float* 
 // KPMAX = 16: 4 items per thread, fused Gram available (GRAM).  KPMAX = 32: 2 items per thread, no fused Gram
 // (its K x K register tile does not fit beside the update's working set; the engine runs the stand-alone
 // Gram kernel for those batches).
-template <int KPMAX, bool CD, bool GRAM>
-__global__ void __launch_bounds__(UPD_THREADS, KPMAX == 32 ? 2 : 3)
+template <int KPMAX, bool CD, bool GRAM, int MINB = (KPMAX == 32 ? 2 : 3), bool STREAMN = false>
+__global__ void __launch_bounds__(UPD_THREADS, MINB)
 update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long sstride,
               const double* __restrict__ gram_in, BatchMeta b, float l1, float l2, FusedOut out) {
   constexpr int VEC = KPMAX == 16 ? 4 : 2;
@@ -744,8 +790,8 @@ update_kernel(FactorView f, const float* __restrict__ NUM, int nsplit, long long
                                                                        col_begin, col_end, tile, gsum)));
   } else {
     float* tileN = tile + UPD_TILE_F_FLOATS;
-    CNMF_KP_SWITCH(K, KPMAX, (scal = mu_body<KP, VEC, GRAM>(f, NUM, nsplit, sstride, G, K, o, l1, l2, col_begin, col_end,
-                                                             tile, tileN, gsum)));
+    CNMF_KP_SWITCH(K, KPMAX, (scal = mu_body<KP, VEC, GRAM, STREAMN>(f, NUM, nsplit, sstride, G, K, o, l1, l2, col_begin, col_end,
+                                                                      tile, tileN, gsum)));
   }
   const int chunks = gridDim.x;
   if (want_scal) {
@@ -1109,21 +1155,54 @@ int launch_matrix_sums(const float* X, int rows, int cols, int ld, double* out2,
     default: set_last_error("kp must be 16 or 32"); return -1;       \
   }
 
+template <int KPMAX, bool CD, bool GRAM, int MINB, bool STREAMN>
+static int launch_update_inst(dim3 grid, const FactorView& f, const float* NUM, int nsplit, long long sstride,
+                              const double* gram_in, const BatchMeta& b, float l1, float l2, const FusedOut& out,
+                              cudaStream_t s) {
+  // MU stages the thread's factor values (and, unless the products are streamed, the products) in shared memory
+  // (rolled component loop); CD only needs the tile when it also emits the Gram
+  const size_t smem = sizeof(float) * (CD ? (GRAM ? (size_t)UPD_TILE_F_FLOATS : 0)
+                                          : (size_t)UPD_TILE_F_FLOATS + (STREAMN ? 0 : UPD_TILE_N_FLOATS));
+  static bool attr_set = false;
+  if (!attr_set && smem > 0) {
+    CNMF_CUDA_CHECK(cudaFuncSetAttribute(update_kernel<KPMAX, CD, GRAM, MINB, STREAMN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  update_kernel<KPMAX, CD, GRAM, MINB, STREAMN><<<grid, UPD_THREADS, smem, s>>>(f, NUM, nsplit, sstride, gram_in, b, l1, l2, out);
+  CNMF_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// MU with the fused Gram at kp == 16, CNMF_UPD_VARIANT: 2 (default) = products streamed from global memory one
+// component ahead of their use, no product tile in shared memory, 4 blocks per SM (128 registers); 0 = round 1's
+// layout (products staged in a second shared-memory tile, 3 blocks per SM); 1 / 3 = streamed at 3 / 5 blocks per SM.
+// Measured on c3 (profiles/r2m_update_variants.log): update launches 1031 / 1085 / 962 / 1065 ms per 3 steps for
+// variants 0 / 1 / 2 / 3 -- the kernel is bound by its instruction count, not by occupancy; every variant computes the
+// same bits.
+static int upd_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CNMF_UPD_VARIANT");
+    v = e ? atoi(e) : 2;
+    if (v < 0 || v > 3) v = 2;
+  }
+  return v;
+}
+
 template <int KPMAX, bool CD, bool GRAM>
 static int launch_update_variant(dim3 grid, const FactorView& f, const float* NUM, int nsplit, long long sstride,
                                  const double* gram_in, const BatchMeta& b, float l1, float l2, const FusedOut& out,
                                  cudaStream_t s) {
-  // MU stages the thread's factor values and products in shared memory (rolled component loop); CD only needs
-  // the tile when it also emits the Gram
-  const size_t smem = sizeof(float) * (CD ? (GRAM ? (size_t)UPD_TILE_F_FLOATS : 0) : (size_t)UPD_TILE_F_FLOATS + UPD_TILE_N_FLOATS);
-  static bool attr_set = false;
-  if (!attr_set && smem > 0) {
-    CNMF_CUDA_CHECK(cudaFuncSetAttribute(update_kernel<KPMAX, CD, GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+  if constexpr (KPMAX == 16 && !CD && GRAM) {
+    switch (upd_variant()) {
+      case 1: return launch_update_inst<KPMAX, CD, GRAM, 3, true>(grid, f, NUM, nsplit, sstride, gram_in, b, l1, l2, out, s);
+      case 2: return launch_update_inst<KPMAX, CD, GRAM, 4, true>(grid, f, NUM, nsplit, sstride, gram_in, b, l1, l2, out, s);
+      case 3: return launch_update_inst<KPMAX, CD, GRAM, 5, true>(grid, f, NUM, nsplit, sstride, gram_in, b, l1, l2, out, s);
+      default: break;
+    }
   }
-  update_kernel<KPMAX, CD, GRAM><<<grid, UPD_THREADS, smem, s>>>(f, NUM, nsplit, sstride, gram_in, b, l1, l2, out);
-  CNMF_CUDA_CHECK(cudaGetLastError());
-  return 0;
+  return launch_update_inst<KPMAX, CD, GRAM, (KPMAX == 32 ? 2 : 3), false>(grid, f, NUM, nsplit, sstride, gram_in, b, l1, l2, out, s);
 }
 
 template <bool CD>

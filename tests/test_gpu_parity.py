@@ -762,10 +762,10 @@ def test_two_gpu_sharded_factorize_allgather_consensus():
     assert r.stdout.count("merged spectra match the reference fixture") == 2, r.stdout[-2000:]
 
 
-@pytest.mark.parametrize("env", [{"CNMF_FUSE_W": "1"}, {"CNMF_GEMM_PAIR": "1"}])
+@pytest.mark.parametrize("env", [{"CNMF_FUSE_W": "1"}, {"CNMF_GEMM_PAIR": "1"}, {"CNMF_UPD_VARIANT": "0"}])
 def test_opt_in_kernel_variants_keep_parity(env):
-    """The two opt-in GEMM variants -- the W-half multiplicative update applied in the GEMM epilogue (CNMF_FUSE_W=1) and
-    the CTA-pair cta_group::2 kernel (CNMF_GEMM_PAIR=1) -- on a multi-tile, mixed-K batch (45 restarts, K = 5..13,
+    """The opt-in kernel variants -- the W-half multiplicative update applied in the GEMM epilogue (CNMF_FUSE_W=1), the
+    CTA-pair cta_group::2 kernel (CNMF_GEMM_PAIR=1) and round 1's update-kernel layout (CNMF_UPD_VARIANT=0) -- on a multi-tile, mixed-K batch (45 restarts, K = 5..13,
     405 packed rows) against the numpy oracle: identical n_iter, spectra within 1e-4.  They are opt-in because they
     measured slower than the default kernels (profiles/r2b_*, r2f_*), not because they are less exact."""
     import json
