@@ -75,21 +75,33 @@ int cnmf_handle_s::prof_begin(cudaStream_t s, double work, int cls) {
     if (cudaEventCreate(&e) != cudaSuccess) return -1;
     ev_pool.push_back(e);
   }
-  const int slot = (int)ev_used;
-  ev_used += 2;
-  cudaEventRecord(ev_pool[slot], s);
-  ev_pending.push_back(Pending{slot, cls, work});
-  return slot;
+  int begin;
+  // call sites count their launch (launches += 1) before prof_begin: exactly one more than at the last prof_end
+  // means nothing else was enqueued by the library in between
+  if (prof_last_end >= 0 && prof_last_stream == s && launches == prof_last_launches + 1) {
+    begin = prof_last_end;
+  } else {
+    begin = (int)ev_used++;
+    cudaEventRecord(ev_pool[begin], s);
+  }
+  const int end = (int)ev_used++;
+  ev_pending.push_back(Pending{begin, end, cls, work});
+  return (int)ev_pending.size() - 1;
 }
 
 void cnmf_handle_s::prof_end(cudaStream_t s, int slot) {
-  if (slot >= 0) cudaEventRecord(ev_pool[slot + 1], s);
+  if (slot < 0) return;
+  const int end = ev_pending[slot].end;
+  cudaEventRecord(ev_pool[end], s);
+  prof_last_end = end;
+  prof_last_launches = launches;
+  prof_last_stream = s;
 }
 
 void cnmf_handle_s::prof_collect() {
   for (auto& pr : ev_pending) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ev_pool[pr.slot], ev_pool[pr.slot + 1]) == cudaSuccess) {
+    if (cudaEventElapsedTime(&ms, ev_pool[pr.begin], ev_pool[pr.end]) == cudaSuccess) {
       prof_ms[pr.cls] += ms;
       prof_work[pr.cls] += pr.work;
       prof_launches[pr.cls] += 1;
@@ -97,6 +109,7 @@ void cnmf_handle_s::prof_collect() {
   }
   ev_pending.clear();
   ev_used = 0;
+  prof_last_end = -1;
 }
 
 void* cnmf_handle_s::pool_take(size_t bytes) {
@@ -214,6 +227,7 @@ int cnmf_profile_enable(cnmf_handle_t h, int on) {
   }
   h->ev_pending.clear();
   h->ev_used = 0;
+  h->prof_last_end = -1;
   if (on) {       // event creation is kept out of the timed region: a pool for ~32 000 launches up front
     while (h->ev_pool.size() < 65536) {
       cudaEvent_t e;
@@ -558,7 +572,8 @@ static int factorize_impl(cnmf_dataset_t d, int n_restarts, const int32_t* ks_in
     CNMF_CUDA_CHECK(cudaMemsetAsync(fb.Fc, 0, (size_t)SK * d->ld_c * 4, s));
     CNMF_TRY(launch_rng_init(seeds, ks.data(), off.data(), avgs.data(), n_restarts, d->n_rows, d->n_cols, fb.Fr, d->ld_r,
                              fb.Fc, d->ld_c, h, s));
-    CNMF_CUDA_CHECK(cudaStreamSynchronize(s));
+    // no host synchronisation here: launch_rng_init stages its arguments itself, and the solve is enqueued behind
+    // the generator on the same stream (t_rng_ms = enqueue time; the kernel's time is part of t_solve_ms)
     h->t_rng_ms = ms_since(t_rng);
     return run_and_download(d, ks, SK, fb, *p, spectra_host, usages_host, n_iter_host, err_host, s, spectra_dev, ld_dev);
   }

@@ -20,7 +20,12 @@ struct cnmf_handle_s {
   cudaEvent_t ev_upd = nullptr, ev_gram = nullptr;
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
-  struct Pending { int slot; int cls; double work; };   // slot = index of the start event in ev_pool
+  struct Pending { int begin; int end; int cls; double work; };   // indices of the start / end events in ev_pool
+  // a profiled launch that directly follows another profiled launch (no other counted launch in between, same
+  // stream) takes the predecessor's end event as its start: one event record per kernel boundary instead of two
+  int prof_last_end = -1;
+  long long prof_last_launches = -1;
+  cudaStream_t prof_last_stream = nullptr;
   std::vector<Pending> ev_pending;
   size_t ev_used = 0;
   // kernel classes: 0 = batched GEMM (work = algorithmic FLOPs), 1 = fused update kernels (work = algorithmic bytes)
@@ -28,7 +33,7 @@ struct cnmf_handle_s {
   double prof_ms[PROF_CLASSES] = {0.0, 0.0}, prof_work[PROF_CLASSES] = {0.0, 0.0};
   long long prof_launches[PROF_CLASSES] = {0, 0};
   double t_rng_ms = 0, t_h2d_ms = 0, t_solve_ms = 0, t_d2h_ms = 0;   // host wall-clock phases of the last cnmf_factorize
-  int prof_begin(cudaStream_t s, double work, int cls = 0);    // records the start event; returns slot or -1
+  int prof_begin(cudaStream_t s, double work, int cls = 0);    // start event (recorded or shared); returns slot or -1
   void prof_end(cudaStream_t s, int slot);
   void prof_collect();                              // after a stream sync: fold pending pairs into the totals
   std::map<std::string, std::pair<void*, size_t>> ws;   // named grow-only device buffers

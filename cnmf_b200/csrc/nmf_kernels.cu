@@ -1163,11 +1163,13 @@ static int launch_update_inst(dim3 grid, const FactorView& f, const float* NUM, 
   // (rolled component loop); CD only needs the tile when it also emits the Gram
   const size_t smem = sizeof(float) * (CD ? (GRAM ? (size_t)UPD_TILE_F_FLOATS : 0)
                                           : (size_t)UPD_TILE_F_FLOATS + (STREAMN ? 0 : UPD_TILE_N_FLOATS));
-  static bool attr_set = false;
-  if (!attr_set && smem > 0) {
+  static bool attr_set[64] = {};               // per device: the attribute belongs to the device's copy of the function
+  int dev = 0;
+  CNMF_CUDA_CHECK(cudaGetDevice(&dev));
+  if (smem > 0 && (dev < 0 || dev >= 64 || !attr_set[dev])) {
     CNMF_CUDA_CHECK(cudaFuncSetAttribute(update_kernel<KPMAX, CD, GRAM, MINB, STREAMN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   update_kernel<KPMAX, CD, GRAM, MINB, STREAMN><<<grid, UPD_THREADS, smem, s>>>(f, NUM, nsplit, sstride, gram_in, b, l1, l2, out);
   CNMF_CUDA_CHECK(cudaGetLastError());

@@ -46,6 +46,32 @@ def shard_jobs(n_jobs, rank, world):
     return [i for i in range(n_jobs) if (i - rank) % world == 0]
 
 
+_LAYOUTS = {}     # (ks_all, world) -> (rows_per_rank, first_row): the slab layout is a function of the job table only
+
+
+def _slab_layout(ks_all, world):
+    """Rows every rank contributes and the first slab row of every job, for a slab of (world, max_rows) rows.
+    Cached: a K-sweep calls factorize_sharded with the same table over and over, and 17 passes of Python over
+    900 jobs are ~1 ms of idle GPU per call."""
+    key = (tuple(ks_all), int(world))
+    hit = _LAYOUTS.get(key)
+    if hit is None:
+        n_jobs = len(ks_all)
+        per_rank = [shard_jobs(n_jobs, r, world) for r in range(world)]
+        rows_per_rank = [sum(ks_all[j] for j in jobs) for jobs in per_rank]
+        max_rows = max(max(rows_per_rank), 1)
+        first_row = [0] * n_jobs
+        for r, jobs in enumerate(per_rank):
+            o = 0
+            for j in jobs:
+                first_row[j] = r * max_rows + o
+                o += ks_all[j]
+        if len(_LAYOUTS) > 16:
+            _LAYOUTS.clear()
+        hit = _LAYOUTS[key] = (rows_per_rank, max_rows, first_row, per_rank)
+    return hit
+
+
 def allgather_spectra(local_spectra, local_jobs, ks_all, n_genes, device=None):
     """All-gather the per-rank spectra slabs and return the list of spectra for ALL jobs, in job order.
 
@@ -132,12 +158,8 @@ class ShardedSpectra:
         self.world = int(world)
         self.max_rows = int(gathered.shape[1])
         self.ld = int(gathered.shape[2])
-        self.first_row = [0] * len(ks_all)
-        for r in range(world):
-            o = 0
-            for j in shard_jobs(len(ks_all), r, world):
-                self.first_row[j] = r * self.max_rows + o
-                o += ks_all[j]
+        _, max_rows, self.first_row, _ = _slab_layout(self.ks_all, self.world)
+        assert max_rows == self.max_rows, "slab does not have the layout of this job table"
 
     def rows_of_jobs(self, jobs):
         """Slab rows (flattened world*max_rows index) of the given jobs, job by job, component by component."""
@@ -173,10 +195,8 @@ def factorize_sharded(ds, ks_all, seeds_all, nmf_kwargs, comm=None):
     Returns (ShardedSpectra, n_iter of the local jobs, local job indices)."""
     import torch
     rank, world, _ = dist_info()
-    n_jobs = len(ks_all)
-    jobs = shard_jobs(n_jobs, rank, world)
-    rows_per_rank = [sum(ks_all[j] for j in shard_jobs(n_jobs, r, world)) for r in range(world)]
-    max_rows = max(max(rows_per_rank), 1)
+    _, max_rows, _, per_rank = _slab_layout(ks_all, world)
+    jobs = per_rank[rank]
     _, ld = ds.ld()
     dev = torch.device("cuda:%d" % ds.engine.device)
     gathered = torch.zeros((world, max_rows, ld), dtype=torch.float32, device=dev)

@@ -386,3 +386,25 @@ def test_kmeans_draws_are_data_independent_and_in_sklearn_order():
             pot, closest = d[best].sum(), d[best]
             idx.append(int(cand[best]))
         assert idx == list(ref_idx), (t, idx, list(ref_idx))
+
+
+def test_slab_layout_matches_the_worker_filter_rule():
+    """parallel._slab_layout (cached) against the definition: rank r owns the jobs idx % world == r (cnmf.py:52-53), its
+    slab holds their spectra in job order, every slab padded to the largest per-rank row count."""
+    from cnmf_b200.parallel import _slab_layout, shard_jobs
+    ks_all = [k for k in (5, 7, 13, 6) for _ in range(11)]
+    for world in (1, 2, 3, 8):
+        rows_per_rank, max_rows, first_row, per_rank = _slab_layout(ks_all, world)
+        assert per_rank == [shard_jobs(len(ks_all), r, world) for r in range(world)]
+        assert rows_per_rank == [sum(ks_all[j] for j in jobs) for jobs in per_rank]
+        assert max_rows == max(rows_per_rank)
+        seen = set()
+        for r, jobs in enumerate(per_rank):
+            o = 0
+            for j in jobs:
+                assert first_row[j] == r * max_rows + o
+                rows = set(range(first_row[j], first_row[j] + ks_all[j]))
+                assert not (rows & seen)
+                seen |= rows
+                o += ks_all[j]
+        assert _slab_layout(list(ks_all), world) is _slab_layout(tuple(ks_all), world)      # cached by value
