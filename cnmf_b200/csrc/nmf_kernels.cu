@@ -432,6 +432,103 @@ __device__ __forceinline__ void fused_gram_tile(float* tile, double* gsum) {
   __syncthreads();                                            // scratch (= tile) free again
 }
 
+// KP = 12 / 16 (four row blocks of RB = KP / 4 components): the Gram is symmetric, so only the 10 blocks on or above the
+// diagonal are accumulated -- 3 + 3 + 3 + 1 blocks over the four warps (27 instead of 36 entries per thread at KP = 12,
+// 48 instead of 64 at KP = 16, where the full row block did not fit in 128 registers) -- and the reduction reads an entry
+// below the diagonal from its mirror image.  Every entry is still the fixed-order fp64 sum over the 32 lanes of ONE warp
+// of per-lane fp32 sums over the same 4 quads in the same order, and a * b = b * a: bit-identical to the full version.
+struct SymGramMap {
+  // block (bi, bj), bi <= bj  ->  owning warp and its slot in that warp's list
+  //   warp 0: (0,0) (0,1) (0,2)   warp 1: (0,3) (1,1) (1,2)   warp 2: (1,3) (2,2) (2,3)   warp 3: (3,3)
+  static __device__ __forceinline__ void owner(int bi, int bj, int& warp, int& slot) {
+    const int id = bi * 4 + bj - (bi * (bi + 1)) / 2;       // 0..9 in row-major order of the upper triangle
+    warp = id / 3;
+    slot = id % 3;
+  }
+};
+
+template <int KP, int TILE, int W>
+__device__ __forceinline__ void sym_gram_accumulate(const float* tile, float2 (&acc)[3][KP / 4][KP / 4]) {
+  constexpr int RB = KP / 4;
+  constexpr int NB = W == 3 ? 1 : 3;
+  // blocks of this warp as (bi, bj)
+  constexpr int BI[3] = {W == 0 ? 0 : (W == 1 ? 0 : (W == 2 ? 1 : 3)), W == 0 ? 0 : (W == 1 ? 1 : 2), W == 0 ? 0 : (W == 1 ? 1 : 2)};
+  constexpr int BJ[3] = {W == 0 ? 0 : (W == 1 ? 3 : (W == 2 ? 3 : 3)), W == 0 ? 1 : (W == 1 ? 1 : 2), W == 0 ? 2 : (W == 1 ? 2 : 3)};
+  const int lane = threadIdx.x & 31;
+  const float4* t4 = reinterpret_cast<const float4*>(tile);
+  constexpr int QUADS = TILE / 4, ROW4 = TILE / 4;
+#pragma unroll 1
+  for (int q = lane; q < QUADS; q += 32) {
+    float4 v[4][RB];                                  // the row blocks this warp touches (unused ones are never loaded)
+#pragma unroll
+    for (int blk = 0; blk < 4; ++blk) {
+      bool used = false;
+#pragma unroll
+      for (int k = 0; k < NB; ++k) used = used || BI[k] == blk || BJ[k] == blk;
+      if (used) {
+#pragma unroll
+        for (int a = 0; a < RB; ++a) v[blk][a] = t4[(blk * RB + a) * ROW4 + q];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k)
+#pragma unroll
+      for (int a = 0; a < RB; ++a)
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+          const float4 x = v[BI[k]][a], y = v[BJ[k]][b];
+          acc[k][a][b] = fma2(make_float2(x.x, x.y), make_float2(y.x, y.y), acc[k][a][b]);
+          acc[k][a][b] = fma2(make_float2(x.z, x.w), make_float2(y.z, y.w), acc[k][a][b]);
+        }
+  }
+}
+
+template <int KP, int TILE>
+__device__ __forceinline__ void fused_gram_tile_sym(float* tile, double* gsum) {
+  constexpr int RB = KP / 4;
+  constexpr int STRIDE = 3 * RB * RB + 1;
+  static_assert(UPD_THREADS == 128, "four warps share the ten blocks");
+  static_assert(UPD_THREADS * STRIDE <= KP * TILE, "reduction scratch must fit in the tile it aliases");
+  const int warp = threadIdx.x >> 5;
+  float2 acc[3][RB][RB];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int a = 0; a < RB; ++a)
+#pragma unroll
+      for (int b = 0; b < RB; ++b) acc[k][a][b] = make_float2(0.f, 0.f);
+  switch (warp) {                                             // warp-uniform; block lists are compile-time constants
+    case 0: sym_gram_accumulate<KP, TILE, 0>(tile, acc); break;
+    case 1: sym_gram_accumulate<KP, TILE, 1>(tile, acc); break;
+    case 2: sym_gram_accumulate<KP, TILE, 2>(tile, acc); break;
+    default: sym_gram_accumulate<KP, TILE, 3>(tile, acc); break;
+  }
+  __syncthreads();                                            // every warp is done reading the tile
+  float* scratch = tile + threadIdx.x * STRIDE;               // odd stride: conflict-free scalar accesses
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int a = 0; a < RB; ++a)
+#pragma unroll
+      for (int b = 0; b < RB; ++b) scratch[(k * RB + a) * RB + b] = acc[k][a][b].x + acc[k][a][b].y;
+  __syncthreads();
+  for (int e = threadIdx.x; e < KP * KP; e += UPD_THREADS) {  // entry (row, i): fixed-order fp64 sum over its warp's lanes
+    const int row = e / KP, i = e % KP;
+    const int r0 = min(row, i), r1 = max(row, i);             // the entry on or above the diagonal that holds the value
+    int bi = r0 / RB, bj = r1 / RB, a = r0 % RB, b = r1 % RB;
+    // inside a diagonal block both (a, b) and (b, a) were accumulated; take the one the full version used: (row, i)
+    if (bi == bj) { a = row % RB; b = i % RB; }
+    int w, slot;
+    SymGramMap::owner(bi, bj, w, slot);
+    const float* src = tile + (size_t)(w * 32) * STRIDE + (slot * RB + a) * RB + b;
+    double sum = 0.0;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) sum += (double)src[l * STRIDE];
+    gsum[e] += sum;
+  }
+  __syncthreads();                                            // scratch (= tile) free again
+}
+
 // f16x2: fp16 operand pieces of the tile a block has just written, straight from the shared-memory tile (so the factor
 // is not read back from HBM by a separate launch).  Normalisation is per (row, 512-column tile): the warp that owns a
 // row takes the tile maximum of F * pscale, picks the power of two that puts it in [2^14, 2^15) and emits
@@ -450,38 +547,128 @@ __device__ __forceinline__ void emit_tile_f16(const FactorView& f, const float* 
   const int group = t0 / TILE;
   for (int c = warp; c < K; c += UPD_THREADS / 32) {
     const float4* src = reinterpret_cast<const float4*>(tile + c * TILE);
-    float4 v[4];
+    float2 v[4][2];                            // packed pairs: the scalings and the residual run on the 2-wide pipe
     float m = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      v[j] = src[lane + 32 * j];
-      v[j].x *= ps[j].x; v[j].y *= ps[j].y; v[j].z *= ps[j].z; v[j].w *= ps[j].w;
-      m = fmaxf(fmaxf(m, fmaxf(v[j].x, v[j].y)), fmaxf(v[j].z, v[j].w));
+      const float4 q = src[lane + 32 * j];
+      v[j][0] = mul2(make_float2(q.x, q.y), make_float2(ps[j].x, ps[j].y));
+      v[j][1] = mul2(make_float2(q.z, q.w), make_float2(ps[j].z, ps[j].w));
+      m = fmaxf(fmaxf(m, fmaxf(v[j][0].x, v[j][0].y)), fmaxf(v[j][1].x, v[j][1].y));
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
     const float sc = f16_group_scale(m);       // same bits as the stand-alone emit_f16_kernel
-    const float inv = 1.f / sc;
+    // sc = 2^e with e in [-126, 113] (f16_group_scale): 1 / sc is the same float with the exponent mirrored -- exactly
+    // what the division returns, without the division
+    const float2 inv = bcast2(__uint_as_float(0x7f000000u - __float_as_uint(sc)));
     const long long rowoff = (long long)(o + c) * f.ld;
     if (lane == 0) f.tile_scale[(long long)(o + c) * f.n_ktiles + group] = sc;
-    __half* ph = static_cast<__half*>(f.P_hi) + rowoff;
-    __half* pm = static_cast<__half*>(f.P_mid) + rowoff;
+    __half* ph = static_cast<__half*>(f.P_hi) + rowoff + t0 + 4 * lane;
+    __half* pm = static_cast<__half*>(f.P_mid) + rowoff + t0 + 4 * lane;
+    const int cols_left = f.ld - (t0 + 4 * lane);        // ld is a multiple of 4: a quad is written whole or not at all
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int col = t0 + 4 * lane + 128 * j;
-      if (col < f.ld) {
-        const float x0 = v[j].x * inv, x1 = v[j].y * inv, x2 = v[j].z * inv, x3 = v[j].w * inv;
-        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
-        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-        const __half2 m01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), m23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+      if (128 * j < cols_left) {
+        const float2 x01 = mul2(v[j][0], inv), x23 = mul2(v[j][1], inv);
+        const __half2 h01 = __float22half2_rn(x01), h23 = __float22half2_rn(x23);
+        const float2 r01 = add2(x01, neg2(__half22float2(h01))), r23 = add2(x23, neg2(__half22float2(h23)));
+        const __half2 m01 = __float22half2_rn(r01), m23 = __float22half2_rn(r23);
         uint2 oh, om;
         oh.x = *reinterpret_cast<const uint32_t*>(&h01); oh.y = *reinterpret_cast<const uint32_t*>(&h23);
         om.x = *reinterpret_cast<const uint32_t*>(&m01); om.y = *reinterpret_cast<const uint32_t*>(&m23);
-        *reinterpret_cast<uint2*>(ph + col) = oh;
-        *reinterpret_cast<uint2*>(pm + col) = om;
+        *reinterpret_cast<uint2*>(ph + 128 * j) = oh;
+        *reinterpret_cast<uint2*>(pm + 128 * j) = om;
       }
     }
   }
+}
+
+// 16-byte shared-memory load by 32-bit shared-window address: the Gram rows are addressed from a register that is set up
+// once per block (ptxas otherwise rebuilds the window base of the static array inside the component loop)
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// Component loop of the streamed-product MU update (mu_body, STREAMN): for c = 0..K-1
+//   den = Gram[c,:] . F_old[:, items] (component order) + l1 + l2 F_old[c];  F_new[c] = F_old[c] * NUM[c] / den
+// with NUM[c + 1] already in flight.  Running pointers (one 64-bit add per array and component), the Gram row by shared
+// address, two components per trip (the in-flight registers alternate instead of being copied), and the ragged last
+// item group of a row (n % 4 != 0: product columns >= n are undefined) as its own instantiation so that the common
+// case carries no selects.  SIMPLE = one product slice and no tf32 pieces to write (the W half of the default f16x2
+// path): the slice loop and the piece pointers drop out of the body.  Same arithmetic, same order as the rolled loop
+// of round 1.
+template <int KP, int VEC, bool GRAM, bool RAGGED, bool SIMPLE>
+__device__ __forceinline__ float2 mu_components(float* __restrict__ pFc, float* pH, float* pL, const float* __restrict__ pNc,
+                                                int nsplit, long long sstride, unsigned ld, unsigned g_row, int K, float l1,
+                                                float l2, int n_left, const float2 (&fv)[KP][VecIO<VEC>::NP],
+                                                const float2 (&pscale)[VecIO<VEC>::NP], float* myF) {
+  constexpr int NP = VecIO<VEC>::NP;
+  constexpr int TILE = UPD_THREADS * VEC;
+  float2 sacc = make_float2(0.f, 0.f);
+  float2 nvn[NP];
+  VecIO<VEC>::ld(pNc, nvn);
+#pragma unroll 2
+  for (int c = 0; c < K; ++c) {
+    float2 den[NP];                                  // summed in component order, like the reference's W @ HHt row
+#pragma unroll
+    for (int i4 = 0; i4 < KP / 4; ++i4) {
+      const float4 gq = lds128(g_row + 16 * i4);
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        den[p] = i4 == 0 ? mul2(bcast2(gq.x), fv[0][p]) : fma2(bcast2(gq.x), fv[4 * i4 + 0][p], den[p]);
+        den[p] = fma2(bcast2(gq.y), fv[4 * i4 + 1][p], den[p]);
+        den[p] = fma2(bcast2(gq.z), fv[4 * i4 + 2][p], den[p]);
+        den[p] = fma2(bcast2(gq.w), fv[4 * i4 + 3][p], den[p]);
+      }
+    }
+    g_row += 4 * KP;
+    float2 fvc[NP], nvc[NP], out[NP];
+    VecIO<VEC>::ld(myF, fvc);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) nvc[p] = nvn[p];
+    // the last component re-reads its own row instead of predicating the load (a predicated load has to preserve its
+    // destination registers, which costs the copies the two-component trip is there to avoid)
+    VecIO<VEC>::ld(pNc + ((c + 1 < K) ? ld : 0u), nvn);
+    if constexpr (!SIMPLE) {
+      for (int s = 1; s < nsplit; ++s) {             // split-K slices, added in slice order
+        float2 t[NP];
+        VecIO<VEC>::ld(pNc + s * sstride, t);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) nvc[p] = add2(nvc[p], t[p]);
+      }
+    }
+    if constexpr (RAGGED) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        if (2 * p >= n_left) nvc[p].x = 0.f;
+        if (2 * p + 1 >= n_left) nvc[p].y = 0.f;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      // regularisation terms unconditionally: adding l1 = 0 and l2 * F = 0 is exact, a uniform branch costs more
+      float2 d = fma2(bcast2(l2), fvc[p], add2(den[p], bcast2(l1)));
+      // zero denominators -> eps (sklearn _nmf.py:615,701); the Newton quotient needs a normal number
+      d.x = (d.x < FLT_MIN_NORMAL) ? EPSILON_F32 : d.x;
+      d.y = (d.y < FLT_MIN_NORMAL) ? EPSILON_F32 : d.y;
+      out[p] = mul2(fvc[p], div_nr2(nvc[p], d));
+      sacc = fma2(nvc[p], out[p], sacc);
+    }
+    if constexpr (SIMPLE) {
+      VecIO<VEC>::st(pFc, out);
+    } else {
+      store_items<VEC>(pFc, pH, pL, 0u, out, pscale);
+      if (pH) { pH += ld; pL += ld; }
+    }
+    if constexpr (GRAM) VecIO<VEC>::st(myF, out);
+    pFc += ld;
+    pNc += ld;
+    myF += TILE;
+  }
+  return sacc;
 }
 
 // Multiplicative update, rolled over the components: the thread's old values stay in registers for the K x K
@@ -498,6 +685,8 @@ __device__ __forceinline__ double mu_body(const FactorView& f, const float* __re
   constexpr int NP = VecIO<VEC>::NP;
   constexpr int TILE = UPD_THREADS * VEC;
   const float4* G4 = reinterpret_cast<const float4*>(G);
+  const unsigned g_addr = (unsigned)__cvta_generic_to_shared(G);
+  const bool simple = nsplit == 1 && f.F_hi == nullptr;        // block-uniform
   const unsigned ld = (unsigned)f.ld;
   float* const myF = tileF + VEC * threadIdx.x;
   float* const myN = tileN + VEC * threadIdx.x;
@@ -513,7 +702,6 @@ __device__ __forceinline__ double mu_body(const FactorView& f, const float* __re
       float2 fv[KP][NP];
       const float* const pN = NUM + e0;
       const int n_left = f.n - col;
-      float2 nvn[NP];                                // STREAMN: the products of component c + 1, in flight
       if constexpr (STREAMN) {
 #pragma unroll
         for (int i = 0; i < KP; ++i) {
@@ -524,7 +712,6 @@ __device__ __forceinline__ double mu_body(const FactorView& f, const float* __re
             for (int p = 0; p < NP; ++p) fv[i][p] = make_float2(0.f, 0.f);
           }
         }
-        VecIO<VEC>::ld(pN, nvn);
         if (n_left < VEC) {                          // ragged tail: columns >= n of the factor count as zeros
 #pragma unroll
           for (int i = 0; i < KP; ++i)
@@ -550,58 +737,53 @@ __device__ __forceinline__ double mu_body(const FactorView& f, const float* __re
       for (int p = 0; p < NP; ++p) pscale[p] = make_float2(1.f, 1.f);
       if (f.piece_scale) VecIO<VEC>::ld(f.piece_scale + col, pscale);
       float2 sacc = make_float2(0.f, 0.f);
-      unsigned off = 0;
-#pragma unroll 1
-      for (int c = 0; c < K; ++c, off += ld) {
-        float2 den[NP];                              // summed in component order, like the reference's W @ HHt row
-#pragma unroll
-        for (int i4 = 0; i4 < KP / 4; ++i4) {
-          const float4 gq = G4[c * (KP / 4) + i4];
-#pragma unroll
-          for (int p = 0; p < NP; ++p) {
-            den[p] = i4 == 0 ? mul2(bcast2(gq.x), fv[0][p]) : fma2(bcast2(gq.x), fv[4 * i4 + 0][p], den[p]);
-            den[p] = fma2(bcast2(gq.y), fv[4 * i4 + 1][p], den[p]);
-            den[p] = fma2(bcast2(gq.z), fv[4 * i4 + 2][p], den[p]);
-            den[p] = fma2(bcast2(gq.w), fv[4 * i4 + 3][p], den[p]);
-          }
+      if constexpr (STREAMN) {
+        if (simple) {
+          if (n_left >= VEC)
+            sacc = mu_components<KP, VEC, GRAM, false, true>(pF, pH, pL, pN, 1, 0, ld, g_addr, K, l1, l2, n_left, fv, pscale, myF);
+          else
+            sacc = mu_components<KP, VEC, GRAM, true, true>(pF, pH, pL, pN, 1, 0, ld, g_addr, K, l1, l2, n_left, fv, pscale, myF);
+        } else {
+          if (n_left >= VEC)
+            sacc = mu_components<KP, VEC, GRAM, false, false>(pF, pH, pL, pN, nsplit, sstride, ld, g_addr, K, l1, l2, n_left, fv,
+                                                              pscale, myF);
+          else
+            sacc = mu_components<KP, VEC, GRAM, true, false>(pF, pH, pL, pN, nsplit, sstride, ld, g_addr, K, l1, l2, n_left, fv,
+                                                             pscale, myF);
         }
-        float2 fvc[NP], nvc[NP], out[NP];
-        VecIO<VEC>::ld(myF + c * TILE, fvc);
-        if constexpr (STREAMN) {
-          // the products are read once, straight from global memory, one component ahead of their use (the
-          // component loop body is ~100 instructions: enough lead for an L2 / HBM access at 4 blocks per SM)
+      } else {
+        unsigned off = 0;
+#pragma unroll 1
+        for (int c = 0; c < K; ++c, off += ld) {
+          float2 den[NP];                            // summed in component order, like the reference's W @ HHt row
 #pragma unroll
-          for (int p = 0; p < NP; ++p) nvc[p] = nvn[p];
-          if (c + 1 < K) VecIO<VEC>::ld(pN + off + ld, nvn);
-          for (int s = 1; s < nsplit; ++s) {         // split-K slices, added in slice order
-            float2 t[NP];
-            VecIO<VEC>::ld(pN + s * sstride + off, t);
-#pragma unroll
-            for (int p = 0; p < NP; ++p) nvc[p] = add2(nvc[p], t[p]);
-          }
-          if (n_left < VEC) {                        // product columns >= n are not defined
+          for (int i4 = 0; i4 < KP / 4; ++i4) {
+            const float4 gq = G4[c * (KP / 4) + i4];
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
-              if (2 * p >= n_left) nvc[p].x = 0.f;
-              if (2 * p + 1 >= n_left) nvc[p].y = 0.f;
+              den[p] = i4 == 0 ? mul2(bcast2(gq.x), fv[0][p]) : fma2(bcast2(gq.x), fv[4 * i4 + 0][p], den[p]);
+              den[p] = fma2(bcast2(gq.y), fv[4 * i4 + 1][p], den[p]);
+              den[p] = fma2(bcast2(gq.z), fv[4 * i4 + 2][p], den[p]);
+              den[p] = fma2(bcast2(gq.w), fv[4 * i4 + 3][p], den[p]);
             }
           }
-        } else {
+          float2 fvc[NP], nvc[NP], out[NP];
+          VecIO<VEC>::ld(myF + c * TILE, fvc);
           VecIO<VEC>::ld(myN + c * TILE, nvc);
-        }
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-          // regularisation terms unconditionally: adding l1 = 0 and l2 * F = 0 is exact, a uniform branch costs more
-          const float2 d0 = fma2(bcast2(l2), fvc[p], add2(den[p], bcast2(l1)));
-          float2 d = d0;
-          // zero denominators -> eps (sklearn _nmf.py:615,701); the Newton quotient needs a normal number
-          d.x = (d.x < FLT_MIN_NORMAL) ? EPSILON_F32 : d.x;
-          d.y = (d.y < FLT_MIN_NORMAL) ? EPSILON_F32 : d.y;
-          out[p] = mul2(fvc[p], div_nr2(nvc[p], d));
-          sacc = fma2(nvc[p], out[p], sacc);
+          for (int p = 0; p < NP; ++p) {
+            // regularisation terms unconditionally: adding l1 = 0 and l2 * F = 0 is exact, a uniform branch costs more
+            const float2 d0 = fma2(bcast2(l2), fvc[p], add2(den[p], bcast2(l1)));
+            float2 d = d0;
+            // zero denominators -> eps (sklearn _nmf.py:615,701); the Newton quotient needs a normal number
+            d.x = (d.x < FLT_MIN_NORMAL) ? EPSILON_F32 : d.x;
+            d.y = (d.y < FLT_MIN_NORMAL) ? EPSILON_F32 : d.y;
+            out[p] = mul2(fvc[p], div_nr2(nvc[p], d));
+            sacc = fma2(nvc[p], out[p], sacc);
+          }
+          store_items<VEC>(pF, pH, pL, off, out, pscale);
+          if constexpr (GRAM) VecIO<VEC>::st(myF + c * TILE, out);
         }
-        store_items<VEC>(pF, pH, pL, off, out, pscale);
-        if constexpr (GRAM) VecIO<VEC>::st(myF + c * TILE, out);
       }
       scal += (double)(sacc.x + sacc.y);
     } else if constexpr (GRAM) {
@@ -616,7 +798,8 @@ __device__ __forceinline__ double mu_body(const FactorView& f, const float* __re
       if constexpr (VEC == 4) {
         if (f.P_hi) emit_tile_f16<TILE>(f, tileF, K, o, t0);
       }
-      fused_gram_tile<KP, TILE>(tileF, gsum);
+      if constexpr (KP == 12 || KP == 16) fused_gram_tile_sym<KP, TILE>(tileF, gsum);
+      else fused_gram_tile<KP, TILE>(tileF, gsum);
     }
   }
   return scal;
