@@ -595,7 +595,7 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
 // Component loop of the streamed-product MU update (mu_body, STREAMN): for c = 0..K-1
 //   den = Gram[c,:] . F_old[:, items] (component order) + l1 + l2 F_old[c];  F_new[c] = F_old[c] * NUM[c] / den
 // with NUM[c + 1] already in flight.  Running pointers (one 64-bit add per array and component), the Gram row by shared
-// address, two components per trip (the in-flight registers alternate instead of being copied), and the ragged last
+// address, three components per trip (the in-flight registers rotate instead of being copied), and the ragged last
 // item group of a row (n % 4 != 0: product columns >= n are undefined) as its own instantiation so that the common
 // case carries no selects.  SIMPLE = one product slice and no tf32 pieces to write (the W half of the default f16x2
 // path): the slice loop and the piece pointers drop out of the body.  Same arithmetic, same order as the rolled loop
@@ -608,9 +608,12 @@ __device__ __forceinline__ float2 mu_components(float* __restrict__ pFc, float* 
   constexpr int NP = VecIO<VEC>::NP;
   constexpr int TILE = UPD_THREADS * VEC;
   float2 sacc = make_float2(0.f, 0.f);
-  float2 nvn[NP];
+  // products of components c + 1 and c + 2 in flight: one component of lead (~80 instructions) left the quotient
+  // waiting on the load (15 % of the kernel's stall samples, profiles/r2s_ncu_update_summary.txt)
+  float2 nvn[NP], nvn2[NP];
   VecIO<VEC>::ld(pNc, nvn);
-#pragma unroll 2
+  VecIO<VEC>::ld(pNc + (1 < K ? ld : 0u), nvn2);
+#pragma unroll 3
   for (int c = 0; c < K; ++c) {
     float2 den[NP];                                  // summed in component order, like the reference's W @ HHt row
 #pragma unroll
@@ -628,10 +631,10 @@ __device__ __forceinline__ float2 mu_components(float* __restrict__ pFc, float* 
     float2 fvc[NP], nvc[NP], out[NP];
     VecIO<VEC>::ld(myF, fvc);
 #pragma unroll
-    for (int p = 0; p < NP; ++p) nvc[p] = nvn[p];
-    // the last component re-reads its own row instead of predicating the load (a predicated load has to preserve its
-    // destination registers, which costs the copies the two-component trip is there to avoid)
-    VecIO<VEC>::ld(pNc + ((c + 1 < K) ? ld : 0u), nvn);
+    for (int p = 0; p < NP; ++p) { nvc[p] = nvn[p]; nvn[p] = nvn2[p]; }
+    // the last components re-read their own row instead of predicating the load (a predicated load has to preserve its
+    // destination registers, which costs the copies the unrolled trip is there to avoid)
+    VecIO<VEC>::ld(pNc + ((c + 2 < K) ? 2u * ld : 0u), nvn2);
     if constexpr (!SIMPLE) {
       for (int s = 1; s < nsplit; ++s) {             // split-K slices, added in slice order
         float2 t[NP];
