@@ -483,8 +483,43 @@ __device__ __forceinline__ void sym_gram_accumulate(const float* tile, float2 (&
   }
 }
 
+// What a thread adds up in the reduction of fused_gram_tile_sym, fixed for the whole block: entries t = tid, tid + 128
+// of the KP (KP + 1) / 2 entries on or above the diagonal (row-major), each read from its owner's scratch slot and added
+// to gsum[row][i] and to its mirror image gsum[i][row].
+// (Kept in shared memory, 3 words per entry: registers that live across the tile loop would be spilled.)
+template <int KP> struct SymGramPlan {
+  static constexpr int NUP = KP * (KP + 1) / 2;
+  static constexpr int ROUNDS = (NUP + UPD_THREADS - 1) / UPD_THREADS;
+};
+constexpr int SYM_PLAN_WORDS = 3 * 2 * UPD_THREADS;       // ROUNDS <= 2 for KP <= 16
+
+template <int KP>
+__device__ __forceinline__ void sym_gram_plan(int* plan) {    // plan[(r * 3 + {0: src, 1: e1, 2: e2}) * UPD_THREADS + tid]
+  constexpr int RB = KP / 4;
+  constexpr int STRIDE = 3 * RB * RB + 1;
+  static_assert(SymGramPlan<KP>::ROUNDS <= 2, "plan buffer holds two rounds");
+#pragma unroll
+  for (int r = 0; r < SymGramPlan<KP>::ROUNDS; ++r) {
+    const int t = threadIdx.x + r * UPD_THREADS;
+    int row = 0, rem = t;
+    while (row < KP - 1 && rem >= KP - row) { rem -= KP - row; ++row; }   // t -> (row, i), row <= i, row-major
+    const int i = row + rem;
+    int src = -1, e1 = 0, e2 = 0;
+    if (t < SymGramPlan<KP>::NUP) {
+      int w, slot;
+      SymGramMap::owner(row / RB, i / RB, w, slot);
+      src = (w * 32) * STRIDE + (slot * RB + row % RB) * RB + i % RB;
+      e1 = row * KP + i;
+      e2 = i * KP + row;
+    }
+    plan[(r * 3 + 0) * UPD_THREADS + threadIdx.x] = src;
+    plan[(r * 3 + 1) * UPD_THREADS + threadIdx.x] = e1;
+    plan[(r * 3 + 2) * UPD_THREADS + threadIdx.x] = e2;
+  }
+}
+
 template <int KP, int TILE>
-__device__ __forceinline__ void fused_gram_tile_sym(float* tile, double* gsum) {
+__device__ __forceinline__ void fused_gram_tile_sym(float* tile, double* gsum, const int* plan) {
   constexpr int RB = KP / 4;
   constexpr int STRIDE = 3 * RB * RB + 1;
   static_assert(UPD_THREADS == 128, "four warps share the ten blocks");
@@ -512,19 +547,18 @@ __device__ __forceinline__ void fused_gram_tile_sym(float* tile, double* gsum) {
 #pragma unroll
       for (int b = 0; b < RB; ++b) scratch[(k * RB + a) * RB + b] = acc[k][a][b].x + acc[k][a][b].y;
   __syncthreads();
-  for (int e = threadIdx.x; e < KP * KP; e += UPD_THREADS) {  // entry (row, i): fixed-order fp64 sum over its warp's lanes
-    const int row = e / KP, i = e % KP;
-    const int r0 = min(row, i), r1 = max(row, i);             // the entry on or above the diagonal that holds the value
-    int bi = r0 / RB, bj = r1 / RB, a = r0 % RB, b = r1 % RB;
-    // inside a diagonal block both (a, b) and (b, a) were accumulated; take the one the full version used: (row, i)
-    if (bi == bj) { a = row % RB; b = i % RB; }
-    int w, slot;
-    SymGramMap::owner(bi, bj, w, slot);
-    const float* src = tile + (size_t)(w * 32) * STRIDE + (slot * RB + a) * RB + b;
-    double sum = 0.0;
+#pragma unroll
+  for (int r = 0; r < SymGramPlan<KP>::ROUNDS; ++r) {         // fixed-order fp64 sum over the owner warp's 32 lanes
+    const int so = plan[(r * 3 + 0) * UPD_THREADS + threadIdx.x];
+    if (so >= 0) {
+      const int e1 = plan[(r * 3 + 1) * UPD_THREADS + threadIdx.x], e2 = plan[(r * 3 + 2) * UPD_THREADS + threadIdx.x];
+      const float* src = tile + so;
+      double sum = 0.0;
 #pragma unroll 8
-    for (int l = 0; l < 32; ++l) sum += (double)src[l * STRIDE];
-    gsum[e] += sum;
+      for (int l = 0; l < 32; ++l) sum += (double)src[l * STRIDE];
+      gsum[e1] += sum;
+      if (e2 != e1) gsum[e2] += sum;                          // a * b = b * a: the mirror entry is the same sum
+    }
   }
   __syncthreads();                                            // scratch (= tile) free again
 }
@@ -694,6 +728,9 @@ __device__ __forceinline__ double mu_body(const FactorView& f, const float* __re
   float* const myF = tileF + VEC * threadIdx.x;
   float* const myN = tileN + VEC * threadIdx.x;
   double scal = 0.0;
+  constexpr bool SYM = GRAM && (KP == 12 || KP == 16);
+  __shared__ int gplan[SYM ? SYM_PLAN_WORDS : 1];
+  if constexpr (SYM) sym_gram_plan<KP>(gplan);                // read after the tile loop's first barrier
 #pragma unroll 1
   for (int t0 = col_begin; t0 < col_end; t0 += TILE) {
     const int col = t0 + VEC * threadIdx.x;
@@ -801,7 +838,7 @@ __device__ __forceinline__ double mu_body(const FactorView& f, const float* __re
       if constexpr (VEC == 4) {
         if (f.P_hi) emit_tile_f16<TILE>(f, tileF, K, o, t0);
       }
-      if constexpr (KP == 12 || KP == 16) fused_gram_tile_sym<KP, TILE>(tileF, gsum);
+      if constexpr (SYM) fused_gram_tile_sym<KP, TILE>(tileF, gsum, gplan);
       else fused_gram_tile<KP, TILE>(tileF, gsum);
     }
   }
