@@ -728,7 +728,7 @@ __device__ __forceinline__ double mu_body(const FactorView& f, const float* __re
   float* const myF = tileF + VEC * threadIdx.x;
   float* const myN = tileN + VEC * threadIdx.x;
   double scal = 0.0;
-  constexpr bool SYM = GRAM && (KP == 12 || KP == 16);
+  constexpr bool SYM = GRAM && VEC == 4 && (KP == 12 || KP == 16);
   __shared__ int gplan[SYM ? SYM_PLAN_WORDS : 1];
   if constexpr (SYM) sym_gram_plan<KP>(gplan);                // read after the tile loop's first barrier
 #pragma unroll 1
@@ -857,6 +857,9 @@ __device__ __forceinline__ double update_body(const FactorView& f, const float* 
   const volatile float* Gs = G;
   const unsigned ld = (unsigned)f.ld;
   double scal = 0.0;
+  constexpr bool SYM = GRAM && VEC == 4 && (KP == 12 || KP == 16);
+  __shared__ int gplan[SYM ? SYM_PLAN_WORDS : 1];
+  if constexpr (SYM) sym_gram_plan<KP>(gplan);
 #pragma unroll 1
   for (int t0 = col_begin; t0 < col_end; t0 += TILE) {
     const int col = t0 + VEC * threadIdx.x;
@@ -955,7 +958,8 @@ __device__ __forceinline__ double update_body(const FactorView& f, const float* 
       if constexpr (VEC == 4) {
         if (f.P_hi) emit_tile_f16<TILE>(f, tile, K, o, t0);
       }
-      fused_gram_tile<KP, TILE>(tile, gsum);
+      if constexpr (SYM) fused_gram_tile_sym<KP, TILE>(tile, gsum, gplan);
+      else fused_gram_tile<KP, TILE>(tile, gsum);
     }
   }
   return scal;
