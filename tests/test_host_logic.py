@@ -408,3 +408,48 @@ def test_slab_layout_matches_the_worker_filter_rule():
                 seen |= rows
                 o += ks_all[j]
         assert _slab_layout(list(ks_all), world) is _slab_layout(tuple(ks_all), world)      # cached by value
+
+
+def test_symmetric_gram_plan_covers_every_entry_once():
+    """Index arithmetic of the update kernels' symmetric Gram (nmf_kernels.cu: SymGramMap, sym_gram_accumulate's block
+    lists, sym_gram_plan), restated: the 10 blocks on or above the diagonal go 3 + 3 + 3 + 1 to the four warps; every
+    entry (row, i) of the KP x KP Gram receives exactly one sum, read from a scratch slot that its owner warp wrote, and
+    the mirror image of an entry reads the same slot."""
+    lists = {0: [(0, 0), (0, 1), (0, 2)], 1: [(0, 3), (1, 1), (1, 2)], 2: [(1, 3), (2, 2), (2, 3)], 3: [(3, 3)]}
+
+    def owner(bi, bj):
+        idx = bi * 4 + bj - (bi * (bi + 1)) // 2
+        return idx // 3, idx % 3
+
+    for w, blocks in lists.items():                     # the compile-time lists and the closed form agree
+        for slot, (bi, bj) in enumerate(blocks):
+            assert owner(bi, bj) == (w, slot)
+    assert sorted(b for bl in lists.values() for b in bl) == [(i, j) for i in range(4) for j in range(i, 4)]
+
+    threads = 128
+    for KP in (12, 16):
+        RB = KP // 4
+        stride = 3 * RB * RB + 1
+        assert threads * stride <= KP * 512             # the scratch aliases the KP x 512 tile
+        nup = KP * (KP + 1) // 2
+        written = {}
+        slots = set()
+        for t in range(nup):
+            row, rem = 0, t
+            while row < KP - 1 and rem >= KP - row:
+                rem -= KP - row
+                row += 1
+            i = row + rem
+            assert row <= i < KP
+            w, slot = owner(row // RB, i // RB)
+            src = (w * 32) * stride + (slot * RB + row % RB) * RB + i % RB
+            assert slot < len(lists[w]) and (slot * RB + row % RB) * RB + i % RB < stride - 1
+            assert src not in slots                     # one distinct slot per distinct entry
+            slots.add(src)
+            for e in {row * KP + i, i * KP + row}:
+                assert e not in written
+                written[e] = src
+        assert sorted(written) == list(range(KP * KP))
+        for row in range(KP):
+            for i in range(KP):
+                assert written[row * KP + i] == written[i * KP + row]
