@@ -18,7 +18,7 @@ Printed JSON (rank 0): `value` = restarts/s with X resident in HBM (random init 
 left in HBM); `e2e` = the same through the public call with HOST buffers (H2D of X and device-side preparation, the
 solve, the all-gather, D2H of all spectra inside the timed region); `with_consensus` = factorize + all-gather +
 cNMF.consensus numerics for every K (Ks sharded over the ranks) with its HBM roofline; `roofline` = the dominant
-kernel (the batched tcgen05 GEMM) from CUDA events inside the timed region; `cpu_baseline` / `cd_default` = the
+kernel (the batched tcgen05 GEMM) from CUDA events inside the timed region (recorded on rank 0); `cpu_baseline` / `cd_default` = the
 reference's own scikit-learn call timed on the host cores.
 `--impl reference` times the reference's CPU implementation (oracle/reference_path.py: the reference's call
 sequence on scikit-learn, float64): one restart of the job table to convergence per step, K cycling through the
@@ -268,7 +268,9 @@ def run_ours(args, rank, world, local):
     if rank == 0:
         clocks.start()
     launches0 = eng.launch_count
-    eng.profile(True)
+    # per-launch CUDA events (the roofline's kernel times) on the rank that reports them; on the other ranks they would
+    # only add their ~3 us per launch to a max-over-ranks time nobody reads them from
+    eng.profile(rank == 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
