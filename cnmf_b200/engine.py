@@ -31,18 +31,52 @@ def _params_precision(p):
 
 def check_supported(ks=None, init="random", beta_loss="frobenius"):
     """Options the CUDA path does not implement are refused where the user states them (prepare / the CLI), not
-    hours later inside factorize: n_components > 32, init != 'random' (cnmf.py:1252 also offers 'nndsvd'),
-    beta_loss outside {frobenius, kullback-leibler, itakura-saito}."""
+    hours later inside factorize: n_components > 32, an init scikit-learn does not know, beta_loss outside
+    {frobenius, kullback-leibler, itakura-saito}.  init: 'random' (the reference default, cnmf.py:335; generated on
+    the device) and the NNDSVD family ('nndsvd' is the CLI's other choice, cnmf.py:1252; starting factors computed on
+    the host by cnmf_b200.nndsvd, then the same batched solve)."""
+    from .nndsvd import INITS
     if ks is not None:
         bad = [int(k) for k in np.atleast_1d(ks) if int(k) < 1 or int(k) > _lib.MAX_COMPONENTS]
         if bad:
             raise ValueError("cnmf_b200: n_components must be in [1, %d] on the CUDA path (got %s); the batched "
                              "kernels keep a restart's K x K Gram matrix and its K factor values per item on chip"
                              % (_lib.MAX_COMPONENTS, bad))
-    if init != "random":
-        raise NotImplementedError("cnmf_b200: only init='random' (the reference default, cnmf.py:335) is implemented "
-                                  "on the CUDA path (got %r)" % (init,))
+    if init is not None and init not in INITS:
+        raise ValueError("Invalid init parameter: got %r instead of one of %r" % (init, (None,) + INITS))
     loss_code(beta_loss)
+
+
+def nndsvd_starts(X, ks, seeds, init):
+    """Packed starting factors (W^T rows: sum ks x cells, H rows: sum ks x genes; fp32) of every restart (k, seed) for
+    init in {'nndsvd', 'nndsvda', 'nndsvdar', None}: scikit-learn's `_initialize_nmf` as the reference's call reaches it
+    (cnmf.py:672), restated in cnmf_b200/nndsvd.py.  One randomized SVD per restart on the host (threads: LAPACK / BLAS
+    release the GIL)."""
+    import concurrent.futures
+    import os
+    from .nndsvd import nndsvd_init, resolve_init
+    ks = [int(k) for k in ks]
+    n, g = X.shape
+    offs = np.concatenate([[0], np.cumsum(ks)]).astype(np.int64)
+    W0 = np.empty((int(offs[-1]), n), np.float32)
+    H0 = np.empty((int(offs[-1]), g), np.float32)
+
+    def one(r):
+        which = resolve_init(init, ks[r], n, g)
+        if which == "random":
+            raise ValueError("init=None resolves to 'random' for n_components > min(shape): use the seeded device generator")
+        W, H = nndsvd_init(X, ks[r], int(seeds[r]), which)
+        W0[offs[r]:offs[r + 1]] = W.T
+        H0[offs[r]:offs[r + 1]] = H
+
+    workers = max(1, min(8, (os.cpu_count() or 1) // 4, len(ks)))
+    if workers == 1:
+        for r in range(len(ks)):
+            one(r)
+    else:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=workers) as ex:
+            list(ex.map(one, range(len(ks))))
+    return W0, H0
 
 
 def make_params(nmf_kwargs, n_samples, n_features, precision, for_refit=False):
@@ -55,8 +89,8 @@ def make_params(nmf_kwargs, n_samples, n_features, precision, for_refit=False):
     loss = loss_code(beta)
     if loss != LOSS_FROBENIUS and solver != "mu":      # sklearn _nmf.py:1195-1199
         raise ValueError("Invalid beta_loss parameter: solver %r does not handle beta_loss = %r" % (solver, beta))
-    if not for_refit and nmf_kwargs.get("init", "random") != "random":      # no random init when update_H=False
-        raise NotImplementedError("cnmf_b200: only init='random' is implemented on the CUDA path")
+    if not for_refit:                                   # a refit (update_H=False) has no initialisation to choose
+        check_supported(None, nmf_kwargs.get("init", "random"), beta)
     if solver not in ("mu", "cd"):
         raise ValueError("solver must be 'mu' or 'cd'")
     alpha_W = float(nmf_kwargs.get("alpha_W", 0.0))
@@ -219,6 +253,9 @@ class Dataset:
         ks = np.ascontiguousarray(ks, dtype=np.int32)
         seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
         R = len(ks)
+        if nmf_kwargs.get("init", "random") != "random":
+            raise ValueError("factorize_seeds_dev draws the seeded random init on the device; init=%r goes through "
+                             "Dataset.factorize(X_host=...)" % (nmf_kwargs.get("init"),))
         p = self.params(nmf_kwargs)
         self._check_loss(p)
         n_iter = np.zeros(R, np.int32)
@@ -303,8 +340,10 @@ class Dataset:
     def params(self, nmf_kwargs):
         return make_params(nmf_kwargs, self.shape[0], self.shape[1], self.precision)
 
-    def factorize(self, ks, seeds, nmf_kwargs, return_usages=False, W0=None, H0=None):
-        """All restarts (ks[r], seeds[r]) at once.  Returns (spectra_list, usages_list|None, n_iter, err)."""
+    def factorize(self, ks, seeds, nmf_kwargs, return_usages=False, W0=None, H0=None, X_host=None):
+        """All restarts (ks[r], seeds[r]) at once.  Returns (spectra_list, usages_list|None, n_iter, err).
+        W0 / H0: packed starting factors (sum ks x cells, sum ks x genes) instead of the seeded random init; X_host: the
+        host matrix, needed only when nmf_kwargs['init'] is one of the NNDSVD family (starts computed from it)."""
         ks = np.ascontiguousarray(ks, dtype=np.int32)
         R = len(ks)
         SK = int(ks.sum())
@@ -315,6 +354,14 @@ class Dataset:
         usages = np.empty((SK, n), np.float32) if return_usages else None
         n_iter = np.zeros(R, np.int32)
         err = np.zeros(R, np.float64)
+        init = nmf_kwargs.get("init", "random")
+        if W0 is None and init != "random":
+            # NNDSVD family (cnmf.py:1252 / SK _nmf.py:309-369): starting factors from cnmf_b200.nndsvd on the host, one
+            # randomized SVD per restart (the seed enters through its test matrix), then the ordinary batched solve
+            if X_host is None:
+                raise ValueError("init=%r: pass X_host (the matrix the dataset was created from) or W0 / H0; the "
+                                 "device generator only covers init='random'" % (init,))
+            W0, H0 = nndsvd_starts(X_host, ks, seeds, init)
         if W0 is None:
             seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
             check(self.lib.cnmf_factorize(self._d, R, ptr(ks), ptr(seeds), ctypes.byref(p), ptr(spectra), ptr(usages),

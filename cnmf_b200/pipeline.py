@@ -279,13 +279,16 @@ class cNMF:
             H = np.asarray(kw["H"])
             W, _, _ = ds.refit(H, kw)
             return H, W.astype(np.float64)
-        sp, us, _, _ = ds.factorize([int(kw["n_components"])], [int(kw["random_state"])], kw, return_usages=True)
+        from .engine import Dataset
+        sp, us, _, _ = ds.factorize([int(kw["n_components"])], [int(kw["random_state"])], kw, return_usages=True,
+                                    X_host=None if isinstance(X, Dataset) else X)
         return sp[0].astype(np.float64), us[0].astype(np.float64)
 
-    def _nmf_batched(self, X, ks, seeds, nmf_kwargs):
-        """All restarts at once; returns list of spectra (float64) and per-restart iteration counts."""
+    def _nmf_batched(self, X, ks, seeds, nmf_kwargs, X_host=None):
+        """All restarts at once; returns list of spectra (float64) and per-restart iteration counts.  X_host: the host
+        matrix, used only for the NNDSVD family of initialisations (their SVD runs on the host)."""
         ds = self._dataset(X)
-        sp, _, n_iter, err = ds.factorize(ks, seeds, nmf_kwargs)
+        sp, _, n_iter, err = ds.factorize(ks, seeds, nmf_kwargs, X_host=X_host)
         return [s.astype(np.float64) for s in sp], n_iter, err
 
     # ------------------------------------------------------------------ factorize / combine
@@ -315,7 +318,7 @@ class cNMF:
                                                                         "" if len(groups) == 1 else "s"))
         hit_max = False
         for lo, hi in groups:
-            spectra, n_iter, _ = self._nmf_batched(ds, ks[lo:hi], seeds[lo:hi], kw)
+            spectra, n_iter, _ = self._nmf_batched(ds, ks[lo:hi], seeds[lo:hi], kw, X_host=norm.X)
             hit_max = hit_max or int(np.max(n_iter)) >= int(kw["max_iter"])
             for j, sp in zip(jobs[lo:hi], spectra):
                 p = run_params.iloc[j]
@@ -584,9 +587,9 @@ def main():
     ap.add_argument("--tpm", type=str, default=None)
     ap.add_argument("--max-nmf-iter", type=int, default=1000)
     ap.add_argument("--beta-loss", type=str, choices=["frobenius", "kullback-leibler", "itakura-saito"], default="frobenius")
-    ap.add_argument("--init", type=str, choices=["random"], default="random",
-                    help="[cnmf_b200] only the reference default 'random' is implemented on the CUDA path (cnmf.py:1252 "
-                         "also offers 'nndsvd')")
+    ap.add_argument("--init", type=str, choices=["random", "nndsvd"], default="random",
+                    help="Initialization algorithm for NMF (cnmf.py:1252); 'nndsvd' starts every restart from a "
+                         "host-side randomized SVD of the normalised counts")
     ap.add_argument("--densify", dest="densify", action="store_true", default=False)
     ap.add_argument("--worker-index", type=int, default=0)
     ap.add_argument("--skip-completed-runs", action="store_true", default=False)

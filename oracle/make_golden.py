@@ -9,7 +9,8 @@ network downloads (download_pytest_data.py:38-52) and are not available offline,
 fixtures -- outputs of the reference itself on deterministic synthetic inputs -- are what
 pins the oracle and, through it, the CUDA path.
 
-Fixture ``<tag>.npz`` (one per solver / loss, tags ``sim_mu`` / ``sim_cd`` / ``sim_kl``; ``c1_mu`` / ``c1_cd`` are
+Fixture ``<tag>.npz`` (one per solver / loss, tags ``sim_mu`` / ``sim_cd`` / ``sim_kl``; ``sim_nndsvd`` = init='nndsvd'
+with the default solver; ``c1_mu`` / ``c1_cd`` are
 BASELINE.json configs[0] -- 1 000 cells x 500 HVG, K=7, 10 restarts -- in full) holds
   counts          int16 cells x genes_all  (input given to reference prepare())
   hvg_idx         positions of the HVGs chosen by the reference inside genes_all
@@ -49,7 +50,10 @@ CASES = {
     # BASELINE.json configs[0] in full: 1 000 cells x 500 HVG, K=7, n_iter=10 (both solvers)
     "c1_mu": (1000, 640, 7, 500, [7], 10, 14, 2.0, 0.5),
     "c1_cd": (1000, 640, 7, 500, [7], 10, 14, "frobenius", 0.5),
+    # `--init nndsvd` (cnmf.py:1252) with the reference's default solver: every restart starts from a randomized SVD
+    "sim_nndsvd": (400, 260, 5, 200, [4, 5], 4, 14, "frobenius", 0.5),
 }
+INIT_OF = {"sim_nndsvd": "nndsvd"}          # prepare(init=...) of a case; default 'random' (cnmf.py:335)
 
 
 def run_case(tag, spec):
@@ -66,7 +70,7 @@ def run_case(tag, spec):
         ref.save_df_to_npz(df, counts_fn)
         obj = ref.cNMF(output_dir=tmp, name="g")
         obj.prepare(counts_fn, components=ks, n_iter=n_iter, densify=True, seed=seed,
-                    beta_loss=beta_loss, num_highvar_genes=nhvg)
+                    beta_loss=beta_loss, num_highvar_genes=nhvg, init=INIT_OF.get(tag, "random"))
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             obj.factorize(0, 1)
@@ -78,6 +82,7 @@ def run_case(tag, spec):
         run_params = yaml.load(open(obj.paths["nmf_run_parameters"]), Loader=yaml.FullLoader)
         out.update(counts=counts.astype(np.int16), hvg_idx=hvg_idx, ks=np.array(ks), n_iter=n_iter,
                    seed=seed, solver=run_params["solver"], beta_loss=str(run_params["beta_loss"]),
+                   init=str(run_params["init"]),
                    table=table[["n_components", "iter", "nmf_seed"]].values.astype(np.int64))
         for k in ks:
             merged = ref.load_df_from_npz(obj.paths["merged_spectra"] % k)

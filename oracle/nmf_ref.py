@@ -229,11 +229,17 @@ def cd_frobenius(X, W, H, tol=1e-4, max_iter=1000, l1_reg_W=0.0, l2_reg_W=0.0,
 
 
 def nmf(X, k, seed, solver="mu", tol=1e-4, max_iter=1000, dtype=np.float64,
-        alpha_W=0.0, alpha_H=0.0, l1_ratio=0.0, beta=2):
-    """One restart as cNMF.factorize issues it (cnmf.py:738-741): random init + solver."""
+        alpha_W=0.0, alpha_H=0.0, l1_ratio=0.0, beta=2, init="random"):
+    """One restart as cNMF.factorize issues it (cnmf.py:738-741): init + solver.  init != 'random' (`--init nndsvd`,
+    cnmf.py:1252): the starting factors come from scikit-learn's own `_initialize_nmf` -- the third-party code the
+    reference's call runs -- not from a restatement."""
     X = np.asarray(X, dtype=dtype)
     n, g = X.shape
-    W, H = init_random(X.mean(), n, g, k, seed, dtype=dtype)
+    if init == "random":
+        W, H = init_random(X.mean(), n, g, k, seed, dtype=dtype)
+    else:
+        from sklearn.decomposition._nmf import _initialize_nmf
+        W, H = _initialize_nmf(X, k, init=init, random_state=seed)
     l1W, l2W, l1H, l2H = reg_terms(n, g, alpha_W, alpha_H, l1_ratio)
     if solver == "mu" and beta != 2:
         return mu_beta(X, W, H, beta, tol, max_iter, l1W, l2W, l1H, l2H)

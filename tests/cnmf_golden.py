@@ -21,6 +21,7 @@ def load_golden(tag):
     z["tpm"] = tpm
     z["tpm_std"] = tpm.std(axis=0, ddof=0)
     z["solver"] = str(z["solver"])
+    z["init"] = str(z["init"]) if "init" in z else "random"
     # what was passed to the reference's prepare(beta_loss=...) and the beta the solver ran with (cnmf.py:629-631)
     bl = str(z["beta_loss"]) if "beta_loss" in z else ("2.0" if z["solver"] == "mu" else "frobenius")
     z["beta_loss_arg"] = {"2.0": 2.0, "frobenius": "frobenius"}.get(bl, bl)

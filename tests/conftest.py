@@ -16,6 +16,6 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
 
 
-@pytest.fixture(scope="session", params=["sim_mu", "sim_cd", "sim_kl", "c1_mu", "c1_cd"])
+@pytest.fixture(scope="session", params=["sim_mu", "sim_cd", "sim_kl", "sim_nndsvd", "c1_mu", "c1_cd"])
 def golden(request):
     return load_golden(request.param)

@@ -148,6 +148,8 @@ def _fixture_cases():
     for tag in ("c1_mu", "c1_cd"):          # BASELINE configs[0] in full: 1 000 x 500, K=7, 10 restarts
         for precision in ("f16x2", "tf32x3-general"):
             out.append((tag, precision))
+    for precision in ("f16x2", "tf32x3-general"):      # `--init nndsvd` (cnmf.py:1252), the reference's default solver
+        out.append(("sim_nndsvd", precision))
     return out
 
 
@@ -160,9 +162,9 @@ def test_factorize_matches_reference_fixture(eng, precision, tag):
     precision = precision.replace("-hostrng", "")
     ds = eng.dataset(g["X"], precision=precision)
     kw = dict(solver=g["solver"], tol=1e-4, max_iter=1000, alpha_W=0.0, alpha_H=0.0, l1_ratio=0.0,
-              beta_loss=2.0 if g["solver"] == "mu" else "frobenius", init="random", rng=rng)
+              beta_loss=2.0 if g["solver"] == "mu" else "frobenius", init=g["init"], rng=rng)
     table = g["table"]
-    sp, us, n_iter, err = ds.factorize(table[:, 0], table[:, 2], kw, return_usages=True)
+    sp, us, n_iter, err = ds.factorize(table[:, 0], table[:, 2], kw, return_usages=True, X_host=g["X"])
     errs = []
     for r, (k, it, seed) in enumerate(table):
         ref = g["merged_k%d" % k][it * k:(it + 1) * k]
@@ -170,7 +172,7 @@ def test_factorize_matches_reference_fixture(eng, precision, tag):
         errs.append(e)
         limit = ILL_CONDITIONED.get((tag, int(k), int(it)), TOL_SPECTRA)
         assert e < limit, (tag, precision, k, it, e, limit)
-        Wo, Ho, n_o = nmf_ref.nmf(g["X"], int(k), int(seed), solver=g["solver"])
+        Wo, Ho, n_o = nmf_ref.nmf(g["X"], int(k), int(seed), solver=g["solver"], init=g["init"])
         assert n_o == int(n_iter[r]), (tag, precision, k, it, n_o, int(n_iter[r]))
         # reported final error = ||X - W H||_F of the returned factors
         e_true = nmf_ref.frobenius_error(g["X"], us[r].astype(np.float64), sp[r].astype(np.float64))
@@ -435,7 +437,7 @@ def test_consensus_kernels_larger_random(eng):
 
 
 # ------------------------------------------------------------------------------------ end to end through the facade
-@pytest.mark.parametrize("tag", ["sim_mu", "sim_cd", "sim_kl", "c1_mu", "c1_cd"])
+@pytest.mark.parametrize("tag", ["sim_mu", "sim_cd", "sim_kl", "sim_nndsvd", "c1_mu", "c1_cd"])
 def test_pipeline_matches_reference_outputs(tmp_path, tag):
     """prepare -> factorize -> combine -> consensus through cnmf_b200.cNMF on the fixture's counts; every
     file the reference wrote is reproduced within tolerance (the reference test's own criterion is a sum of
@@ -452,7 +454,7 @@ def test_pipeline_matches_reference_outputs(tmp_path, tag):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         obj.prepare(fn, components=list(g["ks"]), n_iter=int(g["n_iter"]), seed=int(g["seed"]), densify=True,
-                    beta_loss=g["beta_loss_arg"], num_highvar_genes=len(g["hvg_idx"]))
+                    beta_loss=g["beta_loss_arg"], num_highvar_genes=len(g["hvg_idx"]), init=g["init"])
         obj.factorize()
         obj.combine()
         dt = float(g["dt"])

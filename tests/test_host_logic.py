@@ -206,8 +206,9 @@ def test_solver_selection_rule():
         make_params(dict(solver="cd", beta_loss="kullback-leibler"), 10, 10, "tf32x3")
     with pytest.raises(NotImplementedError):
         make_params(dict(solver="mu", beta_loss=0.5), 10, 10, "tf32x3")
-    with pytest.raises(NotImplementedError):
-        make_params(dict(solver="cd", init="nndsvd"), 10, 10, "tf32x3")
+    with pytest.raises(ValueError, match="Invalid init"):      # sklearn's message for an unknown init
+        make_params(dict(solver="cd", init="svd"), 10, 10, "tf32x3")
+    assert make_params(dict(solver="cd", init="nndsvd"), 10, 10, "tf32x3").solver == 1
     p = make_params(dict(solver="cd", alpha_W=0.5, alpha_H="same", l1_ratio=0.25, tol=1e-3, max_iter=7), 100, 40, "fp32")
     assert (p.solver, p.max_iter, p.tol) == (1, 7, 1e-3)
     assert p.l1_reg_W == 40 * 0.5 * 0.25 and p.l2_reg_H == 100 * 0.5 * 0.75      # sklearn _nmf.py:1249-1260
@@ -319,29 +320,32 @@ def test_prepare_sparse_semantics_and_zero_std_rule(tmp_path):
 
 
 def test_unsupported_options_are_refused_at_prepare(tmp_path):
-    """K > 32 and init != 'random' fail when the user states them (prepare / get_nmf_iter_params / the CLI), not in
-    factorize; a refit ignores `init` (no random init when update_H=False, sklearn _nmf.py:1223-1228)."""
+    """K > 32 and an init scikit-learn does not know fail when the user states them (prepare / get_nmf_iter_params /
+    the CLI), not in factorize; the NNDSVD family is accepted (cnmf.py:1252); a refit ignores `init` (no initialisation
+    when update_H=False, sklearn _nmf.py:1223-1228)."""
     from cnmf_b200.engine import check_supported, make_params
     from cnmf_b200.synth import make_counts
     fn = _counts_file(tmp_path, make_counts(120, 40, k_true=3, seed=2, libsize=300.0))
     obj = cNMF(output_dir=str(tmp_path), name="u")
     with pytest.raises(ValueError, match=r"\[1, 32\]"):
         obj.prepare(fn, components=[5, 40], n_iter=2, seed=1, densify=True)
-    with pytest.raises(NotImplementedError, match="init='random'"):
-        obj.prepare(fn, components=[5], n_iter=2, seed=1, densify=True, init="nndsvd")
+    with pytest.raises(ValueError, match="Invalid init"):
+        obj.prepare(fn, components=[5], n_iter=2, seed=1, densify=True, init="svd")
     with pytest.raises(ValueError, match=r"\[1, 32\]"):
         obj.get_nmf_iter_params(ks=[33], n_iter=2)
     with pytest.raises(NotImplementedError):
         check_supported([5], "random", 0.5)
-    with pytest.raises(NotImplementedError):
-        make_params(dict(solver="cd", init="nndsvd"), 10, 10, "tf32x3")
-    p = make_params(dict(solver="cd", init="nndsvd"), 10, 10, "tf32x3", for_refit=True)
+    with pytest.raises(ValueError, match="Invalid init"):
+        make_params(dict(solver="cd", init="svd"), 10, 10, "tf32x3")
+    for init in ("random", "nndsvd", "nndsvda", "nndsvdar", None):
+        check_supported([5], init, "frobenius")
+    p = make_params(dict(solver="cd", init="svd"), 10, 10, "tf32x3", for_refit=True)
     assert p.solver == 1
     from cnmf_b200 import pipeline
     import sys
     argv = sys.argv
     try:
-        sys.argv = ["cnmf", "prepare", "--init", "nndsvd", "-c", fn, "-k", "5"]
+        sys.argv = ["cnmf", "prepare", "--init", "svd", "-c", fn, "-k", "5"]
         with pytest.raises(SystemExit):
             pipeline.main()
     finally:
@@ -453,3 +457,44 @@ def test_symmetric_gram_plan_covers_every_entry_once():
         for row in range(KP):
             for i in range(KP):
                 assert written[row * KP + i] == written[i * KP + row]
+
+
+def test_nndsvd_starting_factors_equal_scikit_learns():
+    """cnmf_b200.nndsvd (numpy / scipy.linalg restatement of SK/decomposition/_nmf.py:309-369 and of randomized_svd,
+    SK/utils/extmath.py) against scikit-learn's own `_initialize_nmf` -- what the reference's call with init='nndsvd'
+    (cnmf.py:672, 1252) starts from: bit-identical in float64 (the dtype the reference runs in), dense and CSR, tall
+    and wide; the packed layout handed to cnmf_factorize_init holds W^T rows then H rows per restart."""
+    import scipy.sparse as sp
+    from sklearn.decomposition._nmf import _initialize_nmf
+    from cnmf_b200.engine import nndsvd_starts
+    from cnmf_b200.nndsvd import nndsvd_init, resolve_init
+    rng = np.random.RandomState(0)
+    for shape in ((400, 200), (150, 300)):
+        X = rng.poisson(1.0, size=shape).astype(np.float64) / (1.0 + rng.rand(shape[1]))
+        for init in ("nndsvd", "nndsvda", "nndsvdar"):
+            for k, seed in ((5, 14), (13, 123456)):
+                W0, H0 = _initialize_nmf(X, k, init=init, random_state=seed)
+                W1, H1 = nndsvd_init(X, k, seed, init)
+                assert np.array_equal(W0, W1) and np.array_equal(H0, H1), (shape, init, k)
+        X32 = X.astype(np.float32)
+        W0, H0 = _initialize_nmf(X32, 7, init="nndsvd", random_state=3)
+        W1, H1 = nndsvd_init(X32, 7, 3, "nndsvd")
+        assert W1.dtype == np.float32 and np.abs(W0 - W1).max() <= 4e-7 * np.abs(W0).max()
+        assert np.abs(H0 - H1).max() <= 4e-7 * np.abs(H0).max()
+    Xs = sp.csr_matrix(rng.poisson(0.3, size=(300, 120)).astype(np.float64))
+    W0, H0 = _initialize_nmf(Xs, 6, init="nndsvd", random_state=3)
+    W1, H1 = nndsvd_init(Xs, 6, 3, "nndsvd")
+    assert np.array_equal(W0, W1) and np.array_equal(H0, H1)
+    # packed starts of a mixed batch
+    X = rng.poisson(1.0, size=(120, 60)).astype(np.float64)
+    ks, seeds = [3, 5, 4], [11, 12, 13]
+    Wp, Hp = nndsvd_starts(X, ks, seeds, "nndsvd")
+    assert Wp.shape == (12, 120) and Hp.shape == (12, 60) and Wp.dtype == np.float32
+    o = 0
+    for k, seed in zip(ks, seeds):
+        W0, H0 = _initialize_nmf(X, k, init="nndsvd", random_state=seed)
+        assert np.array_equal(Wp[o:o + k], W0.T.astype(np.float32)) and np.array_equal(Hp[o:o + k], H0.astype(np.float32))
+        o += k
+    assert resolve_init(None, 5, 100, 50) == "nndsvda" and resolve_init(None, 60, 100, 50) == "random"
+    with pytest.raises(ValueError, match="can only be used"):
+        resolve_init("nndsvd", 60, 100, 50)
